@@ -1,0 +1,315 @@
+// C-ABI entry points (include/b200smpl.h): model lifetime, workspace planning, and the slab
+// pipelines that chain the kernels for forward and backward.
+#include <atomic>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace b200smpl {
+
+static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+constexpr int DEFAULT_SLAB = 1024;   // bodies per L2-resident pass (vpT slab = n_pad * S * 4 B ~ 89 MB)
+
+struct Plan {
+  int S;                 // slab pitch (multiple of 128)
+  int lbs_splits;        // dA partials written by lbs_bwd
+  int k_splits;          // split-K partials of the backward GEMM
+  size_t off_feat, off_featf, off_A, off_jposed, off_vpT;
+  size_t off_dvp_hi, off_dvp_lo, off_dA, off_dtr, off_dJposed, off_dfeat;
+  size_t total;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static Plan make_plan(const b200smpl_model* m, int batch, int mode, int slab_bodies, bool backward) {
+  const DevModel& d = m->dm;
+  Plan p{};
+  const int Bp = round_up(std::max(batch, 1), 128);
+  int S = slab_bodies > 0 ? round_up(slab_bodies, 128) : DEFAULT_SLAB;
+  p.S = std::min(S, Bp);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  const size_t S_ = (size_t)p.S;
+  p.off_feat = take(S_ * d.fl.pitch * 2);
+  p.off_featf = take(mode == B200SMPL_MODE_FP32_SIMT ? S_ * d.fl.nf_pad * 4 : 0);
+  p.off_A = take((size_t)NJ * AELEMS * S_ * 4);
+  p.off_jposed = take((size_t)NJ * 3 * S_ * 4);
+  p.off_vpT = take((size_t)d.n_pad * S_ * 4);
+  if (backward) {
+    p.lbs_splits = lbs_bwd_splits(d, p.S, m->num_sms);
+    p.k_splits = mode == B200SMPL_MODE_FP32_SIMT ? 1 : blend_bwd_umma_splits(d, mode, p.S, m->num_sms);
+    p.off_dvp_hi = take(S_ * d.n_pad * 2);
+    p.off_dvp_lo = take(mode == B200SMPL_MODE_BF16 ? 0 : S_ * d.n_pad * 2);
+    p.off_dA = take((size_t)(p.lbs_splits + 1) * NJ * AELEMS * S_ * 4);
+    p.off_dtr = take((size_t)(p.lbs_splits + 1) * 3 * S_ * 4);
+    p.off_dJposed = take((size_t)NJ * 3 * S_ * 4);
+    p.off_dfeat = take((size_t)p.k_splits * S_ * d.fl.nf_pad * 4);
+  }
+  p.total = off + 1024;   // slack for aligning the caller's base pointer
+  return p;
+}
+
+static int check_common(const b200smpl_model* m, int batch, int mode, const void* ws) {
+  if (m == nullptr) return fail(B200SMPL_ERR_INVALID, "null model handle");
+  if (m->device < 0) return fail(B200SMPL_ERR_CUDA, "host-only model handle: no CUDA device (there is no CPU fallback)");
+  if (batch < 1) return fail(B200SMPL_ERR_INVALID, "batch must be >= 1");
+  if (mode != B200SMPL_MODE_FP32 && mode != B200SMPL_MODE_BF16 && mode != B200SMPL_MODE_FP32_SIMT)
+    return fail(B200SMPL_ERR_INVALID, "unknown mode");
+  if (ws == nullptr) return fail(B200SMPL_ERR_WORKSPACE, "null workspace");
+  return 0;
+}
+
+}  // namespace b200smpl
+
+using namespace b200smpl;
+
+extern "C" {
+
+int b200smpl_abi_version(void) { return B200SMPL_ABI_VERSION; }
+const char* b200smpl_last_error(void) { return g_last_error.c_str(); }
+int64_t b200smpl_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int b200smpl_model_create(const b200smpl_model_desc* desc, int device, b200smpl_model** out) {
+  if (desc == nullptr || out == nullptr) return fail(B200SMPL_ERR_INVALID, "null argument");
+  *out = nullptr;
+  b200smpl_model* m = new b200smpl_model();
+  std::string err;
+  int rc = pack_model(desc, m->host, m->dm, err);
+  if (rc != 0) {
+    delete m;
+    return fail(rc, err);
+  }
+  m->nvj = desc->num_vertex_joints;
+  m->nreg = desc->num_regressed_joints;
+  m->device = device;
+  if (device < 0) {
+    *out = m;
+    return 0;
+  }
+  auto cleanup = [&]() {
+    for (void* p : m->allocs) cudaFree(p);
+    delete m;
+  };
+  int prev = 0;
+  cudaError_t e = cudaGetDevice(&prev);
+  if (e == cudaSuccess) e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    cleanup();
+    return fail(B200SMPL_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+    m->num_sms = prop.multiProcessorCount;
+    if (prop.major != 10) {
+      cleanup();
+      cudaSetDevice(prev);
+      return fail(B200SMPL_ERR_CUDA, "this library is built for sm_100a (B200) only; device is sm_" +
+                                         std::to_string(prop.major) + std::to_string(prop.minor));
+    }
+  }
+  auto upload = [&](const void* src, size_t bytes, const void** dst) -> bool {
+    void* p = nullptr;
+    if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return false;
+    m->allocs.push_back(p);
+    if (bytes && cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    *dst = p;
+    return true;
+  };
+  HostArrays& h = m->host;
+  DevModel& d = m->dm;
+  bool ok = true;
+#define UP(field, vec) ok = ok && upload((vec).data(), (vec).size() * sizeof((vec)[0]), (const void**)&d.field)
+  UP(Wf, h.Wf);
+  UP(Wb_hi, h.Wb_hi);
+  UP(Wb_lo, h.Wb_lo);
+  UP(W32, h.W32);
+  UP(vmeta, h.vmeta);
+  UP(vwts, h.vwts);
+  UP(Jt, h.Jt);
+  UP(Jsd, h.Jsd);
+  UP(term_ptr, h.term_ptr);
+  UP(term_joint, h.term_joint);
+  UP(term_qrow, h.term_qrow);
+  UP(term_c, h.term_c);
+#undef UP
+  cudaSetDevice(prev);
+  if (!ok) {
+    e = cudaGetLastError();
+    cleanup();
+    return fail(B200SMPL_ERR_CUDA, std::string("model upload failed: ") + cudaGetErrorString(e));
+  }
+  *out = m;
+  return 0;
+}
+
+void b200smpl_model_destroy(b200smpl_model* m) {
+  if (m == nullptr) return;
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+}
+
+int b200smpl_model_get_info(const b200smpl_model* m, b200smpl_model_info* info) {
+  if (m == nullptr || info == nullptr) return fail(B200SMPL_ERR_INVALID, "null argument");
+  info->num_verts = m->dm.V;
+  info->num_joints_out = m->dm.njout;
+  info->num_betas = m->dm.fl.nb;
+  info->num_blend_rows = m->dm.n_rows;
+  info->num_blend_rows_padded = m->dm.n_pad;
+  info->feature_pitch = m->dm.fl.pitch;
+  info->num_virtual_groups = m->dm.nq;
+  info->device = m->device;
+  return 0;
+}
+
+int b200smpl_model_debug_array(const b200smpl_model* m, const char* name, const void** data, size_t* bytes) {
+  if (m == nullptr || name == nullptr || data == nullptr || bytes == nullptr)
+    return fail(B200SMPL_ERR_INVALID, "null argument");
+  const HostArrays& h = m->host;
+  const std::string n(name);
+#define RET(key, vec)                          \
+  if (n == key) {                              \
+    *data = (vec).data();                      \
+    *bytes = (vec).size() * sizeof((vec)[0]);  \
+    return 0;                                  \
+  }
+  RET("Wf", h.Wf) RET("Wb_hi", h.Wb_hi) RET("Wb_lo", h.Wb_lo) RET("W32", h.W32) RET("vmeta", h.vmeta)
+  RET("vwts", h.vwts) RET("term_ptr", h.term_ptr) RET("term_joint", h.term_joint) RET("term_qrow", h.term_qrow)
+  RET("term_c", h.term_c) RET("Jt", h.Jt) RET("Jsd", h.Jsd)
+#undef RET
+  return fail(B200SMPL_ERR_INVALID, "unknown debug array: " + n);
+}
+
+size_t b200smpl_forward_workspace_bytes(const b200smpl_model* m, int batch, int mode, int slab_bodies) {
+  if (m == nullptr) return 0;
+  return make_plan(m, batch, mode, slab_bodies, false).total;
+}
+size_t b200smpl_backward_workspace_bytes(const b200smpl_model* m, int batch, int mode, int slab_bodies) {
+  if (m == nullptr) return 0;
+  return make_plan(m, batch, mode, slab_bodies, true).total;
+}
+
+int b200smpl_forward(const b200smpl_model* m, const b200smpl_forward_args* a, void* stream) {
+  if (a == nullptr) return fail(B200SMPL_ERR_INVALID, "null args");
+  int rc = check_common(m, a->batch, a->mode, a->workspace);
+  if (rc) return rc;
+  if (!a->betas || !a->pose || !a->joints) return fail(B200SMPL_ERR_INVALID, "betas, pose and joints are required");
+  if (a->joints2d && !a->cam) return fail(B200SMPL_ERR_INVALID, "joints2d requires cam");
+  const Plan p = make_plan(m, a->batch, a->mode, a->slab_bodies, false);
+  if (a->workspace_bytes < p.total) return fail(B200SMPL_ERR_WORKSPACE, "forward workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevModel& d = m->dm;
+  char* ws = (char*)align_up((size_t)a->workspace, 1024);
+  __nv_bfloat16* feat = (__nv_bfloat16*)(ws + p.off_feat);
+  float* featf = a->mode == B200SMPL_MODE_FP32_SIMT ? (float*)(ws + p.off_featf) : nullptr;
+  float* A_T = (float*)(ws + p.off_A);
+  float* jposed_T = (float*)(ws + p.off_jposed);
+  float* vpT = (float*)(ws + p.off_vpT);
+  const int S = p.S, B = a->batch;
+  const bool aa = a->pose_is_axis_angle != 0;
+  const int row_begin = a->vertices ? 0 : d.n_virt0;
+  for (int b0 = 0; b0 < B; b0 += S) {
+    const int nb = std::min(S, B - b0);
+    const int Sw = round_up(nb, 128);
+    if ((rc = launch_pose_fwd(d, a->betas, a->pose, aa, b0, nb, S, Sw, feat, featf, A_T, jposed_T, st))) return rc;
+    if (a->mode == B200SMPL_MODE_FP32_SIMT)
+      rc = launch_blend_fwd_simt(d, featf, S, Sw, vpT, row_begin, d.n_pad, st);
+    else
+      rc = launch_blend_fwd_umma(d, a->mode, feat, S, Sw, vpT, row_begin, d.n_pad, st);
+    if (rc) return rc;
+    if (a->vertices)
+      if ((rc = launch_lbs_fwd(d, vpT, S, A_T, b0, nb, a->transl, a->vertices, m->num_sms, st))) return rc;
+    if ((rc = launch_joints_fwd(d, vpT, S, A_T, jposed_T, b0, nb, a->transl, a->cam, a->joints, a->joints2d, st)))
+      return rc;
+  }
+  return 0;
+}
+
+int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, void* stream) {
+  if (a == nullptr) return fail(B200SMPL_ERR_INVALID, "null args");
+  int rc = check_common(m, a->batch, a->mode, a->workspace);
+  if (rc) return rc;
+  if (!a->betas || !a->pose || !a->grad_betas || !a->grad_pose)
+    return fail(B200SMPL_ERR_INVALID, "betas, pose, grad_betas and grad_pose are required");
+  if (a->grad_joints2d && (!a->cam || !a->joints))
+    return fail(B200SMPL_ERR_INVALID, "grad_joints2d requires cam and the forward joints");
+  const Plan p = make_plan(m, a->batch, a->mode, a->slab_bodies, true);
+  if (a->workspace_bytes < p.total) return fail(B200SMPL_ERR_WORKSPACE, "backward workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevModel& d = m->dm;
+  const int S = p.S, B = a->batch, nbeta = d.fl.nb;
+  const bool aa = a->pose_is_axis_angle != 0;
+  const bool have_v = a->grad_vertices != nullptr;
+  const bool have_j = a->grad_joints != nullptr || a->grad_joints2d != nullptr;
+  if (a->grad_cam && !a->grad_joints2d) B200_CUDA_TRY(cudaMemsetAsync(a->grad_cam, 0, (size_t)B * 3 * 4, st));
+  if (!have_v && !have_j) {
+    B200_CUDA_TRY(cudaMemsetAsync(a->grad_betas, 0, (size_t)B * nbeta * 4, st));
+    B200_CUDA_TRY(cudaMemsetAsync(a->grad_pose, 0, (size_t)B * (aa ? 72 : 216) * 4, st));
+    if (a->grad_transl) B200_CUDA_TRY(cudaMemsetAsync(a->grad_transl, 0, (size_t)B * 3 * 4, st));
+    return 0;
+  }
+  char* ws = (char*)align_up((size_t)a->workspace, 1024);
+  __nv_bfloat16* feat = (__nv_bfloat16*)(ws + p.off_feat);
+  float* featf = a->mode == B200SMPL_MODE_FP32_SIMT ? (float*)(ws + p.off_featf) : nullptr;
+  float* A_T = (float*)(ws + p.off_A);
+  float* jposed_T = (float*)(ws + p.off_jposed);
+  float* vpT = (float*)(ws + p.off_vpT);
+  __nv_bfloat16* dvp_hi = (__nv_bfloat16*)(ws + p.off_dvp_hi);
+  __nv_bfloat16* dvp_lo = a->mode == B200SMPL_MODE_BF16 ? nullptr : (__nv_bfloat16*)(ws + p.off_dvp_lo);
+  float* dA_part = (float*)(ws + p.off_dA);
+  float* dtr_part = (float*)(ws + p.off_dtr);
+  float* dJposed_T = (float*)(ws + p.off_dJposed);
+  float* dfeat_part = (float*)(ws + p.off_dfeat);
+  // partial 0 belongs to joints_bwd (when present), the skinning partials follow
+  const int jpart = have_j ? 1 : 0;
+  const int n_parts = jpart + (have_v ? p.lbs_splits : 0);
+  const int row_begin = have_v ? 0 : d.n_virt0;
+  const int row_end = have_j ? d.n_rows : d.n_virt0;
+  int k_splits = 1;
+  if (a->mode != B200SMPL_MODE_FP32_SIMT) {
+    const int slabs = (row_end + 63) / 64 - row_begin / 64;
+    k_splits = std::max(1, std::min(p.k_splits, slabs / 8));
+  }
+  for (int b0 = 0; b0 < B; b0 += S) {
+    const int nb = std::min(S, B - b0);
+    const int Sw = round_up(nb, 128);
+    if ((rc = launch_pose_fwd(d, a->betas, a->pose, aa, b0, nb, S, Sw, feat, featf, A_T, jposed_T, st))) return rc;
+    if (a->mode == B200SMPL_MODE_FP32_SIMT)
+      rc = launch_blend_fwd_simt(d, featf, S, Sw, vpT, row_begin, d.n_pad, st);
+    else
+      rc = launch_blend_fwd_umma(d, a->mode, feat, S, Sw, vpT, row_begin, d.n_pad, st);
+    if (rc) return rc;
+    if (have_v)
+      if ((rc = launch_lbs_bwd(d, vpT, S, Sw, A_T, b0, nb, a->grad_vertices, dvp_hi, dvp_lo,
+                               dA_part + (size_t)jpart * NJ * AELEMS * S, dtr_part + (size_t)jpart * 3 * S,
+                               p.lbs_splits, st)))
+        return rc;
+    if (have_j)
+      if ((rc = launch_joints_bwd(d, vpT, S, Sw, A_T, b0, nb, a->cam, a->joints, a->grad_joints, a->grad_joints2d,
+                                  dvp_hi, dvp_lo, dA_part, dtr_part, dJposed_T, a->grad_cam, st)))
+        return rc;
+    if (a->mode == B200SMPL_MODE_FP32_SIMT)
+      rc = launch_blend_bwd_simt(d, dvp_hi, dvp_lo, Sw, dfeat_part, row_begin, row_end, st);
+    else
+      rc = launch_blend_bwd_umma(d, a->mode, dvp_hi, dvp_lo, S, Sw, dfeat_part, k_splits, row_begin, row_end, st);
+    if (rc) return rc;
+    if ((rc = launch_pose_bwd(d, a->betas, a->pose, aa, b0, nb, S, dA_part, n_parts, dtr_part, dfeat_part, k_splits,
+                              have_j ? dJposed_T : nullptr, a->grad_betas, a->grad_pose, a->grad_transl, st)))
+      return rc;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,352 @@
+// Blend-shape contractions on the 5th-gen tensor cores (tcgen05 + TMEM, operands staged by TMA).
+//
+//   forward : vpT[n][b]   = sum_k Wf[n][k]   * feat[b][k]      (SURVEY.md section 8 rows a4 + a7:
+//             shape blend + pose-corrective blend + template, all folded into one K axis)
+//   backward: dfeat[b][f] = sum_n dvp[b][n]  * Wb[f][n]        (data gradient, split-K over n)
+//
+// Both are the same kernel: D[m][n] (fp32, row-major) = sum_seg sum_k A_seg[m][k] * B_seg[n][k] with
+// bf16 K-major operands.  fp32 accuracy comes from the bf16x3 error-compensated split laid out
+// along K (see FeatLayout in common.cuh), so the tensor pipe only ever sees kind::f16 MMAs with
+// fp32 accumulation in TMEM.
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2-5 epilogue
+// (tcgen05.ld -> registers -> 16-byte global stores).  One 128 x BN output tile per CTA; smem ring
+// of STAGES x (128x64 + BNx64) bf16 tiles in the 128-byte swizzle; two CTAs can share an SM in
+// the forward configuration so one CTA's epilogue overlaps the other's main loop.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace b200smpl {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // bf16 elements = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int MAX_SEG = 3;
+
+struct GemmMaps {
+  CUtensorMap a[MAX_SEG];
+  CUtensorMap b[MAX_SEG];
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) __trap();   // a lost arrival must fail loudly, not hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) = 1 (unused for swizzled K-major) | SBO>>4 [32,46) = 1024 B
+// between 8-row groups | version [46,48) = 1 | layout [61,64) = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+// cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b format BF16 [7,10)=[10,13)=1, K-major both,
+// n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// grid: (m tiles, n tiles, k splits)
+template <int BN, int STAGES, int MIN_CTAS>
+__global__ void __launch_bounds__(GEMM_THREADS, MIN_CTAS)
+umma_gemm_kernel(const __grid_constant__ GemmMaps maps, int nseg, int slab_begin, int slab_end, int slabs_per_split,
+                 int a_row0, int b_row0, float* __restrict__ D, int ldd, long long split_stride) {
+  using SM = GemmSmem<BN, STAGES>;
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int s_begin = slab_begin + blockIdx.z * slabs_per_split;
+  const int s_end = min(slab_end, s_begin + slabs_per_split);
+  const int slabs = max(0, s_end - s_begin);
+  const int total_iters = slabs * nseg;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < nseg; ++s) {
+      prefetch_tmap(&maps.a[s]);
+      prefetch_tmap(&maps.b[s]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < total_iters; ++it) {
+        const int seg = it / slabs, slab = s_begin + (it - seg * slabs);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        unsigned char* sa = smem + stage * SM::STAGE_BYTES;
+        unsigned char* sb = sa + SM::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+        tma_load_2d(sa, &maps.a[seg], &full_bar[stage], slab * BK, a_row0 + m0);
+        tma_load_2d(sb, &maps.b[seg], &full_bar[stage], slab * BK, b_row0 + n0);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < total_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
+        const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + SM::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advance 32 bytes (16 bf16) along K inside the swizzle row: +2 in 16-byte units
+          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
+        if (it == total_iters - 1) umma_commit(tmem_full_bar);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    float* drow = D + (long long)blockIdx.z * split_stride + (long long)row * ldd + n0;
+    if (total_iters > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(drow + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 4) *reinterpret_cast<uint4*>(drow + c0) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 matrix [rows][pitch] (K contiguous), visible extent k_extent x rows, box 64 x box_rows, 128B swizzle
+static int make_map(CUtensorMap* map, const void* base, int k_extent, int rows, int pitch_elems, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return fail(B200SMPL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200SMPL_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return 0;
+}
+
+constexpr int FWD_BN = 128, FWD_STAGES = 3;
+constexpr int BWD_BN_MAX = 256, BWD_STAGES = 4;
+
+int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat, int S, int Sw, float* vpT,
+                          int row_begin, int row_end, cudaStream_t st) {
+  const int kuse = (mode == B200SMPL_MODE_BF16) ? m.fl.k_bf16 : m.fl.k_fp32;
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc;
+  if ((rc = make_map(&maps.a[0], m.Wf, kuse, m.n_pad, m.fl.pitch, BM))) return rc;
+  if ((rc = make_map(&maps.b[0], feat, kuse, S, m.fl.pitch, FWD_BN))) return rc;
+  const int slabs = (kuse + BK - 1) / BK;
+  using SM = GemmSmem<FWD_BN, FWD_STAGES>;
+  auto kern = umma_gemm_kernel<FWD_BN, FWD_STAGES, 2>;
+  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+  dim3 grid((row_end - row_begin) / BM, Sw / FWD_BN, 1);
+  kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(maps, 1, 0, slabs, slabs, row_begin, 0,
+                                              vpT + (size_t)row_begin * S, S, 0LL);
+  B200_LAUNCH_CHECK("blend_fwd_umma");
+  return 0;
+}
+
+// number of split-K partials the backward GEMM writes for slab width S
+int blend_bwd_umma_splits(const DevModel& m, int mode, int S, int num_sms) {
+  (void)mode;
+  const int mtiles = (S + BM - 1) / BM;
+  const int slabs = (m.n_rows + BK - 1) / BK;
+  int want = (num_sms + mtiles - 1) / mtiles;
+  want = std::max(1, std::min(want, slabs / 8));
+  return want;
+}
+
+template <int BN>
+static int launch_bwd_bn(const GemmMaps& maps, int nseg, int slab_begin, int slab_end, int nsplit, int Sw,
+                         float* dfeat_part, int nf_pad, long long split_stride, cudaStream_t st) {
+  using SM = GemmSmem<BN, BWD_STAGES>;
+  auto kern = umma_gemm_kernel<BN, BWD_STAGES, 1>;
+  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+  const int slabs = slab_end - slab_begin;
+  const int sps = (slabs + nsplit - 1) / nsplit;
+  dim3 grid(Sw / BM, 1, nsplit);
+  kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(maps, nseg, slab_begin, slab_end, sps, 0, 0, dfeat_part, nf_pad,
+                                              split_stride);
+  B200_LAUNCH_CHECK("blend_bwd_umma");
+  return 0;
+}
+
+// dfeat_part[nsplit][S][nf_pad]; rows [0, Sw) of every split are written
+int launch_blend_bwd_umma(const DevModel& m, int mode, const __nv_bfloat16* dvp_hi, const __nv_bfloat16* dvp_lo,
+                          int S, int Sw, float* dfeat_part, int nsplit, int row_begin, int row_end,
+                          cudaStream_t st) {
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const int nf_pad = m.fl.nf_pad;
+  int rc;
+  const bool split3 = (mode != B200SMPL_MODE_BF16) && dvp_lo != nullptr;
+  const int nseg = split3 ? 3 : 1;
+  // K extent = row_end: columns beyond it are never read (TMA zero-fills out-of-bounds)
+  if ((rc = make_map(&maps.a[0], dvp_hi, row_end, Sw, m.n_pad, BM))) return rc;
+  if ((rc = make_map(&maps.b[0], m.Wb_hi, row_end, nf_pad, m.n_pad, nf_pad))) return rc;
+  if (split3) {
+    if ((rc = make_map(&maps.a[1], dvp_lo, row_end, Sw, m.n_pad, BM))) return rc;
+    if ((rc = make_map(&maps.b[1], m.Wb_hi, row_end, nf_pad, m.n_pad, nf_pad))) return rc;
+    if ((rc = make_map(&maps.a[2], dvp_hi, row_end, Sw, m.n_pad, BM))) return rc;
+    if ((rc = make_map(&maps.b[2], m.Wb_lo, row_end, nf_pad, m.n_pad, nf_pad))) return rc;
+  }
+  const int slab_begin = row_begin / BK, slab_end = (row_end + BK - 1) / BK;
+  const long long split_stride = (long long)S * nf_pad;
+  switch (nf_pad) {
+    case 224: return launch_bwd_bn<224>(maps, nseg, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
+    case 208: return launch_bwd_bn<208>(maps, nseg, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
+    case 240: return launch_bwd_bn<240>(maps, nseg, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
+    default: return fail(B200SMPL_ERR_INVALID, "unsupported num_betas for the tensor-core backward (nf_pad=" + std::to_string(nf_pad) + ")");
+  }
+}
+
+}  // namespace b200smpl

@@ -1,0 +1,185 @@
+// Shared definitions of the B200-native SMPL kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200smpl.h"
+
+namespace b200smpl {
+
+constexpr int NJ = 24;             // SMPL chain joints (compile-time)
+constexpr int NPOSE = 9 * (NJ - 1);  // 207 pose-corrective features
+constexpr int AELEMS = 12;         // per-joint skinning transform, row-major 3x4 [R | t]
+constexpr int TILE_V = 32;         // vertices per skinning tile (= output flush granularity)
+constexpr int MAX_CHILD = 4;
+constexpr int MAX_BETAS = 16;
+
+// vmeta bit layout (one u32 per vertex in processing order)
+//  [0:5) j0  [5:10) j1  [10:15) j2  [15:20) j3   slot joint ids
+//  [20:24) reload mask (slot s must be (re)loaded before this vertex)
+//  [24:29) position of the vertex inside its tile in ORIGINAL order (ol)
+//  [29]    valid (vertex index < V)
+constexpr uint32_t VMETA_VALID = 1u << 29;
+
+struct ChainTables {
+  int8_t parent[NJ];
+  int8_t depth[NJ];
+  int8_t nchild[NJ];
+  int8_t child[NJ][MAX_CHILD];
+  int32_t maxdepth;
+};
+
+// Feature (K) layout of the packed blend operand, in elements.  One body's feature row is
+//   [1,1,1 | b_hi b_lo b_hi | pf_hi | (pad to k_bf16) | pf_lo | pf_hi | pad]
+// and the matching model rows hold
+//   [t_hi t_lo t_lo2 | S_hi S_hi S_lo | P_hi | 0 | P_hi | P_lo | 0]
+// so the first k_bf16 columns alone are the "bf16 mode" product (template + shape terms stay
+// error-compensated, the pose-corrective term is single bf16) and all k_fp32 columns give the
+// bf16x3 split product (~2^-16 relative, fp32 accumulate).
+struct FeatLayout {
+  int nb;       // betas
+  int off_s0, off_s1, off_s2;   // 3, 3+nb, 3+2nb
+  int off_p0;   // 3+3nb
+  int k_bf16;   // roundup16(off_p0 + 207)
+  int off_p1;   // k_bf16
+  int off_p2;   // k_bf16 + 207
+  int k_fp32;   // roundup16(off_p2 + 207)
+  int pitch;    // = k_fp32 (elements; *2 bytes is a multiple of 16)
+  int nf;       // nb + 207 gradient features
+  int nf_pad;   // roundup16(nf)
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+inline FeatLayout make_feat_layout(int nb) {
+  FeatLayout L;
+  L.nb = nb;
+  L.off_s0 = 3;
+  L.off_s1 = 3 + nb;
+  L.off_s2 = 3 + 2 * nb;
+  L.off_p0 = 3 + 3 * nb;
+  L.k_bf16 = round_up(L.off_p0 + NPOSE, 16);
+  L.off_p1 = L.k_bf16;
+  L.off_p2 = L.k_bf16 + NPOSE;
+  L.k_fp32 = round_up(L.off_p2 + NPOSE, 16);
+  L.pitch = L.k_fp32;
+  L.nf = nb + NPOSE;
+  L.nf_pad = round_up(L.nf, 16);
+  return L;
+}
+
+// Device-side view of a packed model (all pointers are device pointers).
+struct DevModel {
+  int V;          // vertices
+  int ntiles;     // ceil(V / 32) rounded up to a multiple of 4
+  int n_real;     // 3V
+  int nq;         // virtual q-groups (3 rows each) appended after the real rows
+  int n_rows;     // n_virt0 + 3nq
+  int n_virt0;    // first virtual row = ntiles*96 (multiple of 128)
+  int n_pad;      // n_rows rounded up to 128
+  int njout;      // 24 + nvj + nreg
+  int nterms;
+  FeatLayout fl;
+  ChainTables chain;
+  const __nv_bfloat16* Wf;     // [n_pad][fl.pitch]         forward operand, K-major
+  const __nv_bfloat16* Wb_hi;  // [fl.nf_pad][n_pad]        backward operand (K = n), hi part
+  const __nv_bfloat16* Wb_lo;  // [fl.nf_pad][n_pad]        lo part
+  const float* W32;            // [1 + nf][n_pad]           fp32 rows: template, shapedirs, posedirs
+  const uint32_t* vmeta;       // [ntiles*32]
+  const float4* vwts;          // [ntiles*32]
+  const float* Jt;             // [24][3]   J_regressor . v_template
+  const float* Jsd;            // [24][3][nb]  J_regressor . shapedirs
+  const int32_t* term_ptr;     // [njout-24+1]
+  const uint8_t* term_joint;   // [nterms] skinning joint of the term
+  const int32_t* term_qrow;    // [nterms] first of the 3 blend rows holding q
+  const float* term_c;         // [nterms]
+};
+
+struct HostArrays {
+  std::vector<__nv_bfloat16> Wf, Wb_hi, Wb_lo;
+  std::vector<float> W32, Jt, Jsd, term_c;
+  std::vector<uint32_t> vmeta;
+  std::vector<float> vwts;     // 4 per vertex
+  std::vector<int32_t> term_ptr, term_qrow;
+  std::vector<uint8_t> term_joint;
+};
+
+}  // namespace b200smpl
+
+struct b200smpl_model {
+  int device = -1;
+  b200smpl::DevModel dm{};       // device pointers (null for host-only)
+  b200smpl::HostArrays host;     // kept for host-only handles / debug queries
+  std::vector<void*> allocs;
+  int nvj = 0, nreg = 0;
+  int num_sms = 148;
+};
+
+namespace b200smpl {
+
+// error plumbing ------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+void count_launch(int n = 1);
+
+#define B200_CUDA_TRY(expr)                                                                       \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return ::b200smpl::fail(B200SMPL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define B200_LAUNCH_CHECK(name)                                                                   \
+  do {                                                                                            \
+    cudaError_t _e = cudaGetLastError();                                                          \
+    if (_e != cudaSuccess)                                                                        \
+      return ::b200smpl::fail(B200SMPL_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(_e)); \
+    ::b200smpl::count_launch();                                                                   \
+  } while (0)
+
+// host pack (pack.cpp)
+int pack_model(const b200smpl_model_desc* d, HostArrays& h, DevModel& dm, std::string& err);
+
+// kernel launchers ----------------------------------------------------------------------------
+// The batch is processed in slabs of at most S bodies.  Every scratch array is slab-local: its
+// body index is the slab column (body - b0) and its body pitch is S.  nb = live bodies of the
+// slab, Sw = nb rounded up to 128 (columns in [nb, Sw) are kept zero / finite).
+int launch_pose_fwd(const DevModel& m, const float* betas, const float* pose, bool axis_angle, int b0, int nb, int S,
+                    int Sw, __nv_bfloat16* feat, float* featf, float* A_T, float* jposed_T, cudaStream_t st);
+int launch_pose_bwd(const DevModel& m, const float* betas, const float* pose, bool axis_angle, int b0, int nb, int S,
+                    const float* dA_part, int n_dA_parts, const float* dtr_part, const float* dfeat_part,
+                    int n_dfeat_parts, const float* dJposed_T, float* grad_betas, float* grad_pose,
+                    float* grad_transl, cudaStream_t st);
+
+int launch_blend_fwd_simt(const DevModel& m, const float* featf, int S, int Sw, float* vpT, int row_begin,
+                          int row_end, cudaStream_t st);
+int launch_blend_bwd_simt(const DevModel& m, const __nv_bfloat16* dvp_hi, const __nv_bfloat16* dvp_lo, int Sw,
+                          float* dfeat, int row_begin, int row_end, cudaStream_t st);
+int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat, int S, int Sw, float* vpT,
+                          int row_begin, int row_end, cudaStream_t st);
+int launch_blend_bwd_umma(const DevModel& m, int mode, const __nv_bfloat16* dvp_hi, const __nv_bfloat16* dvp_lo,
+                          int S, int Sw, float* dfeat_part, int nsplit, int row_begin, int row_end,
+                          cudaStream_t st);
+int blend_bwd_umma_splits(const DevModel& m, int mode, int S, int num_sms);
+
+int launch_lbs_fwd(const DevModel& m, const float* vpT, int S, const float* A_T, int b0, int nb,
+                   const float* transl, float* verts, int num_sms, cudaStream_t st);
+int lbs_bwd_splits(const DevModel& m, int S, int num_sms);
+int launch_lbs_bwd(const DevModel& m, const float* vpT, int S, int Sw, const float* A_T, int b0, int nb,
+                   const float* grad_verts, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_part,
+                   float* dtr_part, int nsplit, cudaStream_t st);
+
+int launch_joints_fwd(const DevModel& m, const float* vpT, int S, const float* A_T, const float* jposed_T, int b0,
+                      int nb, const float* transl, const float* cam, float* joints, float* joints2d,
+                      cudaStream_t st);
+int launch_joints_bwd(const DevModel& m, const float* vpT, int S, int Sw, const float* A_T, int b0, int nb,
+                      const float* cam, const float* joints, const float* grad_joints,
+                      const float* grad_joints2d, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_part,
+                      float* dtr_part, float* dJposed_T, float* grad_cam, cudaStream_t st);
+
+}  // namespace b200smpl

@@ -1,0 +1,149 @@
+"""The small in-tree helpers of the SMPL path as autograd Functions over the C-ABI kernels
+(SURVEY.md section 8 rows a13-a18).  CUDA float32 tensors only -- no CPU path."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def _stream(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _req(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("{} must be a CUDA tensor: the b200 SMPL ops have no CPU implementation".format(name))
+    if t.dtype != torch.float32:
+        raise TypeError("{} must be float32".format(name))
+    return t.contiguous()
+
+
+class _Rot6d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _req(x, "x").reshape(-1, 6)
+        n = x.shape[0]
+        out = torch.empty((n, 3, 3), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().b200smpl_rot6d_to_rotmat(x.data_ptr(), out.data_ptr(), n, _stream(x)), "rot6d")
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = g.contiguous()
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().b200smpl_rot6d_to_rotmat_backward(x.data_ptr(), g.data_ptr(), gx.data_ptr(),
+                                                                     x.shape[0], _stream(x)), "rot6d_bwd")
+        return gx
+
+
+def rot6d_to_rotmat(x: torch.Tensor) -> torch.Tensor:
+    """utils/rigid_transform_utils.py:27-41: (B,6k) -> (B*k,3,3); gradient flows to the input's shape."""
+    shape = x.shape
+    return _Rot6d.apply(x.reshape(-1, 6)).reshape(-1, 3, 3) if x.numel() else x.new_zeros((0, 3, 3)) \
+        if shape else x
+
+
+class _Ortho(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pts, cam, pixel_wh):
+        pts, cam = _req(pts, "points3D"), _req(cam, "cam_params")
+        B, N = pts.shape[0], pts.shape[1]
+        out = torch.empty((B, N, 2), dtype=torch.float32, device=pts.device)
+        with torch.cuda.device(pts.device):
+            _lib.check(_lib.load().b200smpl_orthographic_project(pts.data_ptr(), cam.data_ptr(), out.data_ptr(), B, N,
+                                                                 float(pixel_wh), _stream(pts)), "ortho")
+        ctx.save_for_backward(pts, cam)
+        ctx.pixel_wh = float(pixel_wh)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pts, cam = ctx.saved_tensors
+        g = g.contiguous()
+        B, N = pts.shape[0], pts.shape[1]
+        gp = torch.empty_like(pts) if ctx.needs_input_grad[0] else None
+        gc = torch.empty_like(cam) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(pts.device):
+            _lib.check(_lib.load().b200smpl_orthographic_project_backward(
+                pts.data_ptr(), cam.data_ptr(), g.data_ptr(), None if gp is None else gp.data_ptr(),
+                None if gc is None else gc.data_ptr(), B, N, ctx.pixel_wh, _stream(pts)), "ortho_bwd")
+        return gp, gc, None
+
+
+def orthographic_project(points3D: torch.Tensor, cam_params: torch.Tensor, pixel_wh: float = 0.0) -> torch.Tensor:
+    """utils/cam_utils.py:5-26; pixel_wh>0 fuses utils/joints2d_utils.py:5-10 behind it."""
+    return _Ortho.apply(points3D, cam_params, pixel_wh)
+
+
+class _Persp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pts, rot, trans, focal, wh):
+        pts, rot, trans = _req(pts, "points"), _req(rot, "rotation"), _req(trans, "translation")
+        B, N = pts.shape[0], pts.shape[1]
+        out = torch.empty((B, N, 2), dtype=torch.float32, device=pts.device)
+        with torch.cuda.device(pts.device):
+            _lib.check(_lib.load().b200smpl_perspective_project(pts.data_ptr(), rot.data_ptr(), trans.data_ptr(),
+                                                                out.data_ptr(), B, N, float(focal), float(wh),
+                                                                _stream(pts)), "persp")
+        ctx.save_for_backward(pts, rot, trans)
+        ctx.focal, ctx.wh = float(focal), float(wh)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pts, rot, trans = ctx.saved_tensors
+        g = g.contiguous()
+        B, N = pts.shape[0], pts.shape[1]
+        gp, gr, gt = torch.empty_like(pts), torch.empty_like(rot), torch.empty_like(trans)
+        with torch.cuda.device(pts.device):
+            _lib.check(_lib.load().b200smpl_perspective_project_backward(
+                pts.data_ptr(), rot.data_ptr(), trans.data_ptr(), g.data_ptr(), gp.data_ptr(), gr.data_ptr(),
+                gt.data_ptr(), B, N, ctx.focal, ctx.wh, _stream(pts)), "persp_bwd")
+        return gp, gr, gt, None, None
+
+
+def perspective_project(points, rotation, translation, focal_length: float, img_wh: float) -> torch.Tensor:
+    """utils/cam_utils.py:54-85 with the (focal_length, img_wh) intrinsics form used at
+    player_recon.py:685-688."""
+    return _Persp.apply(points, rotation, translation, focal_length, img_wh)
+
+
+class _J2dLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, joints, cam, joint_map, label, vis, proj_wh, norm_wh, log_var):
+        joints, cam, label = _req(joints, "joints"), _req(cam, "cam"), _req(label, "label")
+        B, NJ = joints.shape[0], joints.shape[1]
+        nmap = joint_map.numel()
+        loss = torch.zeros(2, dtype=torch.float32, device=joints.device)
+        gj = torch.empty_like(joints)
+        gc = torch.empty_like(cam)
+        visu8 = None if vis is None else vis.to(torch.uint8).contiguous()
+        with torch.cuda.device(joints.device):
+            _lib.check(_lib.load().b200smpl_joints2d_loss(
+                joints.data_ptr(), cam.data_ptr(), joint_map.data_ptr(), label.data_ptr(),
+                None if visu8 is None else visu8.data_ptr(), B, NJ, nmap, float(proj_wh), float(norm_wh),
+                float(log_var), loss.data_ptr(), gj.data_ptr(), gc.data_ptr(), _stream(joints)), "joints2d_loss")
+        ctx.save_for_backward(gj, gc)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        gj, gc = ctx.saved_tensors
+        return gj * g, gc * g, None, None, None, None, None, None
+
+
+def joints2d_loss(joints: torch.Tensor, cam: torch.Tensor, joint_map: torch.Tensor, label_pixels: torch.Tensor,
+                  vis: Optional[torch.Tensor] = None, proj_wh: float = 512.0, norm_wh: float = 256.0,
+                  log_var: float = 0.0) -> torch.Tensor:
+    """Fused reprojection loss: orthographic_project_torch(joints, cam)[:, joint_map] ->
+    undo_keypoint_normalisation(., proj_wh) -> joints2D term of the multi-task loss
+    (losses/multi_task_loss.py:97-113) with a fixed log-variance.  joint_map: int32 CUDA tensor."""
+    return _J2dLoss.apply(joints, cam, joint_map, label_pixels, vis, proj_wh, norm_wh, log_var)
