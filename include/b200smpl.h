@@ -195,6 +195,13 @@ B200SMPL_API int b200smpl_joints2d_loss(const float* joints, const float* cam, c
 B200SMPL_API const char* b200smpl_last_error(void);
 B200SMPL_API int b200smpl_abi_version(void);
 
+/* Per-kernel device timing for bench.py's roofline: while enabled (enable != 0) every kernel launch
+ * is bracketed by CUDA events on its own stream.  b200smpl_timing_report synchronises those events and
+ * writes one line per kernel name, "name launches total_ms\n", into buf (NUL-terminated, truncated to
+ * cap), clears the records and returns the number of bytes needed. */
+B200SMPL_API void b200smpl_timing_enable(int enable);
+B200SMPL_API size_t b200smpl_timing_report(char* buf, size_t cap);
+
 /* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
 B200SMPL_API int64_t b200smpl_launch_count(void);
 

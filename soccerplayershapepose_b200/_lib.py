@@ -81,6 +81,8 @@ SYMBOLS = {
     "b200smpl_last_error": (c_char_p, []),
     "b200smpl_abi_version": (c_int, []),
     "b200smpl_launch_count": (c_int64, []),
+    "b200smpl_timing_enable": (None, [c_int]),
+    "b200smpl_timing_report": (c_size_t, [c_char_p, c_size_t]),
 }
 
 _lib = None

@@ -2,6 +2,8 @@
 // pipelines that chain the kernels for forward and backward.
 #include <atomic>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -16,6 +18,27 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- per-launch timing ------------------------------------------------------------------------
+static std::atomic<int> g_timing{0};
+static std::mutex g_timing_mu;
+struct TimingRec { const char* name; cudaEvent_t a, b; };
+static std::vector<TimingRec> g_timing_recs;
+
+LaunchTimer::LaunchTimer(const char* name, cudaStream_t st) : name_(name), st_(st) {
+  if (g_timing.load(std::memory_order_relaxed)) {
+    if (cudaEventCreate(&start_) == cudaSuccess) cudaEventRecord(start_, st_);
+    else start_ = nullptr;
+  }
+}
+LaunchTimer::~LaunchTimer() {
+  if (start_ == nullptr) return;
+  cudaEvent_t stop = nullptr;
+  if (cudaEventCreate(&stop) != cudaSuccess) return;
+  cudaEventRecord(stop, st_);
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  g_timing_recs.push_back({name_, start_, stop});
+}
 
 constexpr int DEFAULT_SLAB = 1024;   // bodies per L2-resident pass (vpT slab = n_pad * S * 4 B ~ 89 MB)
 
@@ -81,6 +104,35 @@ extern "C" {
 int b200smpl_abi_version(void) { return B200SMPL_ABI_VERSION; }
 const char* b200smpl_last_error(void) { return g_last_error.c_str(); }
 int64_t b200smpl_launch_count(void) { return (int64_t)g_launches.load(); }
+
+void b200smpl_timing_enable(int enable) { g_timing.store(enable ? 1 : 0); }
+
+size_t b200smpl_timing_report(char* buf, size_t cap) {
+  std::vector<TimingRec> recs;
+  {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    recs.swap(g_timing_recs);
+  }
+  std::map<std::string, std::pair<long long, double>> agg;
+  for (auto& r : recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& e = agg[r.name];
+      e.first += 1;
+      e.second += ms;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  std::string out;
+  for (auto& kv : agg) out += kv.first + " " + std::to_string(kv.second.first) + " " + std::to_string(kv.second.second) + "\n";
+  if (buf != nullptr && cap > 0) {
+    const size_t n = std::min(cap - 1, out.size());
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return out.size() + 1;
+}
 
 int b200smpl_model_create(const b200smpl_model_desc* desc, int device, b200smpl_model** out) {
   if (desc == nullptr || out == nullptr) return fail(B200SMPL_ERR_INVALID, "null argument");

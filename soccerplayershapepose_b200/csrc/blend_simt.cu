@@ -44,6 +44,7 @@ blend_fwd_simt_kernel(const float* __restrict__ W32, int n_pad, int nf, const fl
 int launch_blend_fwd_simt(const DevModel& m, const float* featf, int S, int Sw, float* vpT, int row_begin,
                           int row_end, cudaStream_t st) {
   dim3 grid((row_end - row_begin) / 32, Sw / 32);
+  LaunchTimer _timer_46("blend_fwd_simt", st);
   blend_fwd_simt_kernel<<<grid, dim3(32, 8), 0, st>>>(m.W32, m.n_pad, m.fl.nf, featf, m.fl.nf_pad, S, vpT,
                                                       row_begin);
   B200_LAUNCH_CHECK("blend_fwd_simt");
@@ -86,6 +87,7 @@ blend_bwd_simt_kernel(const float* __restrict__ W32, int n_pad, int nf, const __
 int launch_blend_bwd_simt(const DevModel& m, const __nv_bfloat16* dvp_hi, const __nv_bfloat16* dvp_lo, int Sw,
                           float* dfeat, int row_begin, int row_end, cudaStream_t st) {
   dim3 grid(m.fl.nf_pad / 8, Sw / 32);
+  LaunchTimer _timer_88("blend_bwd_simt", st);
   blend_bwd_simt_kernel<<<grid, dim3(32, 8), 0, st>>>(m.W32, m.n_pad, m.fl.nf, dvp_hi, dvp_lo, dfeat,
                                                       m.fl.nf_pad, row_begin, row_end);
   B200_LAUNCH_CHECK("blend_bwd_simt");

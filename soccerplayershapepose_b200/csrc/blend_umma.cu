@@ -163,7 +163,10 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, int nseg, int slab_begin
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -289,6 +292,7 @@ int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat
   auto kern = umma_gemm_kernel<FWD_BN, FWD_STAGES, 2>;
   B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
   dim3 grid((row_end - row_begin) / BM, Sw / FWD_BN, 1);
+  LaunchTimer _timer_291("blend_fwd_umma", st);
   kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(maps, 1, 0, slabs, slabs, row_begin, 0,
                                               vpT + (size_t)row_begin * S, S, 0LL);
   B200_LAUNCH_CHECK("blend_fwd_umma");
@@ -314,6 +318,7 @@ static int launch_bwd_bn(const GemmMaps& maps, int nseg, int slab_begin, int sla
   const int slabs = slab_end - slab_begin;
   const int sps = (slabs + nsplit - 1) / nsplit;
   dim3 grid(Sw / BM, 1, nsplit);
+  LaunchTimer _timer_316("blend_bwd_umma", st);
   kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(maps, nseg, slab_begin, slab_end, sps, 0, 0, dfeat_part, nf_pad,
                                               split_stride);
   B200_LAUNCH_CHECK("blend_bwd_umma");

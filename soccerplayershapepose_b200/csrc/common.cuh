@@ -127,6 +127,15 @@ void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 void count_launch(int n = 1);
 
+// optional per-launch device timing (bench.py roofline); see b200smpl_timing_enable
+struct LaunchTimer {
+  LaunchTimer(const char* name, cudaStream_t st);
+  ~LaunchTimer();
+  const char* name_;
+  cudaStream_t st_;
+  cudaEvent_t start_ = nullptr;
+};
+
 #define B200_CUDA_TRY(expr)                                                                       \
   do {                                                                                            \
     cudaError_t _e = (expr);                                                                      \

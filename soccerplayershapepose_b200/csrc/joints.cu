@@ -209,6 +209,7 @@ int launch_joints_fwd(const DevModel& m, const float* vpT, int S, const float* A
   const int pitch = (m.njout * 3) | 1;
   const size_t smem = (size_t)(32 * pitch + 96) * sizeof(float);
   B200_CUDA_TRY(cudaFuncSetAttribute(joints_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchTimer _timer_211("joints_fwd", st);
   joints_fwd_kernel<<<(nb + 31) / 32, JT_THREADS, smem, st>>>(m, vpT, S, A_T, jposed_T, b0, nb, transl, cam, joints,
                                                               joints2d);
   B200_LAUNCH_CHECK("joints_fwd");
@@ -223,6 +224,7 @@ int launch_joints_bwd(const DevModel& m, const float* vpT, int S, int Sw, const 
   const int pitch = (m.njout * 3) | 1;
   const size_t smem = (size_t)(32 * pitch + NJ * AELEMS * 32 + 96 * 3) * sizeof(float);
   B200_CUDA_TRY(cudaFuncSetAttribute(joints_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchTimer _timer_225("joints_bwd", st);
   joints_bwd_kernel<<<Sw / 32, JT_THREADS, smem, st>>>(m, vpT, S, A_T, b0, nb, cam, joints, grad_joints,
                                                        grad_joints2d, dvp_hi, dvp_lo, dA_part, dtr_part, dJposed_T,
                                                        grad_cam);

@@ -259,6 +259,7 @@ int launch_lbs_fwd(const DevModel& m, const float* vpT, int S, const float* A_T,
   split_plan(m.ntiles, groups, num_sms, nsplit, tps);
   const size_t smem = (size_t)(NJ * AELEMS * 32 + LBS_WARPS * 32 * STAGE_PITCH) * sizeof(float);
   B200_CUDA_TRY(cudaFuncSetAttribute(lbs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchTimer _timer_261("lbs_fwd", st);
   lbs_fwd_kernel<<<dim3(groups, nsplit), LBS_THREADS, smem, st>>>(vpT, S, A_T, b0, nb, transl, verts, m.V, m.ntiles,
                                                                   tps, m.vmeta, m.vwts);
   B200_LAUNCH_CHECK("lbs_fwd");
@@ -279,6 +280,7 @@ int launch_lbs_bwd(const DevModel& m, const float* vpT, int S, int Sw, const flo
   const int tps = ((m.ntiles + nsplit - 1) / nsplit + LBS_WARPS - 1) / LBS_WARPS * LBS_WARPS;
   const size_t smem = (size_t)(2 * NJ * AELEMS * 32 + 3 * 32 + LBS_WARPS * 32 * STAGE_PITCH) * sizeof(float);
   B200_CUDA_TRY(cudaFuncSetAttribute(lbs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchTimer _timer_281("lbs_bwd", st);
   lbs_bwd_kernel<<<dim3(Sw / 32, nsplit), LBS_THREADS, smem, st>>>(vpT, S, A_T, b0, nb, grad_verts, m.V, m.ntiles,
                                                                    tps, m.vmeta, m.vwts, dvp_hi, dvp_lo, m.n_pad,
                                                                    dA_part, dtr_part);

@@ -403,9 +403,11 @@ int launch_pose_fwd(const DevModel& m, const float* betas, const float* pose, bo
   const int grid = Sw / 32;
   if (axis_angle) {
     B200_CUDA_TRY(cudaFuncSetAttribute(pose_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LaunchTimer _timer_405("pose_fwd", st);
     pose_fwd_kernel<true><<<grid, POSE_THREADS, smem, st>>>(m, betas, pose, b0, nb, S, feat, featf, A_T, jposed_T);
   } else {
     B200_CUDA_TRY(cudaFuncSetAttribute(pose_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LaunchTimer _timer_408("pose_fwd", st);
     pose_fwd_kernel<false><<<grid, POSE_THREADS, smem, st>>>(m, betas, pose, b0, nb, S, feat, featf, A_T, jposed_T);
   }
   B200_LAUNCH_CHECK("pose_fwd");
@@ -421,11 +423,13 @@ int launch_pose_bwd(const DevModel& m, const float* betas, const float* pose, bo
   const int grid = (nb + 31) / 32;
   if (axis_angle) {
     B200_CUDA_TRY(cudaFuncSetAttribute(pose_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LaunchTimer _timer_423("pose_bwd", st);
     pose_bwd_kernel<true><<<grid, POSE_THREADS, smem, st>>>(m, betas, pose, b0, nb, S, dA_part, n_dA_parts, dtr_part,
                                                             dfeat_part, n_dfeat_parts, dJposed_T, grad_betas,
                                                             grad_pose, grad_transl);
   } else {
     B200_CUDA_TRY(cudaFuncSetAttribute(pose_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LaunchTimer _timer_428("pose_bwd", st);
     pose_bwd_kernel<false><<<grid, POSE_THREADS, smem, st>>>(m, betas, pose, b0, nb, S, dA_part, n_dA_parts, dtr_part,
                                                              dfeat_part, n_dfeat_parts, dJposed_T, grad_betas,
                                                              grad_pose, grad_transl);

@@ -46,9 +46,7 @@ class _Rot6d(torch.autograd.Function):
 
 def rot6d_to_rotmat(x: torch.Tensor) -> torch.Tensor:
     """utils/rigid_transform_utils.py:27-41: (B,6k) -> (B*k,3,3); gradient flows to the input's shape."""
-    shape = x.shape
-    return _Rot6d.apply(x.reshape(-1, 6)).reshape(-1, 3, 3) if x.numel() else x.new_zeros((0, 3, 3)) \
-        if shape else x
+    return _Rot6d.apply(x.reshape(-1, 6))
 
 
 class _Ortho(torch.autograd.Function):

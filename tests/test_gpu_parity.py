@@ -1,0 +1,258 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C-ABI
+library, against the CPU oracle on the same seeded inputs, against the committed known answers,
+and -- at BASELINE.json's batch sizes -- through size-independent properties.
+
+Tolerances (BASELINE.json north_star): vertices / joints 1e-5 m absolute in fp32 modes, 1e-4 m in
+bf16-GEMM mode; gradients 1e-4 relative in fp32 modes (bf16 mode: 3e-2, its operands carry 8
+mantissa bits); index / topology work bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import smpl_oracle as O
+from soccerplayershapepose_b200 import _lib
+from soccerplayershapepose_b200.engine import SMPLEngine
+from soccerplayershapepose_b200.smpl import SMPL, SMPLLayer, SMPLOutput
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = {"fp32": 1e-5, "fp32_simt": 1e-5, "bf16": 1e-4}
+GRAD_TOL = {"fp32": 1e-4, "fp32_simt": 1e-4, "bf16": 3e-2}
+MODES = ["fp32_simt", "fp32", "bf16"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def engine(synthetic_model, dev):
+    return SMPLEngine(synthetic_model, dev)
+
+
+@pytest.fixture(scope="module")
+def oracle64(synthetic_model):
+    return O.SMPLOracle(synthetic_model, dtype=torch.float64)
+
+
+def make_inputs(B, seed):
+    g = torch.Generator().manual_seed(seed)
+    betas = torch.randn(B, 10, generator=g)
+    pose = torch.randn(B, 72, generator=g) * 0.3
+    trans = torch.rand(B, 3, generator=g) * 2 - 1
+    cam = torch.stack([torch.rand(B, generator=g) * 0.6 + 0.6, torch.rand(B, generator=g) * 0.4 - 0.2,
+                       torch.rand(B, generator=g) * 0.4 - 0.2], 1)
+    return betas, pose, trans, cam
+
+
+def rotmats_of(pose):
+    return O.batch_rodrigues(pose.double().reshape(-1, 3)).reshape(pose.shape[0], 24, 3, 3).float()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("B", [1, 5, 37, 130])
+def test_forward_rotmat_surface(engine, oracle64, dev, mode, B):
+    betas, pose, trans, cam = make_inputs(B, 100 + B)
+    rot = rotmats_of(pose)
+    ref = oracle64.forward_flat(betas.double(), rot.double(), trans.double(), pose2rot=False)
+    v, j, j2d = engine.forward(betas.to(dev), rot.to(dev), trans.to(dev), cam.to(dev), mode=_lib.MODES[mode])
+    torch.cuda.synchronize()
+    assert v.shape == (B, 6890, 3) and j.shape == (B, 90, 3) and j2d.shape == (B, 90, 2)
+    assert (v.cpu().double() - ref.vertices).abs().max().item() < POS_TOL[mode]
+    assert (j.cpu().double() - ref.joints).abs().max().item() < POS_TOL[mode]
+    ref2d = O.orthographic_project(ref.joints, cam.double())
+    assert (j2d.cpu().double() - ref2d).abs().max().item() < 2 * POS_TOL[mode]
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_forward_axis_angle_surface_no_transl(engine, oracle64, dev, mode):
+    betas, pose, _, _ = make_inputs(9, 7)
+    ref = oracle64.forward_flat(betas.double(), pose.double(), None, pose2rot=True)
+    v, j, j2d = engine.forward(betas.to(dev), pose.to(dev), None, None, axis_angle=True, mode=_lib.MODES[mode])
+    assert j2d is None
+    assert (v.cpu().double() - ref.vertices).abs().max().item() < POS_TOL[mode]
+    assert (j.cpu().double() - ref.joints).abs().max().item() < POS_TOL[mode]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_known_answers(engine, smpl_kat, dev, mode):
+    k = smpl_kat
+    f = lambda a: torch.from_numpy(a).float().to(dev)  # noqa: E731
+    v, j, _ = engine.forward(f(k["betas"]), f(k["rotmats"]), f(k["trans"]), None, mode=_lib.MODES[mode])
+    sub = torch.from_numpy(k["vert_subset"]).to(dev)
+    assert np.abs(v[:, sub].cpu().numpy() - k["verts_sub"]).max() < POS_TOL[mode]
+    assert np.abs(j.cpu().numpy() - k["joints"]).max() < POS_TOL[mode]
+    va, ja, _ = engine.forward(f(k["betas"][:5]), f(k["pose_aa"]), None, None, axis_angle=True,
+                               mode=_lib.MODES[mode])
+    assert np.abs(va[:, sub].cpu().numpy() - k["aa_verts_sub"]).max() < POS_TOL[mode]
+    assert np.abs(ja.cpu().numpy() - k["aa_joints"]).max() < POS_TOL[mode]
+
+
+def test_tpose_is_template(engine, synthetic_model, dev):
+    v, j, _ = engine.forward(torch.zeros(3, 10, device=dev), torch.zeros(3, 72, device=dev), None, None,
+                             axis_angle=True, mode=_lib.MODE_FP32)
+    vt = torch.from_numpy(synthetic_model["v_template"]).to(dev)
+    assert (v - vt).abs().max().item() < 1e-6
+
+
+def _rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def _oracle_grads(oracle64, betas, pose, trans, cam, dV, dJ, dJ2, axis_angle):
+    b = betas.double().requires_grad_(True)
+    p = pose.double().requires_grad_(True)
+    t = trans.double().requires_grad_(True) if trans is not None else None
+    c = cam.double().requires_grad_(True) if cam is not None else None
+    out = oracle64.forward_flat(b, p, t, pose2rot=axis_angle)
+    loss = 0.0
+    if dV is not None:
+        loss = loss + (out.vertices * dV.double()).sum()
+    if dJ is not None:
+        loss = loss + (out.joints * dJ.double()).sum()
+    if dJ2 is not None:
+        loss = loss + (O.orthographic_project(out.joints, c) * dJ2.double()).sum()
+    loss.backward()
+    return b.grad, p.grad, (None if t is None else t.grad), (None if c is None or c.grad is None else c.grad)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("axis_angle", [False, True])
+def test_backward_full(engine, oracle64, dev, mode, axis_angle):
+    B = 37
+    betas, pose_aa, trans, cam = make_inputs(B, 5)
+    pose = pose_aa if axis_angle else rotmats_of(pose_aa)
+    g = torch.Generator().manual_seed(9)
+    dV = torch.randn(B, 6890, 3, generator=g)
+    dJ = torch.randn(B, 90, 3, generator=g)
+    dJ2 = torch.randn(B, 90, 2, generator=g)
+    rb, rp, rt, rc = _oracle_grads(oracle64, betas, pose, trans, cam, dV, dJ, dJ2, axis_angle)
+    m = _lib.MODES[mode]
+    d = lambda x: x.to(dev)  # noqa: E731
+    _, joints, _ = engine.forward(d(betas), d(pose), d(trans), d(cam), axis_angle=axis_angle, mode=m)
+    gb, gp, gt, gc = engine.backward(d(betas), d(pose), d(trans), d(cam), joints, d(dV), d(dJ), d(dJ2),
+                                     axis_angle=axis_angle, mode=m)
+    tol = GRAD_TOL[mode]
+    assert _rel(gb.cpu().double(), rb) < tol
+    assert _rel(gp.cpu().double().reshape(rp.shape), rp) < tol
+    assert _rel(gt.cpu().double(), rt) < tol
+    assert _rel(gc.cpu().double(), rc) < tol
+
+
+@pytest.mark.parametrize("mode", ["fp32_simt", "fp32"])
+@pytest.mark.parametrize("which", ["verts_only", "joints_only", "j2d_only"])
+def test_backward_partial_gradients(engine, oracle64, dev, mode, which):
+    B = 6
+    betas, pose_aa, trans, cam = make_inputs(B, 11)
+    pose = rotmats_of(pose_aa)
+    g = torch.Generator().manual_seed(2)
+    dV = torch.randn(B, 6890, 3, generator=g) if which == "verts_only" else None
+    dJ = torch.randn(B, 90, 3, generator=g) if which == "joints_only" else None
+    dJ2 = torch.randn(B, 90, 2, generator=g) if which == "j2d_only" else None
+    rb, rp, rt, rc = _oracle_grads(oracle64, betas, pose, trans, cam, dV, dJ, dJ2, False)
+    m = _lib.MODES[mode]
+    d = lambda x: None if x is None else x.to(dev)  # noqa: E731
+    _, joints, _ = engine.forward(d(betas), d(pose), d(trans), d(cam), mode=m, want_vertices=dV is not None)
+    gb, gp, gt, gc = engine.backward(d(betas), d(pose), d(trans), d(cam), joints, d(dV), d(dJ), d(dJ2), mode=m)
+    assert _rel(gb.cpu().double(), rb) < 1e-4
+    assert _rel(gp.cpu().double().reshape(rp.shape), rp) < 1e-4
+    assert _rel(gt.cpu().double(), rt) < 1e-4
+    if which == "j2d_only":
+        assert _rel(gc.cpu().double(), rc) < 1e-4
+    else:
+        assert gc.abs().max().item() == 0.0
+
+
+def test_reference_module_surface(synthetic_model, oracle64, dev):
+    """Call pattern of player_recon.py:1192-1210,1280: leaf rotmats / betas with requires_grad, keyword
+    call with pose2rot=False, loss.backward()."""
+    smpl = SMPL(synthetic_model, batch_size=1).to(dev)
+    names = set(dict(smpl.named_buffers()).keys())
+    assert {"v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights", "parents", "faces_tensor",
+            "J_regressor_extra", "J_regressor_cocoplus", "J_regressor_h36m"} <= names
+    assert smpl.faces.shape == (13776, 3) and np.array_equal(smpl.faces, synthetic_model["faces"])
+    assert torch.equal(smpl.faces_tensor.cpu(), torch.from_numpy(synthetic_model["faces"]))
+    assert torch.equal(smpl.parents.cpu(), torch.from_numpy(synthetic_model["parents"]))
+    betas, pose_aa, _, cam = make_inputs(2, 3)
+    rot = rotmats_of(pose_aa)
+    go = rot[:, :1].clone().to(dev).requires_grad_(True)
+    bp = rot[:, 1:].clone().to(dev).requires_grad_(True)
+    be = betas.clone().to(dev).requires_grad_(True)
+    out = smpl(body_pose=bp, global_orient=go, betas=be, pose2rot=False)
+    assert isinstance(out, SMPLOutput) and out.vertices.shape == (2, 6890, 3) and out.joints.shape == (2, 90, 3)
+    assert out["joints"] is out.joints and out.full_pose is None and out.betas is be
+    ref = oracle64.forward_flat(betas.double(), rot.double(), None, pose2rot=False)
+    assert (out.vertices.detach().cpu().double() - ref.vertices).abs().max().item() < 1e-5
+    loss = (out.joints[:, :45] ** 2).sum() + out.vertices.sum()
+    loss.backward()
+    b64 = betas.double().requires_grad_(True)
+    r64 = rot.double().requires_grad_(True)
+    o = oracle64.forward_flat(b64, r64, None, pose2rot=False)
+    ((o.joints[:, :45] ** 2).sum() + o.vertices.sum()).backward()
+    assert _rel(be.grad.cpu().double(), b64.grad) < 1e-4
+    assert _rel(torch.cat([go.grad, bp.grad], 1).cpu().double(), r64.grad) < 1e-4
+    # default-pose call smpl(betas=pred_shape) (predict/predict_3D.py:148) with a batch of betas
+    out0 = smpl(betas=be.detach())
+    ref0 = oracle64.forward_flat(betas.double(), torch.zeros(2, 72, dtype=torch.float64), None, pose2rot=True)
+    assert (out0.vertices.cpu().double() - ref0.vertices).abs().max().item() < 1e-5
+    # north_star positional surface
+    layer = SMPLLayer(synthetic_model).to(dev)
+    v, j = layer(be.detach(), rot.to(dev), None)
+    assert (j.cpu().double() - ref.joints).abs().max().item() < 1e-5
+    # errors: CPU tensors are refused (no CPU path), wrong shapes raise
+    with pytest.raises(RuntimeError):
+        layer(betas, rot, None)
+    with pytest.raises(ValueError):
+        layer(be.detach()[:, :5], rot.to(dev), None)
+
+
+def test_joints_only_autograd_skips_vertices(synthetic_model, oracle64, dev):
+    smpl = SMPL(synthetic_model).to(dev)
+    betas, pose_aa, trans, cam = make_inputs(4, 8)
+    rot = rotmats_of(pose_aa).to(dev).requires_grad_(True)
+    be = betas.to(dev).requires_grad_(True)
+    camd = cam.to(dev).requires_grad_(True)
+    out = smpl(body_pose=rot[:, 1:], global_orient=rot[:, :1], betas=be, transl=trans.to(dev), pose2rot=False,
+               cam=camd, return_verts=False)
+    assert out.vertices is None
+    (out.joints2d ** 2).sum().backward()
+    b64, r64 = betas.double().requires_grad_(True), rotmats_of(pose_aa).double().requires_grad_(True)
+    c64 = cam.double().requires_grad_(True)
+    o = oracle64.forward_flat(b64, r64, trans.double(), pose2rot=False)
+    (O.orthographic_project(o.joints, c64) ** 2).sum().backward()
+    assert _rel(be.grad.cpu().double(), b64.grad) < 1e-4
+    assert _rel(rot.grad.cpu().double(), r64.grad) < 1e-4
+    assert _rel(camd.grad.cpu().double(), c64.grad) < 1e-4
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_full_size_properties(engine, dev, mode):
+    """BASELINE.json config 2 size (B=4096): slab invariance, determinism of the forward,
+    translation equivariance, and linearity of the backward in the upstream gradient."""
+    B = 4096
+    m = _lib.MODES[mode]
+    betas, pose_aa, trans, _ = make_inputs(B, 1)
+    d = lambda x: x.to(dev)  # noqa: E731
+    betas, pose_aa, trans = d(betas), d(pose_aa), d(trans)
+    v1, j1, _ = engine.forward(betas, pose_aa, trans, None, axis_angle=True, mode=m, slab=1024)
+    v1, j1 = v1.clone(), j1.clone()
+    v2, j2, _ = engine.forward(betas, pose_aa, trans, None, axis_angle=True, mode=m, slab=512)
+    assert torch.equal(v1, v2) and torch.equal(j1, j2)          # slab size never changes a body's result
+    v3, j3, _ = engine.forward(betas, pose_aa, None, None, axis_angle=True, mode=m)
+    assert (v3 + trans[:, None] - v1).abs().max().item() < 1e-6
+    assert (j3 + trans[:, None] - j1).abs().max().item() < 1e-6
+    # a body computed alone equals the same body inside the batch
+    for i in (0, 1717, 4095):
+        vi, ji, _ = engine.forward(betas[i:i + 1], pose_aa[i:i + 1], trans[i:i + 1], None, axis_angle=True, mode=m)
+        assert torch.equal(vi[0], v1[i]) and torch.equal(ji[0], j1[i])
+    # backward: linear in (dV, dJ)
+    g = torch.Generator(device="cpu").manual_seed(4)
+    dV = d(torch.randn(256, 6890, 3, generator=g))
+    dJ = d(torch.randn(256, 90, 3, generator=g))
+    sl = slice(100, 356)
+    ga = engine.backward(betas[sl], pose_aa[sl], trans[sl], None, None, dV, dJ, None, axis_angle=True, mode=m)
+    gb = engine.backward(betas[sl], pose_aa[sl], trans[sl], None, None, 2 * dV, 2 * dJ, None, axis_angle=True, mode=m)
+    for a, b in zip(ga[:3], gb[:3]):
+        assert _rel(b, 2 * a) < (1e-5 if mode == "fp32" else 2e-2)
