@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the SMPL hot path: SMPL meshes/sec, forward+backward (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode fp32|bf16]
+
+One "step" = one forward+backward pass of the batched SMPL layer over one batch of synthetic
+(betas, pose, trans) with upstream gradients (dV, dJ): BASELINE.json configs[1] (B = 4096 bodies on
+one B200), the same per-GPU batch on every rank for N > 1 (batch sharding, no communication).
+
+Prints ONE JSON line (rank 0).  `value` = bodies processed by all ranks / max-over-ranks device
+time with inputs resident in HBM; `e2e` = the same metric through the public module API with the
+step's inputs copied from pinned host memory and the gradients copied back inside the timed region.
+`--impl reference` times the reference's CPU path (the PyTorch-eager oracle port, all host threads)
+on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "SMPL meshes/sec fwd+bwd"
+UNIT = "meshes/s"
+# algorithmic HBM bytes per mesh of the dominant (skinning) kernels, SURVEY.md section 8(d) / DESIGN.md
+LBS_FWD_BYTES = 82680 + 1152 + 82680                 # v_posed in, A in, vertices out
+LBS_BWD_BYTES = 82680 + 82680 + 1152 + 82680 + 1152  # dV in, v_posed in, A in, dv_posed out, dA out
+KERNEL_BYTES = {"lbs_fwd": LBS_FWD_BYTES, "lbs_bwd": LBS_BWD_BYTES}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_inputs(B, seed, device):
+    from soccerplayershapepose_b200.synthetic_inputs import make_smpl_inputs, make_upstream_grads
+    x = make_smpl_inputs(B, seed)
+    dV, dJ = make_upstream_grads(B, seed)
+    return [t.to(device) for t in (x["betas"], x["rotmats"], x["trans"], dV, dJ)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def timing_report(lib):
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.b200smpl_timing_report(buf, 1 << 16)
+    out = {}
+    for ln in buf.value.decode().splitlines():
+        name, n, ms = ln.split()
+        out[name] = (int(n), float(ms))
+    return out
+
+
+def cpu_reference_run(steps, warmup, sample_B, min_seconds=0.0):
+    """The reference's CPU path: PyTorch-eager restatement (oracle/) of models/smpl_official.py on
+    the host cores, forward + backward, fp32, all threads."""
+    from oracle.smpl_oracle import SMPLOracle, batch_rodrigues
+    from soccerplayershapepose_b200.model_io import make_synthetic_smpl
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = make_synthetic_smpl(1234)
+    orc = SMPLOracle(model, dtype=torch.float32)
+    g = torch.Generator().manual_seed(0)
+    betas = torch.randn(sample_B, 10, generator=g)
+    pose = torch.randn(sample_B, 72, generator=g) * 0.3
+    rot = batch_rodrigues(pose.reshape(-1, 3)).reshape(sample_B, 24, 3, 3)
+    trans = torch.rand(sample_B, 3, generator=g) * 2 - 1
+    dV = torch.randn(sample_B, 6890, 3, generator=g)
+    dJ = torch.randn(sample_B, 90, 3, generator=g)
+
+    def step():
+        b, r, t = (x.clone().requires_grad_(True) for x in (betas, rot, trans))
+        out = orc.forward_flat(b, r, t, pose2rot=False)
+        torch.autograd.backward([out.vertices, out.joints], [dV, dJ])
+        return b.grad
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < steps or (time.perf_counter() - t0) < min_seconds:
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return sample_B * n / dt, dt / n * 1e3, n, torch.get_num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--batch-per-gpu", type=int, default=4096)
+    ap.add_argument("--slab", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    B = args.batch_per_gpu
+
+    config = {"workload": "BASELINE.json configs[1]: batched SMPL forward+backward, batch %d per GPU, neutral-model "
+                          "shapes (6890 verts, 24 joints, 10 betas, 90 output joints), synthetic model seed 1234" % B,
+              "batch_per_gpu": B, "global_batch": B * world, "mode": args.mode,
+              "parallelism": "batch-sharded x%d, no communication" % world,
+              "l2": "inputs larger than L2 (dV alone is %.0f MB per step)" % (B * 82680 / 1e6)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        val, ms, n, threads = cpu_reference_run(args.steps, args.warmup, args.cpu_sample)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                 "sample": "oracle port (PyTorch eager CPU) fwd+bwd, batch %d per step" % args.cpu_sample},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the SMPL path has no CPU fallback")
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from soccerplayershapepose_b200 import _lib
+    from soccerplayershapepose_b200.model_io import make_synthetic_smpl
+    from soccerplayershapepose_b200.smpl import SMPLLayer
+    lib = _lib.load()
+    model = make_synthetic_smpl(1234)
+    layer = SMPLLayer(model, mode=args.mode, slab_bodies=args.slab).to(dev)
+    eng = layer._engine(dev)
+    mode = _lib.MODES[args.mode]
+    betas, rot, trans, dV, dJ = make_inputs(B, seed=rank, device=dev)
+
+    def step():
+        eng.forward(betas, rot, trans, None, mode=mode, slab=args.slab)
+        return eng.backward(betas, rot, trans, None, None, dV, dJ, None, mode=mode, slab=args.slab)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.b200smpl_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    launches = lib.b200smpl_launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = B * world * args.steps / (ms_total / 1e3)
+
+    # ---- per-kernel device times over the same K steps (events on the launching stream) ----
+    lib.b200smpl_timing_enable(1)
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize(dev)
+    lib.b200smpl_timing_enable(0)
+    kt = timing_report(lib)
+    peak, peak_src = measured_peaks()
+    step_ms_timed = sum(ms for _, ms in kt.values()) / args.steps
+    dom = max((k for k in kt if k in KERNEL_BYTES), key=lambda k: kt[k][1], default=None)
+    roofline = None
+    if dom is not None:
+        n_launch, ms = kt[dom]
+        per_launch_ms = ms / n_launch
+        bodies_per_launch = B * args.steps / n_launch
+        achieved = KERNEL_BYTES[dom] * bodies_per_launch / (per_launch_ms / 1e3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "bytes_per_mesh": KERNEL_BYTES[dom], "avg_launch_ms": per_launch_ms,
+                    "share_of_step": ms / args.steps / step_ms_timed,
+                    "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(kt.items())}}
+
+    # ---- end to end through the public module API, host buffers in, gradients out ----
+    hb, hr, ht = (x.cpu().pin_memory() for x in (betas, rot, trans))
+    gb_h = torch.empty((B, 10)).pin_memory()
+    gr_h = torch.empty((B, 24, 3, 3)).pin_memory()
+    gt_h = torch.empty((B, 3)).pin_memory()
+
+    def e2e_step():
+        b = hb.to(dev, non_blocking=True).requires_grad_(True)
+        r = hr.to(dev, non_blocking=True).requires_grad_(True)
+        tt = ht.to(dev, non_blocking=True).requires_grad_(True)
+        v, j = layer(b, r, tt)
+        torch.autograd.backward([v, j], [dV, dJ])
+        gb_h.copy_(b.grad, non_blocking=True)
+        gr_h.copy_(r.grad, non_blocking=True)
+        gt_h.copy_(tt.grad, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()       # the step's result is on the host
+
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    sync_all()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_val = B * world * args.steps / float(dt.item())
+    io_bytes = B * (10 + 216 + 3) * 4
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, ms, n, threads = cpu_reference_run(5, 3, args.cpu_sample, min_seconds=10.0)
+        cpu_baseline = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": "oracle port (PyTorch eager CPU, fp32) fwd+bwd at batch %d, %d iterations, "
+                                  "%.1f ms each" % (args.cpu_sample, n, ms)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (bf16x3 split on tcgen05, fp32 accumulate)" if args.mode == "fp32" else "bf16-GEMM / f32",
+                "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -40,7 +40,7 @@ LaunchTimer::~LaunchTimer() {
   g_timing_recs.push_back({name_, start_, stop});
 }
 
-constexpr int DEFAULT_SLAB = 1024;   // bodies per L2-resident pass (vpT slab = n_pad * S * 4 B ~ 89 MB)
+constexpr int DEFAULT_SLAB = 4096;   // bodies per pass (vpT slab = n_pad * S * 4 B)
 
 struct Plan {
   int S;                 // slab pitch (multiple of 128)
