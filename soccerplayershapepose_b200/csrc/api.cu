@@ -47,7 +47,8 @@ struct Plan {
   int lbs_splits;        // dA partials written by lbs_bwd
   int k_splits;          // split-K partials of the backward GEMM
   size_t off_feat, off_featf, off_A, off_jposed, off_vpT;
-  size_t off_dvp_hi, off_dvp_lo, off_dA, off_dtr, off_dJposed, off_dfeat;
+  size_t off_dvp_hi, off_dvp_lo, off_dA, off_dtr, off_dJtot, off_dfeat;
+  int joint_parts;      // dA partials written by joints_bwd
   size_t total;
 };
 
@@ -76,9 +77,10 @@ static Plan make_plan(const b200smpl_model* m, int batch, int mode, int slab_bod
     p.k_splits = mode == B200SMPL_MODE_FP32_SIMT ? 1 : blend_bwd_umma_splits(d, mode, p.S, m->num_sms);
     p.off_dvp_hi = take(S_ * d.n_pad * 2);
     p.off_dvp_lo = take(mode == B200SMPL_MODE_BF16 ? 0 : S_ * d.n_pad * 2);
-    p.off_dA = take((size_t)(p.lbs_splits + 1) * NJ * AELEMS * S_ * 4);
-    p.off_dtr = take((size_t)(p.lbs_splits + 1) * 3 * S_ * 4);
-    p.off_dJposed = take((size_t)NJ * 3 * S_ * 4);
+    p.joint_parts = joints_bwd_parts(d);
+    p.off_dA = take((size_t)(p.lbs_splits + p.joint_parts) * NJ * AELEMS * S_ * 4);
+    p.off_dtr = take((size_t)(p.lbs_splits + p.joint_parts) * 3 * S_ * 4);
+    p.off_dJtot = take((size_t)std::max(batch, 1) * d.njout * 3 * 4);
     p.off_dfeat = take((size_t)p.k_splits * S_ * d.fl.nf_pad * 4);
   }
   p.total = off + 1024;   // slack for aligning the caller's base pointer
@@ -196,6 +198,10 @@ int b200smpl_model_create(const b200smpl_model_desc* desc, int device, b200smpl_
   UP(term_joint, h.term_joint);
   UP(term_qrow, h.term_qrow);
   UP(term_c, h.term_c);
+  UP(qmeta, h.qmeta);
+  UP(qcoef, h.qcoef);
+  UP(vt_j0, h.vt_j0);
+  UP(vt_nj, h.vt_nj);
 #undef UP
   cudaSetDevice(prev);
   if (!ok) {
@@ -239,7 +245,8 @@ int b200smpl_model_debug_array(const b200smpl_model* m, const char* name, const 
   }
   RET("Wf", h.Wf) RET("Wb_hi", h.Wb_hi) RET("Wb_lo", h.Wb_lo) RET("W32", h.W32) RET("vmeta", h.vmeta)
   RET("vwts", h.vwts) RET("term_ptr", h.term_ptr) RET("term_joint", h.term_joint) RET("term_qrow", h.term_qrow)
-  RET("term_c", h.term_c) RET("Jt", h.Jt) RET("Jsd", h.Jsd)
+  RET("term_c", h.term_c) RET("Jt", h.Jt) RET("Jsd", h.Jsd) RET("qmeta", h.qmeta) RET("qcoef", h.qcoef)
+  RET("vt_j0", h.vt_j0) RET("vt_nj", h.vt_nj)
 #undef RET
   return fail(B200SMPL_ERR_INVALID, "unknown debug array: " + n);
 }
@@ -267,7 +274,6 @@ int b200smpl_forward(const b200smpl_model* m, const b200smpl_forward_args* a, vo
   __nv_bfloat16* feat = (__nv_bfloat16*)(ws + p.off_feat);
   float* featf = a->mode == B200SMPL_MODE_FP32_SIMT ? (float*)(ws + p.off_featf) : nullptr;
   float* A_T = (float*)(ws + p.off_A);
-  float* jposed_T = (float*)(ws + p.off_jposed);
   float* vpT = (float*)(ws + p.off_vpT);
   const int S = p.S, B = a->batch;
   const bool aa = a->pose_is_axis_angle != 0;
@@ -275,7 +281,8 @@ int b200smpl_forward(const b200smpl_model* m, const b200smpl_forward_args* a, vo
   for (int b0 = 0; b0 < B; b0 += S) {
     const int nb = std::min(S, B - b0);
     const int Sw = round_up(nb, 128);
-    if ((rc = launch_pose_fwd(d, a->betas, a->pose, aa, b0, nb, S, Sw, feat, featf, A_T, jposed_T, st))) return rc;
+    if ((rc = launch_pose_fwd(d, a->betas, a->pose, aa, b0, nb, S, Sw, feat, featf, A_T, a->transl, a->joints, st)))
+      return rc;
     if (a->mode == B200SMPL_MODE_FP32_SIMT)
       rc = launch_blend_fwd_simt(d, featf, S, Sw, vpT, row_begin, d.n_pad, st);
     else
@@ -283,9 +290,10 @@ int b200smpl_forward(const b200smpl_model* m, const b200smpl_forward_args* a, vo
     if (rc) return rc;
     if (a->vertices)
       if ((rc = launch_lbs_fwd(d, vpT, S, A_T, b0, nb, a->transl, a->vertices, m->num_sms, st))) return rc;
-    if ((rc = launch_joints_fwd(d, vpT, S, A_T, jposed_T, b0, nb, a->transl, a->cam, a->joints, a->joints2d, st)))
-      return rc;
+    if ((rc = launch_joints_fwd(d, vpT, S, A_T, b0, nb, a->transl, a->joints, st))) return rc;
   }
+  if (a->joints2d)   // reprojection of all joints: utils/cam_utils.py:5-26
+    if ((rc = b200smpl_orthographic_project(a->joints, a->cam, a->joints2d, B, d.njout, 0.f, stream))) return rc;
   return 0;
 }
 
@@ -316,16 +324,23 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
   __nv_bfloat16* feat = (__nv_bfloat16*)(ws + p.off_feat);
   float* featf = a->mode == B200SMPL_MODE_FP32_SIMT ? (float*)(ws + p.off_featf) : nullptr;
   float* A_T = (float*)(ws + p.off_A);
-  float* jposed_T = (float*)(ws + p.off_jposed);
   float* vpT = (float*)(ws + p.off_vpT);
   __nv_bfloat16* dvp_hi = (__nv_bfloat16*)(ws + p.off_dvp_hi);
   __nv_bfloat16* dvp_lo = a->mode == B200SMPL_MODE_BF16 ? nullptr : (__nv_bfloat16*)(ws + p.off_dvp_lo);
   float* dA_part = (float*)(ws + p.off_dA);
   float* dtr_part = (float*)(ws + p.off_dtr);
-  float* dJposed_T = (float*)(ws + p.off_dJposed);
+  float* dJtot = (float*)(ws + p.off_dJtot);
   float* dfeat_part = (float*)(ws + p.off_dfeat);
-  // partial 0 belongs to joints_bwd (when present), the skinning partials follow
-  const int jpart = have_j ? 1 : 0;
+  // total joint gradient: grad_joints itself, or grad_joints + reprojected 2D gradient (also yields dcam)
+  const float* dJ = a->grad_joints;
+  if (a->grad_joints2d) {
+    if ((rc = launch_joint_grad_total(a->joints, a->cam, a->grad_joints, a->grad_joints2d, dJtot, a->grad_cam, B,
+                                      d.njout, st)))
+      return rc;
+    dJ = dJtot;
+  }
+  // the joints_bwd partials (when present) come first, the skinning partials follow
+  const int jpart = have_j ? p.joint_parts : 0;
   const int n_parts = jpart + (have_v ? p.lbs_splits : 0);
   const int row_begin = have_v ? 0 : d.n_virt0;
   const int row_end = have_j ? d.n_rows : d.n_virt0;
@@ -337,7 +352,8 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
   for (int b0 = 0; b0 < B; b0 += S) {
     const int nb = std::min(S, B - b0);
     const int Sw = round_up(nb, 128);
-    if ((rc = launch_pose_fwd(d, a->betas, a->pose, aa, b0, nb, S, Sw, feat, featf, A_T, jposed_T, st))) return rc;
+    if ((rc = launch_pose_fwd(d, a->betas, a->pose, aa, b0, nb, S, Sw, feat, featf, A_T, nullptr, nullptr, st)))
+      return rc;
     if (a->mode == B200SMPL_MODE_FP32_SIMT)
       rc = launch_blend_fwd_simt(d, featf, S, Sw, vpT, row_begin, d.n_pad, st);
     else
@@ -349,16 +365,14 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
                                p.lbs_splits, st)))
         return rc;
     if (have_j)
-      if ((rc = launch_joints_bwd(d, vpT, S, Sw, A_T, b0, nb, a->cam, a->joints, a->grad_joints, a->grad_joints2d,
-                                  dvp_hi, dvp_lo, dA_part, dtr_part, dJposed_T, a->grad_cam, st)))
-        return rc;
+      if ((rc = launch_joints_bwd(d, vpT, S, Sw, A_T, b0, nb, dJ, dvp_hi, dvp_lo, dA_part, dtr_part, st))) return rc;
     if (a->mode == B200SMPL_MODE_FP32_SIMT)
       rc = launch_blend_bwd_simt(d, dvp_hi, dvp_lo, Sw, dfeat_part, row_begin, row_end, st);
     else
       rc = launch_blend_bwd_umma(d, a->mode, dvp_hi, dvp_lo, S, Sw, dfeat_part, k_splits, row_begin, row_end, st);
     if (rc) return rc;
     if ((rc = launch_pose_bwd(d, a->betas, a->pose, aa, b0, nb, S, dA_part, n_parts, dtr_part, dfeat_part, k_splits,
-                              have_j ? dJposed_T : nullptr, a->grad_betas, a->grad_pose, a->grad_transl, st)))
+                              have_j ? dJ : nullptr, a->grad_betas, a->grad_pose, a->grad_transl, st)))
       return rc;
   }
   return 0;

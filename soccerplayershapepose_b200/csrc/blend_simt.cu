@@ -38,7 +38,10 @@ blend_fwd_simt_kernel(const float* __restrict__ W32, int n_pad, int nf, const fl
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) vpT[(size_t)(n0 + ty * 4 + i) * S + s0 + tx] = acc[i];
+  for (int i = 0; i < 4; ++i) {   // group-blocked layout: chunk (n / 96, group), line n % 96
+    const size_t n = (size_t)(n0 + ty * 4 + i);
+    vpT[((n / 96) * (S / 32) + (s0 >> 5)) * (size_t)(96 * 32) + (n % 96) * 32 + tx] = acc[i];
+  }
 }
 
 int launch_blend_fwd_simt(const DevModel& m, const float* featf, int S, int Sw, float* vpT, int row_begin,

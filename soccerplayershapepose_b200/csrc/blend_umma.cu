@@ -129,7 +129,10 @@ struct GemmSmem {
 };
 
 // grid: (m tiles, n tiles, k splits)
-template <int BN, int STAGES, int MIN_CTAS>
+// BLOCKED = false: D is row-major with leading dimension ldd (+ blockIdx.z * split_stride).
+// BLOCKED = true : D is the group-blocked blend output: element (row n, column s) lives at
+//                  ((n / 96) * ldd + s / 32) * 3072 + (n % 96) * 32 + s % 32   with ldd = groups per slab.
+template <int BN, int STAGES, int MIN_CTAS, bool BLOCKED>
 __global__ void __launch_bounds__(GEMM_THREADS, MIN_CTAS)
 umma_gemm_kernel(const __grid_constant__ GemmMaps maps, int nseg, int slab_begin, int slab_end, int slabs_per_split,
                  int a_row0, int b_row0, float* __restrict__ D, int ldd, long long split_stride) {
@@ -219,7 +222,16 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, int nseg, int slab_begin
     // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
-    float* drow = D + (long long)blockIdx.z * split_stride + (long long)row * ldd + n0;
+    float* drow;
+    long long cstep;                       // pointer step per 32 output columns
+    if (BLOCKED) {
+      const long long n = (long long)a_row0 + row;
+      drow = D + ((n / 96) * ldd + n0 / 32) * 3072LL + (n % 96) * 32;
+      cstep = 3072;
+    } else {
+      drow = D + (long long)blockIdx.z * split_stride + (long long)row * ldd + n0;
+      cstep = 32;
+    }
     if (total_iters > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
@@ -227,11 +239,12 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, int nseg, int slab_begin
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        float* o = drow + (long long)(c0 / 32) * cstep;
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<uint4*>(drow + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          *reinterpret_cast<uint4*>(o + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
-    } else {
+    } else if (!BLOCKED) {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 4) *reinterpret_cast<uint4*>(drow + c0) = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -281,7 +294,7 @@ constexpr int BWD_BN_MAX = 256, BWD_STAGES = 4;
 
 int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat, int S, int Sw, float* vpT,
                           int row_begin, int row_end, cudaStream_t st) {
-  const int kuse = (mode == B200SMPL_MODE_BF16) ? m.fl.k_bf16 : m.fl.k_fp32;
+  const int kuse = (mode == B200SMPL_MODE_BF16) ? m.fl.k_bf16x2 : m.fl.k_fp32;
   GemmMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc;
@@ -289,12 +302,11 @@ int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat
   if ((rc = make_map(&maps.b[0], feat, kuse, S, m.fl.pitch, FWD_BN))) return rc;
   const int slabs = (kuse + BK - 1) / BK;
   using SM = GemmSmem<FWD_BN, FWD_STAGES>;
-  auto kern = umma_gemm_kernel<FWD_BN, FWD_STAGES, 2>;
+  auto kern = umma_gemm_kernel<FWD_BN, FWD_STAGES, 2, true>;
   B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
   dim3 grid((row_end - row_begin) / BM, Sw / FWD_BN, 1);
   LaunchTimer _timer_291("blend_fwd_umma", st);
-  kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(maps, 1, 0, slabs, slabs, row_begin, 0,
-                                              vpT + (size_t)row_begin * S, S, 0LL);
+  kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(maps, 1, 0, slabs, slabs, row_begin, 0, vpT, S / 32, 0LL);
   B200_LAUNCH_CHECK("blend_fwd_umma");
   return 0;
 }
@@ -313,7 +325,7 @@ template <int BN>
 static int launch_bwd_bn(const GemmMaps& maps, int nseg, int slab_begin, int slab_end, int nsplit, int Sw,
                          float* dfeat_part, int nf_pad, long long split_stride, cudaStream_t st) {
   using SM = GemmSmem<BN, BWD_STAGES>;
-  auto kern = umma_gemm_kernel<BN, BWD_STAGES, 1>;
+  auto kern = umma_gemm_kernel<BN, BWD_STAGES, 1, false>;
   B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
   const int slabs = slab_end - slab_begin;
   const int sps = (slabs + nsplit - 1) / nsplit;

@@ -38,14 +38,15 @@ struct ChainTables {
 //   [1,1,1 | b_hi b_lo b_hi | pf_hi | (pad to k_bf16) | pf_lo | pf_hi | pad]
 // and the matching model rows hold
 //   [t_hi t_lo t_lo2 | S_hi S_hi S_lo | P_hi | 0 | P_hi | P_lo | 0]
-// so the first k_bf16 columns alone are the "bf16 mode" product (template + shape terms stay
-// error-compensated, the pose-corrective term is single bf16) and all k_fp32 columns give the
-// bf16x3 split product (~2^-16 relative, fp32 accumulate).
+// so the first k_bf16x2 columns are the "bf16 mode" product (template + shape terms error-
+// compensated; pose-corrective term = (pf_hi + pf_lo) * P_hi, i.e. bf16 model operand, 16-bit
+// features) and all k_fp32 columns give the bf16x3 split product (~2^-16 relative, fp32 accumulate).
 struct FeatLayout {
   int nb;       // betas
   int off_s0, off_s1, off_s2;   // 3, 3+nb, 3+2nb
   int off_p0;   // 3+3nb
   int k_bf16;   // roundup16(off_p0 + 207)
+  int k_bf16x2; // roundup16(off_p1 + 207): K extent of the bf16 mode (adds the pf_lo * P_hi segment)
   int off_p1;   // k_bf16
   int off_p2;   // k_bf16 + 207
   int k_fp32;   // roundup16(off_p2 + 207)
@@ -66,6 +67,7 @@ inline FeatLayout make_feat_layout(int nb) {
   L.k_bf16 = round_up(L.off_p0 + NPOSE, 16);
   L.off_p1 = L.k_bf16;
   L.off_p2 = L.k_bf16 + NPOSE;
+  L.k_bf16x2 = round_up(L.off_p1 + NPOSE, 16);
   L.k_fp32 = round_up(L.off_p2 + NPOSE, 16);
   L.pitch = L.k_fp32;
   L.nf = nb + NPOSE;
@@ -84,6 +86,7 @@ struct DevModel {
   int n_pad;      // n_rows rounded up to 128
   int njout;      // 24 + nvj + nreg
   int nterms;
+  int ntv;        // virtual (joint) tiles of 32 q-groups appended after the vertex tiles
   FeatLayout fl;
   ChainTables chain;
   const __nv_bfloat16* Wf;     // [n_pad][fl.pitch]         forward operand, K-major
@@ -98,6 +101,10 @@ struct DevModel {
   const uint8_t* term_joint;   // [nterms] skinning joint of the term
   const int32_t* term_qrow;    // [nterms] first of the 3 blend rows holding q
   const float* term_c;         // [nterms]
+  const uint32_t* qmeta;       // [ntv*32] virtual-tile plan: joint | reload<<5 | jl<<8 | last<<13 | valid<<14
+  const float* qcoef;          // [ntv*32] homogeneous coefficient c of the q-group
+  const int32_t* vt_j0;        // [ntv] first output joint (index into joints 24..) of the tile
+  const int32_t* vt_nj;        // [ntv] output joints covered by the tile
 };
 
 struct HostArrays {
@@ -105,7 +112,9 @@ struct HostArrays {
   std::vector<float> W32, Jt, Jsd, term_c;
   std::vector<uint32_t> vmeta;
   std::vector<float> vwts;     // 4 per vertex
-  std::vector<int32_t> term_ptr, term_qrow;
+  std::vector<int32_t> term_ptr, term_qrow, vt_j0, vt_nj;
+  std::vector<uint32_t> qmeta;
+  std::vector<float> qcoef;
   std::vector<uint8_t> term_joint;
 };
 
@@ -159,10 +168,11 @@ int pack_model(const b200smpl_model_desc* d, HostArrays& h, DevModel& dm, std::s
 // body index is the slab column (body - b0) and its body pitch is S.  nb = live bodies of the
 // slab, Sw = nb rounded up to 128 (columns in [nb, Sw) are kept zero / finite).
 int launch_pose_fwd(const DevModel& m, const float* betas, const float* pose, bool axis_angle, int b0, int nb, int S,
-                    int Sw, __nv_bfloat16* feat, float* featf, float* A_T, float* jposed_T, cudaStream_t st);
+                    int Sw, __nv_bfloat16* feat, float* featf, float* A_blk, const float* transl, float* joints,
+                    cudaStream_t st);
 int launch_pose_bwd(const DevModel& m, const float* betas, const float* pose, bool axis_angle, int b0, int nb, int S,
                     const float* dA_part, int n_dA_parts, const float* dtr_part, const float* dfeat_part,
-                    int n_dfeat_parts, const float* dJposed_T, float* grad_betas, float* grad_pose,
+                    int n_dfeat_parts, const float* dJ, float* grad_betas, float* grad_pose,
                     float* grad_transl, cudaStream_t st);
 
 int launch_blend_fwd_simt(const DevModel& m, const float* featf, int S, int Sw, float* vpT, int row_begin,
@@ -183,12 +193,13 @@ int launch_lbs_bwd(const DevModel& m, const float* vpT, int S, int Sw, const flo
                    const float* grad_verts, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_part,
                    float* dtr_part, int nsplit, cudaStream_t st);
 
-int launch_joints_fwd(const DevModel& m, const float* vpT, int S, const float* A_T, const float* jposed_T, int b0,
-                      int nb, const float* transl, const float* cam, float* joints, float* joints2d,
+int launch_joints_fwd(const DevModel& m, const float* vpB, int S, const float* A_blk, int b0, int nb,
+                      const float* transl, float* joints, cudaStream_t st);
+int joints_bwd_parts(const DevModel& m);
+int launch_joints_bwd(const DevModel& m, const float* vpB, int S, int Sw, const float* A_blk, int b0, int nb,
+                      const float* dJ, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_part, float* dtr_part,
                       cudaStream_t st);
-int launch_joints_bwd(const DevModel& m, const float* vpT, int S, int Sw, const float* A_T, int b0, int nb,
-                      const float* cam, const float* joints, const float* grad_joints,
-                      const float* grad_joints2d, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_part,
-                      float* dtr_part, float* dJposed_T, float* grad_cam, cudaStream_t st);
+int launch_joint_grad_total(const float* joints, const float* cam, const float* gj, const float* g2d, float* dJ,
+                            float* gcam, int B, int nj, cudaStream_t st);
 
 }  // namespace b200smpl

@@ -1,234 +1,229 @@
-// Joint outputs: the 90-joint superset of
-// models/smpl_official.py:27-41 -- 24 posed chain joints, 21 joints picked from vertices
-// (smplx VertexJointSelector), 45 joints regressed from vertices (J_regressor_extra / cocoplus /
-// h36m) -- plus transl and the optional weak-perspective reprojection (utils/cam_utils.py:5-26).
+// Joint outputs: the 66 non-chain joints of the 90-joint
+// superset of models/smpl_official.py:27-41 -- 21 joints picked from vertices (smplx
+// VertexJointSelector) and 45 joints regressed from vertices (J_regressor_extra / cocoplus / h36m).
 //
 // No vertex is re-read: a regressed joint  sum_v Jr[j][v] * skin(v)  is rewritten at pack time as
 //   sum_i  A_i . [ q_ji ; c_ji ],   q_ji = sum_v Jr[j][v] w_vi p_v  (linear in the blend features),
-// so the q_ji are extra "virtual" rows of the blend GEMM and a joint costs a handful of 3x4
-// transforms here.  Picked joints are virtual copies of their vertex's rows.  lane = body.
-#include "common.cuh"
+// so the q_ji are extra "virtual" rows of the blend GEMM, grouped 32 q-groups (96 rows) per virtual
+// tile, and a joint costs a handful of 3x4 transforms.  These kernels are the skinning kernels of
+// lbs.cu specialised to virtual tiles: lane = body, group transforms in shared memory via one TMA
+// bulk copy, q rows prefetched from the group-blocked blend output, results transposed through a
+// [96][33] shared tile and written as contiguous row segments of joints (B, 90, 3) / dvp.
+// The 24 chain joints are written by the pose kernel; reprojection is the orthographic kernel.
+#include "skin_common.cuh"
 
 namespace b200smpl {
 
-constexpr int JT_WARPS = 8;
-constexpr int JT_THREADS = JT_WARPS * 32;
+constexpr int JW = 4;                       // warps (= virtual tiles) per CTA
+constexpr int JT = JW * 32;
+constexpr size_t JFWD_SMEM = (size_t)(AG_WORDS + JW * TTILE_WORDS) * 4 + 16;
+constexpr size_t JBWD_SMEM = (size_t)(2 * AG_WORDS + 96 + JW * 2 * TTILE_WORDS) * 4 + 16;
 
-__global__ void __launch_bounds__(JT_THREADS)
-joints_fwd_kernel(DevModel m, const float* __restrict__ vpT, int S, const float* __restrict__ A_T,
-                  const float* __restrict__ jposed_T, int b0, int nb, const float* __restrict__ transl,
-                  const float* __restrict__ cam, float* __restrict__ joints, float* __restrict__ joints2d) {
-  extern __shared__ float smem[];
-  const int ncol = m.njout * 3;
-  const int pitch = ncol | 1;                          // odd pitch -> conflict-free column access by lane
-  float* sJ = smem;                                    // [32][pitch]
-  float* sCam = smem + 32 * pitch;                     // [32][3]
+__global__ void __launch_bounds__(JT, 1)
+joints_fwd_kernel(DevModel m, const float* __restrict__ vpB, int G, const float* __restrict__ A_blk, int b0, int nb,
+                  const float* __restrict__ transl, float* __restrict__ joints) {
+  extern __shared__ __align__(128) float smem[];
+  float* A_s = smem;
+  float* tiles = smem + AG_WORDS;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tiles + JW * TTILE_WORDS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col0 = blockIdx.x * 32;
-  const int col = col0 + lane;
-  const int gb0 = b0 + col0;
-  const int b = gb0 + lane;
-  const bool live = col < nb;
+  const int g = blockIdx.x, col0 = g * 32, gb0 = b0 + col0;
+  const int tv = blockIdx.y * JW + warp;
+  if (threadIdx.x == 0) fetch_group_transforms(A_s, A_blk, g, bar);
+  float q[96];
+  const bool active = tv < m.ntv;
+  if (active) {
+    const float* chunk = vpB + ((size_t)(m.ntiles + tv) * G + g) * CHUNK_WORDS + lane;
+#pragma unroll
+    for (int i = 0; i < 96; ++i) q[i] = ld_stream(chunk + i * 32);
+  }
   float tx = 0.f, ty = 0.f, tz = 0.f;
-  if (transl != nullptr && live) {
-    tx = transl[b * 3 + 0];
-    ty = transl[b * 3 + 1];
-    tz = transl[b * 3 + 2];
-  }
-  if (warp == 0 && cam != nullptr) {
-    sCam[lane * 3 + 0] = live ? cam[b * 3 + 0] : 0.f;
-    sCam[lane * 3 + 1] = live ? cam[b * 3 + 1] : 0.f;
-    sCam[lane * 3 + 2] = live ? cam[b * 3 + 2] : 0.f;
-  }
-  // chain joints
-  for (int r = warp; r < NJ * 3; r += JT_WARPS) {
-    const float t = (r % 3 == 0) ? tx : ((r % 3 == 1) ? ty : tz);
-    sJ[lane * pitch + r] = jposed_T[(size_t)r * S + col] + t;
-  }
-  // picked + regressed joints
-  for (int J = NJ + warp; J < m.njout; J += JT_WARPS) {
-    float x = tx, y = ty, z = tz;
-    const int t0 = m.term_ptr[J - NJ], t1 = m.term_ptr[J - NJ + 1];
-    for (int t = t0; t < t1; ++t) {
-      const int i = m.term_joint[t];
-      const size_t q = (size_t)m.term_qrow[t];
-      const float c = m.term_c[t];
-      const float qx = vpT[q * S + col], qy = vpT[(q + 1) * S + col], qz = vpT[(q + 2) * S + col];
-      const float* a = A_T + (size_t)(i * AELEMS) * S + col;
-      x += a[0] * qx + a[(size_t)1 * S] * qy + a[(size_t)2 * S] * qz + a[(size_t)3 * S] * c;
-      y += a[(size_t)4 * S] * qx + a[(size_t)5 * S] * qy + a[(size_t)6 * S] * qz + a[(size_t)7 * S] * c;
-      z += a[(size_t)8 * S] * qx + a[(size_t)9 * S] * qy + a[(size_t)10 * S] * qz + a[(size_t)11 * S] * c;
-    }
-    sJ[lane * pitch + J * 3 + 0] = x;
-    sJ[lane * pitch + J * 3 + 1] = y;
-    sJ[lane * pitch + J * 3 + 2] = z;
+  if (transl != nullptr && col0 + lane < nb) {
+    const float* t = transl + (size_t)(gb0 + lane) * 3;
+    tx = t[0]; ty = t[1]; tz = t[2];
   }
   __syncthreads();
-  const int nrows = min(32, nb - col0);
-  for (int idx = threadIdx.x; idx < nrows * ncol; idx += JT_THREADS) {
-    const int r = idx / ncol, c = idx - r * ncol;
-    joints[(size_t)gb0 * ncol + idx] = sJ[r * pitch + c];
-  }
-  if (joints2d != nullptr && cam != nullptr) {
-    const int n2 = m.njout * 2;
-    for (int idx = threadIdx.x; idx < nrows * n2; idx += JT_THREADS) {
-      const int r = idx / n2, c = idx - r * n2;
-      const int J = c >> 1, k = c & 1;
-      const float s = sCam[r * 3 + 0], t = sCam[r * 3 + 1 + k];
-      joints2d[(size_t)gb0 * n2 + idx] = s * (sJ[r * pitch + J * 3 + k] + t);
+  mbar_wait(bar, 0);
+  if (!active) return;
+  float* out_s = tiles + warp * TTILE_WORDS;
+  float* out_lane = out_s + lane;
+  const uint32_t* meta = m.qmeta + tv * 32;
+  const float* coef = m.qcoef + tv * 32;
+  float a[AELEMS];
+  float x = tx, y = ty, z = tz;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const uint32_t mt = __ldg(meta + i);
+    if (!(mt & (1u << 14))) continue;
+    if ((mt & (1u << 5)) || i == 0) load_slot(a, A_s, mt & 31, lane);
+    const float c = __ldg(coef + i);
+    const float qx = q[i * 3], qy = q[i * 3 + 1], qz = q[i * 3 + 2];
+    x += fmaf(a[0], qx, fmaf(a[1], qy, fmaf(a[2], qz, a[3] * c)));
+    y += fmaf(a[4], qx, fmaf(a[5], qy, fmaf(a[6], qz, a[7] * c)));
+    z += fmaf(a[8], qx, fmaf(a[9], qy, fmaf(a[10], qz, a[11] * c)));
+    if (mt & (1u << 13)) {                                 // last term of this joint
+      float* o = out_lane + ((mt >> 8) & 31) * (3 * TPITCH);
+      o[0] = x; o[TPITCH] = y; o[2 * TPITCH] = z;
+      x = tx; y = ty; z = tz;
     }
   }
+  __syncwarp();
+  const int ncols = m.vt_nj[tv] * 3;
+  const int nrows = min(32, nb - col0);
+  const size_t ncol_all = (size_t)m.njout * 3;
+  float* dst0 = joints + (size_t)gb0 * ncol_all + (size_t)(NJ + m.vt_j0[tv]) * 3;
+  for (int r = 0; r < nrows; ++r)
+    for (int c = lane; c < ncols; c += 32) dst0[(size_t)r * ncol_all + c] = out_s[c * TPITCH + r];
 }
 
-__device__ __forceinline__ void store_hi_lo(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, float x) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(x);
-  hi[idx] = h;
-  if (lo != nullptr) lo[idx] = __float2bfloat16_rn(x - __bfloat162float(h));
-}
-
-// backward of the above.  dJ_total = grad_joints + [s*g2d_x, s*g2d_y, 0]
-//   chain joints (J < 24): dJposed_T[r][b] (consumed by pose_bwd)
-//   other joints: dq -> virtual columns of dvp ; dA -> dA_part (this kernel's own partial) ;
-//   dtransl partial = sum_J dJ_total ; dcam from the 2D gradient.
-__global__ void __launch_bounds__(JT_THREADS)
-joints_bwd_kernel(DevModel m, const float* __restrict__ vpT, int S, const float* __restrict__ A_T, int b0,
-                  int nb, const float* __restrict__ cam, const float* __restrict__ joints,
-                  const float* __restrict__ grad_joints, const float* __restrict__ grad_joints2d,
-                  __nv_bfloat16* __restrict__ dvp_hi, __nv_bfloat16* __restrict__ dvp_lo,
-                  float* __restrict__ dA_part, float* __restrict__ dtr_part, float* __restrict__ dJposed_T,
-                  float* __restrict__ grad_cam) {
-  extern __shared__ float smem[];
-  const int ncol = m.njout * 3;
-  const int pitch = ncol | 1;
-  float* sG = smem;                                    // [32][pitch]   total joint gradient
-  float* sdA = sG + 32 * pitch;                        // [288][32]
-  float* sCam = sdA + NJ * AELEMS * 32;                // [32][3]
-  float* sdCam = sCam + 96;                            // [32][3]
-  float* sdT = sdCam + 96;                             // [3][32]
+// backward over virtual tiles.  dJ: total joint gradient (B, NJout, 3).
+//   dq -> virtual columns of dvp ; dA -> dA_part[blockIdx.y] ; dtransl partial = sum over the tile's joints
+__global__ void __launch_bounds__(JT, 1)
+joints_bwd_kernel(DevModel m, const float* __restrict__ vpB, int G, const float* __restrict__ A_blk, int b0, int nb,
+                  const float* __restrict__ dJ, __nv_bfloat16* __restrict__ dvp_hi,
+                  __nv_bfloat16* __restrict__ dvp_lo, float* __restrict__ dA_part, float* __restrict__ dtr_part) {
+  extern __shared__ __align__(128) float smem[];
+  float* A_s = smem;
+  float* dA_s = A_s + AG_WORDS;
+  float* dtr_s = dA_s + AG_WORDS;
+  float* tiles = dtr_s + 96;                               // [JW][2][96][33]: joint gradients | packed dq
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tiles + JW * 2 * TTILE_WORDS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col0 = blockIdx.x * 32;
-  const int col = col0 + lane;
-  const int gb0 = b0 + col0;
-  const int b = gb0 + lane;
-  const int nrows = min(32, nb - col0);
-  const bool has2d = grad_joints2d != nullptr && cam != nullptr;
-
-  for (int r = warp; r < NJ * AELEMS; r += JT_WARPS) sdA[r * 32 + lane] = 0.f;
-  if (warp == 0) {
-    const bool live = col < nb;
+  const int g = blockIdx.x, col0 = g * 32, gb0 = b0 + col0;
+  const int tv = blockIdx.y * JW + warp;
+  const bool active = tv < m.ntv;
+  if (threadIdx.x == 0) fetch_group_transforms(A_s, A_blk, g, bar);
+  float q[96];
+  if (active) {
+    const float* chunk = vpB + ((size_t)(m.ntiles + tv) * G + g) * CHUNK_WORDS + lane;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      sCam[lane * 3 + k] = (cam != nullptr && live) ? cam[b * 3 + k] : 0.f;
-      sdCam[lane * 3 + k] = 0.f;
-      sdT[k * 32 + lane] = 0.f;
-    }
+    for (int i = 0; i < 96; ++i) q[i] = ld_stream(chunk + i * 32);
   }
+  for (int r = threadIdx.x; r < AG_WORDS; r += JT) dA_s[r] = 0.f;
+  if (threadIdx.x < 96) dtr_s[threadIdx.x] = 0.f;
   __syncthreads();
-  // stage total joint gradient, coalesced over the [32 bodies][njout*3] block
-  for (int idx = threadIdx.x; idx < 32 * ncol; idx += JT_THREADS) {
-    const int r = idx / ncol, c = idx - r * ncol;
-    float g = 0.f;
-    if (r < nrows) {
-      if (grad_joints != nullptr) g = grad_joints[(size_t)gb0 * ncol + idx];
-      if (has2d) {
-        const int J = c / 3, k = c - J * 3;
-        if (k < 2) {
-          const float g2 = grad_joints2d[((size_t)(gb0 + r) * m.njout + J) * 2 + k];
-          const float s = sCam[r * 3 + 0];
-          g += s * g2;
-          // d/ds : g2 * (x + t_k) ; d/dt_k : s * g2
-          const float xk = joints[(size_t)gb0 * ncol + idx];
-          atomicAdd(&sdCam[r * 3 + 0], g2 * (xk + sCam[r * 3 + 1 + k]));
-          atomicAdd(&sdCam[r * 3 + 1 + k], s * g2);
-        }
-      }
+  mbar_wait(bar, 0);
+  if (active) {
+    float* g_s = tiles + warp * 2 * TTILE_WORDS;
+    uint32_t* q_s = reinterpret_cast<uint32_t*>(g_s + TTILE_WORDS);
+    const int ncols = m.vt_nj[tv] * 3;
+    const int nrows = min(32, nb - col0);
+    const size_t ncol_all = (size_t)m.njout * 3;
+    // stage the gradients of this tile's joints: columns = 3 nj floats of each body row
+    {
+      const float* src0 = dJ + (size_t)gb0 * ncol_all + (size_t)(NJ + m.vt_j0[tv]) * 3;
+      for (int r = 0; r < 32; ++r)
+        for (int c = lane; c < ncols; c += 32)
+          g_s[c * TPITCH + r] = (r < nrows) ? ld_stream(src0 + (size_t)r * ncol_all + c) : 0.f;
     }
-    sG[r * pitch + c] = g;
-  }
-  __syncthreads();
-  // chain joints: transpose out
-  for (int r = warp; r < NJ * 3; r += JT_WARPS) dJposed_T[(size_t)r * S + col] = sG[lane * pitch + r];
-  // translation partial: sum over all joints
-  {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int J = warp; J < m.njout; J += JT_WARPS) {
-      s0 += sG[lane * pitch + J * 3 + 0];
-      s1 += sG[lane * pitch + J * 3 + 1];
-      s2 += sG[lane * pitch + J * 3 + 2];
-    }
-    atomicAdd(&sdT[lane], s0);
-    atomicAdd(&sdT[32 + lane], s1);
-    atomicAdd(&sdT[64 + lane], s2);
-  }
-  // picked / regressed joints
-  for (int J = NJ + warp; J < m.njout; J += JT_WARPS) {
-    const float gx = sG[lane * pitch + J * 3 + 0], gy = sG[lane * pitch + J * 3 + 1],
-                gz = sG[lane * pitch + J * 3 + 2];
-    const int t0 = m.term_ptr[J - NJ], t1 = m.term_ptr[J - NJ + 1];
-    int t = t0;
-    while (t < t1) {
-      const int qrow = m.term_qrow[t];
-      const size_t q = (size_t)qrow;
-      const float qx = vpT[q * S + col], qy = vpT[(q + 1) * S + col], qz = vpT[(q + 2) * S + col];
-      float dx = 0.f, dy = 0.f, dz = 0.f;
-      // all terms that share this q-group are consecutive
-      for (; t < t1 && m.term_qrow[t] == qrow; ++t) {
-        const int i = m.term_joint[t];
-        const float c = m.term_c[t];
-        const float* a = A_T + (size_t)(i * AELEMS) * S + col;
-        dx += a[0] * gx + a[(size_t)4 * S] * gy + a[(size_t)8 * S] * gz;
-        dy += a[(size_t)1 * S] * gx + a[(size_t)5 * S] * gy + a[(size_t)9 * S] * gz;
-        dz += a[(size_t)2 * S] * gx + a[(size_t)6 * S] * gy + a[(size_t)10 * S] * gz;
-        float* d = sdA + (i * AELEMS) * 32 + lane;
-        atomicAdd(d + 0 * 32, gx * qx); atomicAdd(d + 1 * 32, gx * qy); atomicAdd(d + 2 * 32, gx * qz);
-        atomicAdd(d + 3 * 32, gx * c);
-        atomicAdd(d + 4 * 32, gy * qx); atomicAdd(d + 5 * 32, gy * qy); atomicAdd(d + 6 * 32, gy * qz);
-        atomicAdd(d + 7 * 32, gy * c);
-        atomicAdd(d + 8 * 32, gz * qx); atomicAdd(d + 9 * 32, gz * qy); atomicAdd(d + 10 * 32, gz * qz);
-        atomicAdd(d + 11 * 32, gz * c);
-      }
-      const size_t o = (size_t)col * m.n_pad + q;
-      store_hi_lo(dvp_hi, dvp_lo, o + 0, dx);
-      store_hi_lo(dvp_hi, dvp_lo, o + 1, dy);
-      store_hi_lo(dvp_hi, dvp_lo, o + 2, dz);
-    }
-  }
-  __syncthreads();
-  for (int r = warp; r < NJ * AELEMS; r += JT_WARPS) dA_part[(size_t)r * S + col] = sdA[r * 32 + lane];
-  if (warp < 3) dtr_part[(size_t)warp * S + col] = sdT[warp * 32 + lane];
-  if (grad_cam != nullptr && warp == 0 && col < nb) {
+    __syncwarp();
+    const uint32_t* meta = m.qmeta + tv * 32;
+    const float* coef = m.qcoef + tv * 32;
+    float a[9], d[AELEMS];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) grad_cam[b * 3 + k] = sdCam[lane * 3 + k];
+    for (int e = 0; e < AELEMS; ++e) d[e] = 0.f;
+    int jcur = 0;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const uint32_t mt = __ldg(meta + i);
+      uint32_t* qo = q_s + (i * 3) * TPITCH + lane;
+      if (!(mt & (1u << 14))) {                            // dummy slot: its dvp columns must be 0
+        qo[0] = 0u; qo[TPITCH] = 0u; qo[2 * TPITCH] = 0u;
+        continue;
+      }
+      if ((mt & (1u << 5)) || i == 0) {
+        if (i) flush_slot(d, dA_s, jcur, lane);
+        jcur = mt & 31;
+        load_rot(a, A_s, jcur, lane);
+      }
+      const float c = __ldg(coef + i);
+      const float* gj = g_s + ((mt >> 8) & 31) * (3 * TPITCH) + lane;
+      const float gx = gj[0], gy = gj[TPITCH], gz = gj[2 * TPITCH];
+      const float qx = q[i * 3], qy = q[i * 3 + 1], qz = q[i * 3 + 2];
+      qo[0] = pack_hi_lo(fmaf(a[0], gx, fmaf(a[3], gy, a[6] * gz)));
+      qo[TPITCH] = pack_hi_lo(fmaf(a[1], gx, fmaf(a[4], gy, a[7] * gz)));
+      qo[2 * TPITCH] = pack_hi_lo(fmaf(a[2], gx, fmaf(a[5], gy, a[8] * gz)));
+      d[0] = fmaf(gx, qx, d[0]); d[1] = fmaf(gx, qy, d[1]); d[2] = fmaf(gx, qz, d[2]); d[3] = fmaf(gx, c, d[3]);
+      d[4] = fmaf(gy, qx, d[4]); d[5] = fmaf(gy, qy, d[5]); d[6] = fmaf(gy, qz, d[6]); d[7] = fmaf(gy, c, d[7]);
+      d[8] = fmaf(gz, qx, d[8]); d[9] = fmaf(gz, qy, d[9]); d[10] = fmaf(gz, qz, d[10]); d[11] = fmaf(gz, c, d[11]);
+      if (mt & (1u << 13)) { sx += gx; sy += gy; sz += gz; }
+    }
+    flush_slot(d, dA_s, jcur, lane);
+    atomicAdd(&dtr_s[lane], sx);
+    atomicAdd(&dtr_s[32 + lane], sy);
+    atomicAdd(&dtr_s[64 + lane], sz);
+    __syncwarp();
+    flush_dvp_tile(q_s, dvp_hi, dvp_lo, (size_t)col0, m.n_pad, (size_t)m.n_virt0 + (size_t)tv * 96, lane);
   }
+  __syncthreads();
+  float* dA_out = dA_part + ((size_t)blockIdx.y * G + g) * AG_WORDS;
+  for (int r = threadIdx.x; r < AG_WORDS; r += JT) dA_out[r] = dA_s[r];
+  if (threadIdx.x < 96) dtr_part[((size_t)blockIdx.y * G + g) * 96 + threadIdx.x] = dtr_s[threadIdx.x];
 }
 
-int launch_joints_fwd(const DevModel& m, const float* vpT, int S, const float* A_T, const float* jposed_T, int b0,
-                      int nb, const float* transl, const float* cam, float* joints, float* joints2d,
-                      cudaStream_t st) {
-  if (nb <= 0) return 0;
-  const int pitch = (m.njout * 3) | 1;
-  const size_t smem = (size_t)(32 * pitch + 96) * sizeof(float);
-  B200_CUDA_TRY(cudaFuncSetAttribute(joints_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  LaunchTimer _timer_211("joints_fwd", st);
-  joints_fwd_kernel<<<(nb + 31) / 32, JT_THREADS, smem, st>>>(m, vpT, S, A_T, jposed_T, b0, nb, transl, cam, joints,
-                                                              joints2d);
+// total joint gradient when a 2D reprojection gradient is present:
+//   dJ = grad_joints + [s g2d_x, s g2d_y, 0] ;  dcam = [sum g2d.(xy + t), s sum g2d_x, s sum g2d_y]
+__global__ void __launch_bounds__(128)
+joint_grad_total_kernel(const float* __restrict__ joints, const float* __restrict__ cam,
+                        const float* __restrict__ gj, const float* __restrict__ g2d, float* __restrict__ dJ,
+                        float* __restrict__ gcam, int nj) {
+  __shared__ float sh[3][4];
+  const int b = blockIdx.x;
+  const float s = cam[b * 3], tx = cam[b * 3 + 1], ty = cam[b * 3 + 2];
+  float gs = 0.f, gtx = 0.f, gty = 0.f;
+  for (int j = threadIdx.x; j < nj; j += blockDim.x) {
+    const size_t o3 = ((size_t)b * nj + j) * 3, o2 = ((size_t)b * nj + j) * 2;
+    const float gu = g2d[o2], gv = g2d[o2 + 1];
+    dJ[o3] = (gj ? gj[o3] : 0.f) + s * gu;
+    dJ[o3 + 1] = (gj ? gj[o3 + 1] : 0.f) + s * gv;
+    dJ[o3 + 2] = gj ? gj[o3 + 2] : 0.f;
+    gs += gu * (joints[o3] + tx) + gv * (joints[o3 + 1] + ty);
+    gtx += s * gu;
+    gty += s * gv;
+  }
+  float v[3] = {gs, gtx, gty};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = v[k];
+  }
+  __syncthreads();
+  if (gcam != nullptr && threadIdx.x < 3) gcam[b * 3 + threadIdx.x] = sh[threadIdx.x][0] + sh[threadIdx.x][1] + sh[threadIdx.x][2] + sh[threadIdx.x][3];
+}
+
+int joints_bwd_parts(const DevModel& m) { return (m.ntv + JW - 1) / JW; }
+
+int launch_joints_fwd(const DevModel& m, const float* vpB, int S, const float* A_blk, int b0, int nb,
+                      const float* transl, float* joints, cudaStream_t st) {
+  if (nb <= 0 || m.ntv == 0) return 0;
+  B200_CUDA_TRY(cudaFuncSetAttribute(joints_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JFWD_SMEM));
+  LaunchTimer _timer("joints_fwd", st);
+  joints_fwd_kernel<<<dim3((nb + 31) / 32, (m.ntv + JW - 1) / JW), JT, JFWD_SMEM, st>>>(m, vpB, S / 32, A_blk, b0, nb,
+                                                                                        transl, joints);
   B200_LAUNCH_CHECK("joints_fwd");
   return 0;
 }
 
 // Sw: active slab width (multiple of 32); absent bodies get zero dvp columns / partials.
-int launch_joints_bwd(const DevModel& m, const float* vpT, int S, int Sw, const float* A_T, int b0, int nb,
-                      const float* cam, const float* joints, const float* grad_joints,
-                      const float* grad_joints2d, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_part,
-                      float* dtr_part, float* dJposed_T, float* grad_cam, cudaStream_t st) {
-  const int pitch = (m.njout * 3) | 1;
-  const size_t smem = (size_t)(32 * pitch + NJ * AELEMS * 32 + 96 * 3) * sizeof(float);
-  B200_CUDA_TRY(cudaFuncSetAttribute(joints_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  LaunchTimer _timer_225("joints_bwd", st);
-  joints_bwd_kernel<<<Sw / 32, JT_THREADS, smem, st>>>(m, vpT, S, A_T, b0, nb, cam, joints, grad_joints,
-                                                       grad_joints2d, dvp_hi, dvp_lo, dA_part, dtr_part, dJposed_T,
-                                                       grad_cam);
+int launch_joints_bwd(const DevModel& m, const float* vpB, int S, int Sw, const float* A_blk, int b0, int nb,
+                      const float* dJ, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_part, float* dtr_part,
+                      cudaStream_t st) {
+  if (m.ntv == 0) return 0;
+  B200_CUDA_TRY(cudaFuncSetAttribute(joints_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JBWD_SMEM));
+  LaunchTimer _timer("joints_bwd", st);
+  joints_bwd_kernel<<<dim3(Sw / 32, (m.ntv + JW - 1) / JW), JT, JBWD_SMEM, st>>>(m, vpB, S / 32, A_blk, b0, nb, dJ,
+                                                                                 dvp_hi, dvp_lo, dA_part, dtr_part);
   B200_LAUNCH_CHECK("joints_bwd");
+  return 0;
+}
+
+int launch_joint_grad_total(const float* joints, const float* cam, const float* gj, const float* g2d, float* dJ,
+                            float* gcam, int B, int nj, cudaStream_t st) {
+  LaunchTimer _timer("joint_grad_total", st);
+  joint_grad_total_kernel<<<B, 128, 0, st>>>(joints, cam, gj, g2d, dJ, gcam, nj);
+  B200_LAUNCH_CHECK("joint_grad_total");
   return 0;
 }
 

@@ -109,9 +109,64 @@ int pack_model(const b200smpl_model_desc* d, HostArrays& h, DevModel& dm, std::s
     }
     for (auto& kv : group_of_joint) joint_terms[nvj + r].push_back({kv.first, kv.second, (float)csum[kv.first]});
   }
-  const int nq = (int)group_src.size();
+  // ---- lay the q-groups out in 32-group "virtual tiles" (96 blend rows each): the groups of one
+  // output joint are consecutive and never straddle a tile (dummy groups pad the gap), so a warp
+  // that owns a tile can finish whole joints.
+  for (int J = 0; J < nvj + nreg; ++J)
+    if (joint_terms[J].empty()) {                          // all-zero regressor row: one null term keeps the
+      joint_terms[J].push_back({0, (int)group_src.size(), 0.f});   // joint on the common path (value = transl)
+      group_src.emplace_back();
+    }
+  std::vector<int> group_slot(group_src.size(), -1);     // group -> slot (position) in the padded layout
+  std::vector<uint32_t> qmeta;                            // per slot: joint | reload<<5 | jl<<8 | last<<13 | valid<<14
+  std::vector<float> qcoef;
+  std::vector<int32_t> vt_j0, vt_nj;
+  {
+    int prev_joint = -1;
+    for (int J = 0; J < nvj + nreg; ++J) {
+      auto& tv = joint_terms[J];
+      std::stable_sort(tv.begin(), tv.end(), [](const Term& a, const Term& b) { return a.joint < b.joint; });
+      const int k = (int)tv.size();
+      if (k == 0) continue;                               // joint with an all-zero regressor row: stays at transl
+      if (k > 32) { err = "a joint depends on more than 32 skinning joints"; return B200SMPL_ERR_INVALID; }
+      int pos = (int)qmeta.size();
+      if (pos % 32 + k > 32) {                            // pad to the next tile
+        while (qmeta.size() % 32) { qmeta.push_back(0u); qcoef.push_back(0.f); }
+        pos = (int)qmeta.size();
+      }
+      const int tile = pos / 32;
+      if (pos % 32 == 0) { vt_j0.push_back(J); vt_nj.push_back(0); prev_joint = -1; }
+      if (vt_j0[tile] + vt_nj[tile] != J) {               // joints of a tile must be consecutive
+        // a skipped (empty) joint in between: extend the range, its columns are written as transl
+        vt_nj[tile] = J - vt_j0[tile];
+      }
+      const int jl = J - vt_j0[tile];
+      if (jl >= 32) { err = "virtual tile joint range overflow"; return B200SMPL_ERR_INVALID; }
+      for (int t = 0; t < k; ++t) {
+        uint32_t mword = (uint32_t)tv[t].joint | ((tv[t].joint != prev_joint ? 1u : 0u) << 5) | ((uint32_t)jl << 8) |
+                         ((t == k - 1 ? 1u : 0u) << 13) | (1u << 14);
+        prev_joint = tv[t].joint;
+        group_slot[tv[t].group] = (int)qmeta.size();
+        qmeta.push_back(mword);
+        qcoef.push_back(tv[t].c);
+      }
+      vt_nj[tile] = jl + 1;
+    }
+    while (qmeta.size() % 32) { qmeta.push_back(0u); qcoef.push_back(0.f); }
+  }
+  const int ntv = (int)qmeta.size() / 32;
+  // re-index groups by slot: slot s owns blend rows n_virt0 + 3 s + k
+  {
+    std::vector<std::vector<std::pair<int, double>>> by_slot(qmeta.size());
+    for (size_t gi = 0; gi < group_src.size(); ++gi)
+      if (group_slot[gi] >= 0) by_slot[group_slot[gi]] = group_src[gi];
+    for (auto& jt : joint_terms)
+      for (auto& tm : jt) tm.group = group_slot[tm.group];
+    group_src.swap(by_slot);
+  }
+  const int nq = (int)group_src.size();                   // = 32 * ntv slots (dummy slots have zero rows)
   const int n_rows = n_virt0 + 3 * nq;
-  const int n_pad = round_up(n_rows, 128);
+  const int n_pad = round_up(std::max(n_rows, 1), 384);   // whole 128-row GEMM tiles and whole 96-row chunks
 
   // ---- fp32 rows W32[1+nf][n_pad]: row 0 template, 1..nb shapedirs, nb+1.. posedirs ----
   h.W32.assign((size_t)(1 + nf) * n_pad, 0.f);
@@ -256,6 +311,8 @@ int pack_model(const b200smpl_model_desc* d, HostArrays& h, DevModel& dm, std::s
   if (h.term_joint.empty()) { h.term_joint.push_back(0); h.term_qrow.push_back(0); h.term_c.push_back(0.f); }
 
   memset(&dm, 0, sizeof(dm));
+  h.qmeta = qmeta; h.qcoef = qcoef; h.vt_j0 = vt_j0; h.vt_nj = vt_nj;
+  dm.ntv = ntv;
   dm.V = V; dm.ntiles = ntiles; dm.n_real = 3 * V; dm.nq = nq; dm.n_virt0 = n_virt0; dm.n_rows = n_rows;
   dm.n_pad = n_pad; dm.njout = NJ + nvj + nreg; dm.nterms = h.term_ptr.back();
   dm.fl = fl; dm.chain = ch;

@@ -171,7 +171,7 @@ template <bool AA>
 __global__ void __launch_bounds__(POSE_THREADS)
 pose_fwd_kernel(DevModel m, const float* __restrict__ betas, const float* __restrict__ pose, int b0, int nb, int S,
                 __nv_bfloat16* __restrict__ feat, float* __restrict__ featf, float* __restrict__ A_T,
-                float* __restrict__ jposed_T) {
+                const float* __restrict__ transl, float* __restrict__ joints) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sOut = reinterpret_cast<float*>(smem_raw);                        // [OUT_ROWS][OUT_PITCH]
   __nv_bfloat16* sF_all = reinterpret_cast<__nv_bfloat16*>(sOut + OUT_ROWS * OUT_PITCH);  // [warps][pitch]
@@ -236,42 +236,50 @@ pose_fwd_kernel(DevModel m, const float* __restrict__ betas, const float* __rest
     __syncwarp();
   }
   __syncthreads();
-  const int bcol = blockIdx.x * 32 + lane;
-  for (int r = warp; r < OUT_ROWS; r += POSE_WARPS) {
-    const float v = sOut[r * OUT_PITCH + lane];
-    if (r < NJ * AELEMS) A_T[(size_t)r * S + bcol] = v;
-    else jposed_T[(size_t)(r - NJ * AELEMS) * S + bcol] = v;
+  // group-blocked output A_blk[group][288][32] (one contiguous 36 KB block per 32 bodies)
+  (void)S;
+  for (int r = warp; r < NJ * AELEMS; r += POSE_WARPS)
+    A_T[((size_t)blockIdx.x * NJ * AELEMS + r) * 32 + lane] = sOut[r * OUT_PITCH + lane];
+  // the 24 posed chain joints (+ transl) go straight into joints[:, 0:24] as 288 B row segments
+  if (joints != nullptr) {
+    const size_t ncol_all = (size_t)m.njout * 3;
+    for (int idx = threadIdx.x; idx < 32 * NJ * 3; idx += POSE_THREADS) {
+      const int body = idx / (NJ * 3), col = idx - body * (NJ * 3);
+      const int sc = blockIdx.x * 32 + body;
+      if (sc < nb) {
+        const float t = transl != nullptr ? transl[(size_t)(b0 + sc) * 3 + col % 3] : 0.f;
+        joints[(size_t)(b0 + sc) * ncol_all + col] = sOut[(NJ * AELEMS + col) * OUT_PITCH + body] + t;
+      }
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // backward of the pose stage.  Inputs (all body-fastest, pitch Bp):
-//   dA_part[p][288][S] partial sums of dL/dA, dtr_part[p][3][S], dJposed_T[72][S] (may be null),
-//   dfeat_part[p][S][nf_pad] : dL/d[beta | pose_feature] from the blend-GEMM backward.
-// All are slab-local (column = body - b0).
+//   dA_part[p][G][288][32] partial sums of dL/dA, dtr_part[p][G][3][32] (group-blocked, slab-local),
+//   dfeat_part[p][S][nf_pad] : dL/d[beta | pose_feature] from the blend-GEMM backward,
+//   dJ (B, NJout, 3) total joint gradient (may be null): its first 24 joints are the chain joints.
 // ---------------------------------------------------------------------------------------------
-constexpr int IN_ROWS = NJ * AELEMS + NJ * 3 + 3;
+constexpr int IN_ROWS = NJ * AELEMS + 3;
 
 template <bool AA>
 __global__ void __launch_bounds__(POSE_THREADS)
 pose_bwd_kernel(DevModel m, const float* __restrict__ betas, const float* __restrict__ pose, int b0, int nb, int S,
                 const float* __restrict__ dA_part, int n_dA_parts, const float* __restrict__ dtr_part,
-                const float* __restrict__ dfeat_part, int n_dfeat_parts, const float* __restrict__ dJposed_T,
+                const float* __restrict__ dfeat_part, int n_dfeat_parts, const float* __restrict__ dJ,
                 float* __restrict__ grad_betas, float* __restrict__ grad_pose, float* __restrict__ grad_transl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sIn = reinterpret_cast<float*>(smem_raw);                         // [IN_ROWS][OUT_PITCH]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const FeatLayout fl = m.fl;
-  const int bcol = blockIdx.x * 32 + lane;
+  const int G = S / 32, g = blockIdx.x;                  // group-blocked partials [part][group][rows][32]
   for (int r = warp; r < IN_ROWS; r += POSE_WARPS) {
     float v = 0.f;
     if (r < NJ * AELEMS) {
-      for (int p = 0; p < n_dA_parts; ++p) v += dA_part[((size_t)p * NJ * AELEMS + r) * S + bcol];
-    } else if (r < NJ * AELEMS + NJ * 3) {
-      if (dJposed_T != nullptr) v = dJposed_T[(size_t)(r - NJ * AELEMS) * S + bcol];
+      for (int p = 0; p < n_dA_parts; ++p) v += dA_part[(((size_t)p * G + g) * NJ * AELEMS + r) * 32 + lane];
     } else {
-      const int k = r - NJ * AELEMS - NJ * 3;
-      for (int p = 0; p < n_dA_parts; ++p) v += dtr_part[((size_t)p * 3 + k) * S + bcol];
+      const int k = r - NJ * AELEMS;
+      for (int p = 0; p < n_dA_parts; ++p) v += dtr_part[(((size_t)p * G + g) * 3 + k) * 32 + lane];
     }
     sIn[r * OUT_PITCH + lane] = v;
   }
@@ -287,7 +295,7 @@ pose_bwd_kernel(DevModel m, const float* __restrict__ betas, const float* __rest
     chain_forward<AA>(m, betas, pose, b, lane, true, L, raa);
     const int j = lane < NJ ? lane : 0;
     const bool act = lane < NJ;
-    float dGR[9], dGt[3], dJr[3];
+    float dGR[9], dGt[3], dJr[3], dJp[3];
     {
       float dAr[12];
 #pragma unroll
@@ -295,7 +303,8 @@ pose_bwd_kernel(DevModel m, const float* __restrict__ betas, const float* __rest
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const float dat = dAr[r * 4 + 3];
-        dGt[r] = dat + (act ? sIn[(NJ * AELEMS + j * 3 + r) * OUT_PITCH + bl] : 0.f);
+        dJp[r] = (act && dJ != nullptr) ? dJ[((size_t)b * m.njout + j) * 3 + r] : 0.f;
+        dGt[r] = dat + dJp[r];
 #pragma unroll
         for (int c = 0; c < 3; ++c) dGR[r * 3 + c] = dAr[r * 4 + c] - dat * L.Jr[c];
       }
@@ -391,24 +400,32 @@ pose_bwd_kernel(DevModel m, const float* __restrict__ betas, const float* __rest
         for (int e = 0; e < 9; ++e) grad_pose[(size_t)b * (NJ * 9) + j * 9 + e] = dRl[e];
       }
     }
-    if (grad_transl != nullptr && lane < 3)
-      grad_transl[(size_t)b * 3 + lane] = sIn[(NJ * AELEMS + NJ * 3 + lane) * OUT_PITCH + bl];
+    if (grad_transl != nullptr) {                     // skinning / joint partials + the chain joints' own gradient
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        float t = dJp[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == r) grad_transl[(size_t)b * 3 + r] = t + sIn[(NJ * AELEMS + r) * OUT_PITCH + bl];
+      }
+    }
   }
 }
 
 // Sw = active slab width (multiple of 32, >= nb); columns in [nb, Sw) are written as zeros
 int launch_pose_fwd(const DevModel& m, const float* betas, const float* pose, bool axis_angle, int b0, int nb, int S,
-                    int Sw, __nv_bfloat16* feat, float* featf, float* A_T, float* jposed_T, cudaStream_t st) {
+                    int Sw, __nv_bfloat16* feat, float* featf, float* A_T, const float* transl, float* joints,
+                    cudaStream_t st) {
   const size_t smem = (size_t)OUT_ROWS * OUT_PITCH * sizeof(float) + (size_t)POSE_WARPS * m.fl.pitch * 2;
   const int grid = Sw / 32;
   if (axis_angle) {
     B200_CUDA_TRY(cudaFuncSetAttribute(pose_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LaunchTimer _timer_405("pose_fwd", st);
-    pose_fwd_kernel<true><<<grid, POSE_THREADS, smem, st>>>(m, betas, pose, b0, nb, S, feat, featf, A_T, jposed_T);
+    pose_fwd_kernel<true><<<grid, POSE_THREADS, smem, st>>>(m, betas, pose, b0, nb, S, feat, featf, A_T, transl, joints);
   } else {
     B200_CUDA_TRY(cudaFuncSetAttribute(pose_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LaunchTimer _timer_408("pose_fwd", st);
-    pose_fwd_kernel<false><<<grid, POSE_THREADS, smem, st>>>(m, betas, pose, b0, nb, S, feat, featf, A_T, jposed_T);
+    pose_fwd_kernel<false><<<grid, POSE_THREADS, smem, st>>>(m, betas, pose, b0, nb, S, feat, featf, A_T, transl, joints);
   }
   B200_LAUNCH_CHECK("pose_fwd");
   return 0;
@@ -416,7 +433,7 @@ int launch_pose_fwd(const DevModel& m, const float* betas, const float* pose, bo
 
 int launch_pose_bwd(const DevModel& m, const float* betas, const float* pose, bool axis_angle, int b0, int nb, int S,
                     const float* dA_part, int n_dA_parts, const float* dtr_part, const float* dfeat_part,
-                    int n_dfeat_parts, const float* dJposed_T, float* grad_betas, float* grad_pose,
+                    int n_dfeat_parts, const float* dJ, float* grad_betas, float* grad_pose,
                     float* grad_transl, cudaStream_t st) {
   if (nb <= 0) return 0;
   const size_t smem = (size_t)IN_ROWS * OUT_PITCH * sizeof(float);
@@ -425,13 +442,13 @@ int launch_pose_bwd(const DevModel& m, const float* betas, const float* pose, bo
     B200_CUDA_TRY(cudaFuncSetAttribute(pose_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LaunchTimer _timer_423("pose_bwd", st);
     pose_bwd_kernel<true><<<grid, POSE_THREADS, smem, st>>>(m, betas, pose, b0, nb, S, dA_part, n_dA_parts, dtr_part,
-                                                            dfeat_part, n_dfeat_parts, dJposed_T, grad_betas,
+                                                            dfeat_part, n_dfeat_parts, dJ, grad_betas,
                                                             grad_pose, grad_transl);
   } else {
     B200_CUDA_TRY(cudaFuncSetAttribute(pose_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LaunchTimer _timer_428("pose_bwd", st);
     pose_bwd_kernel<false><<<grid, POSE_THREADS, smem, st>>>(m, betas, pose, b0, nb, S, dA_part, n_dA_parts, dtr_part,
-                                                             dfeat_part, n_dfeat_parts, dJposed_T, grad_betas,
+                                                             dfeat_part, n_dfeat_parts, dJ, grad_betas,
                                                              grad_pose, grad_transl);
   }
   B200_LAUNCH_CHECK("pose_bwd");

@@ -142,6 +142,32 @@ def test_packed_model_emulation_matches_oracle(host_engine, synthetic_model):
                 acc = acc + A[term_joint[k]] @ q
             joints[J] = acc
         np.testing.assert_allclose(joints, ref.joints[b].numpy(), atol=2e-7)
+        # ... and from the virtual-tile plan the GPU kernels walk (32 q-groups per tile)
+        qmeta = eng.debug_array("qmeta", np.uint32)
+        qcoef = eng.debug_array("qcoef", np.float32).astype(np.float64)
+        vt_j0 = eng.debug_array("vt_j0", np.int32)
+        vt_nj = eng.debug_array("vt_nj", np.int32)
+        assert len(qmeta) == 32 * len(vt_j0) == nq
+        joints2 = np.full((info.num_joints_out, 3), np.nan)
+        joints2[:24] = joints[:24]
+        for tv in range(len(vt_j0)):
+            acc = trans[b].numpy().copy()
+            cur = -1
+            for i in range(32):
+                mw = int(qmeta[tv * 32 + i])
+                if not (mw >> 14) & 1:
+                    continue
+                if (mw >> 5) & 1:
+                    cur = mw & 31
+                assert cur == (mw & 31)
+                row = n_virt0 + 3 * (tv * 32 + i)
+                acc = acc + A[cur] @ np.append(vp[row:row + 3], qcoef[tv * 32 + i])
+                if (mw >> 13) & 1:
+                    jl = (mw >> 8) & 31
+                    assert jl < vt_nj[tv]
+                    joints2[24 + vt_j0[tv] + jl] = acc
+                    acc = trans[b].numpy().copy()
+        np.testing.assert_allclose(joints2, ref.joints[b].numpy(), atol=2e-7)
 
 
 def test_bf16_split_operand(host_engine):
