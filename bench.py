@@ -201,8 +201,8 @@ def main():
     betas, rot, trans, dV, dJ = make_inputs(B, seed=rank, device=dev)
 
     def step():
-        eng.forward(betas, rot, trans, None, mode=mode, slab=args.slab)
-        return eng.backward(betas, rot, trans, None, None, dV, dJ, None, mode=mode, slab=args.slab)
+        saved = eng.forward(betas, rot, trans, None, mode=mode, slab=args.slab, save=True)[3]
+        return eng.backward(betas, rot, trans, None, None, dV, dJ, None, mode=mode, slab=args.slab, saved=saved)
 
     def sync_all():
         torch.cuda.synchronize(dev)

@@ -102,6 +102,10 @@ B200SMPL_API int b200smpl_model_debug_array(const b200smpl_model* m, const char*
 
 /* Bytes of caller-provided scratch needed by forward / backward for `batch` bodies.
  * slab_bodies = 0 lets the library pick the slab (bodies processed per L2-resident pass). */
+/* Bytes of the optional "saved for backward" buffer (blend output + skinning transforms of the
+ * whole batch, ~93 KB per body).  When forward writes it and backward receives it, the backward
+ * skips the recomputation of the pose stage and of the blend GEMM. */
+B200SMPL_API size_t b200smpl_saved_bytes(const b200smpl_model* m, int batch, int slab_bodies);
 B200SMPL_API size_t b200smpl_forward_workspace_bytes(const b200smpl_model* m, int batch, int mode, int slab_bodies);
 B200SMPL_API size_t b200smpl_backward_workspace_bytes(const b200smpl_model* m, int batch, int mode, int slab_bodies);
 
@@ -119,6 +123,8 @@ typedef struct b200smpl_forward_args {
   float* joints2d;             /* out [B][num_joints_out][2] = s*(x+tx), s*(y+ty); NULL if cam is NULL */
   void* workspace;
   size_t workspace_bytes;
+  void* saved;                 /* out, optional: b200smpl_saved_bytes(B, slab) bytes kept for backward */
+  size_t saved_bytes;
 } b200smpl_forward_args;
 
 /*
@@ -133,7 +139,7 @@ typedef struct b200smpl_backward_args {
   int32_t mode;
   int32_t pose_is_axis_angle;
   int32_t slab_bodies;
-  const float* betas;            /* forward inputs again (the backward recomputes, nothing is saved) */
+  const float* betas;            /* forward inputs again (needed by the chain backward and for recomputation) */
   const float* pose;
   const float* transl;           /* may be NULL */
   const float* cam;              /* may be NULL */
@@ -147,6 +153,8 @@ typedef struct b200smpl_backward_args {
   float* grad_cam;               /* out [B][3] or NULL */
   void* workspace;
   size_t workspace_bytes;
+  const void* saved;             /* optional: what forward wrote with the same batch / slab_bodies; NULL = recompute */
+  size_t saved_bytes;
 } b200smpl_backward_args;
 
 /*

@@ -81,17 +81,17 @@ def main():
         m = _lib.MODES[mode]
         for slab in (1024, 4096):
             for _ in range(2):
-                eng.forward(betas, rot, trans, None, mode=m, slab=slab)
-                eng.backward(betas, rot, trans, None, None, dV, dJ, None, mode=m, slab=slab)
+                sv = eng.forward(betas, rot, trans, None, mode=m, slab=slab, save=True)[3]
+                eng.backward(betas, rot, trans, None, None, dV, dJ, None, mode=m, slab=slab, saved=sv)
             torch.cuda.synchronize()
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             n = 5
             e0.record()
             for _ in range(n):
-                eng.forward(betas, rot, trans, None, mode=m, slab=slab)
+                sv = eng.forward(betas, rot, trans, None, mode=m, slab=slab, save=True)[3]
             e1.record()
             for _ in range(n):
-                eng.backward(betas, rot, trans, None, None, dV, dJ, None, mode=m, slab=slab)
+                eng.backward(betas, rot, trans, None, None, dV, dJ, None, mode=m, slab=slab, saved=sv)
             e2.record()
             torch.cuda.synchronize()
             tf, tb = e0.elapsed_time(e1) / n, e1.elapsed_time(e2) / n
@@ -99,8 +99,8 @@ def main():
                   % (mode, slab, B, tf, tb, B / (tf + tb) / 1e3), flush=True)
         lib.b200smpl_timing_enable(1)
         for _ in range(3):
-            eng.forward(betas, rot, trans, None, mode=m, slab=4096)
-            eng.backward(betas, rot, trans, None, None, dV, dJ, None, mode=m, slab=4096)
+            sv = eng.forward(betas, rot, trans, None, mode=m, slab=4096, save=True)[3]
+            eng.backward(betas, rot, trans, None, None, dV, dJ, None, mode=m, slab=4096, saved=sv)
         torch.cuda.synchronize()
         lib.b200smpl_timing_enable(0)
         print("[%s] per-kernel (3 steps, slab 4096): name launches total_ms\n%s" % (mode, timing_report(lib)), flush=True)

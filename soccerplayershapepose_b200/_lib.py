@@ -44,6 +44,7 @@ class ForwardArgs(Structure):
         ("betas", c_void_p), ("pose", c_void_p), ("transl", c_void_p), ("cam", c_void_p),
         ("vertices", c_void_p), ("joints", c_void_p), ("joints2d", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("saved", c_void_p), ("saved_bytes", c_size_t),
     ]
 
 
@@ -54,6 +55,7 @@ class BackwardArgs(Structure):
         ("grad_vertices", c_void_p), ("grad_joints", c_void_p), ("grad_joints2d", c_void_p),
         ("grad_betas", c_void_p), ("grad_pose", c_void_p), ("grad_transl", c_void_p), ("grad_cam", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("saved", c_void_p), ("saved_bytes", c_size_t),
     ]
 
 
@@ -63,6 +65,7 @@ SYMBOLS = {
     "b200smpl_model_destroy": (None, [c_void_p]),
     "b200smpl_model_get_info": (c_int, [c_void_p, POINTER(ModelInfo)]),
     "b200smpl_model_debug_array": (c_int, [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_size_t)]),
+    "b200smpl_saved_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "b200smpl_forward_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "b200smpl_backward_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "b200smpl_forward": (c_int, [c_void_p, POINTER(ForwardArgs), c_void_p]),

@@ -44,12 +44,11 @@ constexpr int DEFAULT_SLAB = 4096;   // bodies per pass (vpT slab = n_pad * S * 
 
 struct Plan {
   int S;                 // slab pitch (multiple of 128)
-  int lbs_splits;        // dA partials written by lbs_bwd
   int k_splits;          // split-K partials of the backward GEMM
   size_t off_feat, off_featf, off_A, off_jposed, off_vpT;
   size_t off_dvp_hi, off_dvp_lo, off_dA, off_dtr, off_dJtot, off_dfeat;
-  int joint_parts;      // dA partials written by joints_bwd
   size_t total;
+  size_t saved_slab_bytes;   // per slab: A_blk [S/32][288][32] then vpB [n_pad][S]
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -72,14 +71,14 @@ static Plan make_plan(const b200smpl_model* m, int batch, int mode, int slab_bod
   p.off_A = take((size_t)NJ * AELEMS * S_ * 4);
   p.off_jposed = take((size_t)NJ * 3 * S_ * 4);
   p.off_vpT = take((size_t)d.n_pad * S_ * 4);
+  p.saved_slab_bytes = align_up((size_t)NJ * AELEMS * S_ * 4, 1024) + align_up((size_t)d.n_pad * S_ * 4, 1024);
   if (backward) {
-    p.lbs_splits = lbs_bwd_splits(d, p.S, m->num_sms);
     p.k_splits = mode == B200SMPL_MODE_FP32_SIMT ? 1 : blend_bwd_umma_splits(d, mode, p.S, m->num_sms);
     p.off_dvp_hi = take(S_ * d.n_pad * 2);
     p.off_dvp_lo = take(mode == B200SMPL_MODE_BF16 ? 0 : S_ * d.n_pad * 2);
-    p.joint_parts = joints_bwd_parts(d);
-    p.off_dA = take((size_t)(p.lbs_splits + p.joint_parts) * NJ * AELEMS * S_ * 4);
-    p.off_dtr = take((size_t)(p.lbs_splits + p.joint_parts) * 3 * S_ * 4);
+    // dA accumulator [S/32][288][32] directly followed by the dtransl accumulator [S/32][3][32]
+    p.off_dA = take((size_t)(NJ * AELEMS + 3) * S_ * 4);
+    p.off_dtr = p.off_dA + (size_t)NJ * AELEMS * S_ * 4;
     p.off_dJtot = take((size_t)std::max(batch, 1) * d.njout * 3 * 4);
     p.off_dfeat = take((size_t)p.k_splits * S_ * d.fl.nf_pad * 4);
   }
@@ -251,6 +250,12 @@ int b200smpl_model_debug_array(const b200smpl_model* m, const char* name, const 
   return fail(B200SMPL_ERR_INVALID, "unknown debug array: " + n);
 }
 
+size_t b200smpl_saved_bytes(const b200smpl_model* m, int batch, int slab_bodies) {
+  if (m == nullptr) return 0;
+  const Plan p = make_plan(m, batch, B200SMPL_MODE_FP32, slab_bodies, false);
+  const size_t nslabs = ((size_t)std::max(batch, 1) + p.S - 1) / p.S;
+  return nslabs * p.saved_slab_bytes + 1024;
+}
 size_t b200smpl_forward_workspace_bytes(const b200smpl_model* m, int batch, int mode, int slab_bodies) {
   if (m == nullptr) return 0;
   return make_plan(m, batch, mode, slab_bodies, false).total;
@@ -277,10 +282,20 @@ int b200smpl_forward(const b200smpl_model* m, const b200smpl_forward_args* a, vo
   float* vpT = (float*)(ws + p.off_vpT);
   const int S = p.S, B = a->batch;
   const bool aa = a->pose_is_axis_angle != 0;
-  const int row_begin = a->vertices ? 0 : d.n_virt0;
+  // with a saved buffer the whole blend output is kept, so every row is computed
+  const int row_begin = (a->vertices || a->saved) ? 0 : d.n_virt0;
+  char* saved = nullptr;
+  if (a->saved) {
+    if (a->saved_bytes < b200smpl_saved_bytes(m, B, a->slab_bodies)) return fail(B200SMPL_ERR_WORKSPACE, "saved buffer too small");
+    saved = (char*)align_up((size_t)a->saved, 1024);
+  }
   for (int b0 = 0; b0 < B; b0 += S) {
     const int nb = std::min(S, B - b0);
     const int Sw = round_up(nb, 128);
+    if (saved) {
+      A_T = (float*)(saved + (size_t)(b0 / S) * p.saved_slab_bytes);
+      vpT = (float*)((char*)A_T + align_up((size_t)NJ * AELEMS * S * 4, 1024));
+    }
     if ((rc = launch_pose_fwd(d, a->betas, a->pose, aa, b0, nb, S, Sw, feat, featf, A_T, a->transl, a->joints, st)))
       return rc;
     if (a->mode == B200SMPL_MODE_FP32_SIMT)
@@ -339,9 +354,6 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
       return rc;
     dJ = dJtot;
   }
-  // the joints_bwd partials (when present) come first, the skinning partials follow
-  const int jpart = have_j ? p.joint_parts : 0;
-  const int n_parts = jpart + (have_v ? p.lbs_splits : 0);
   const int row_begin = have_v ? 0 : d.n_virt0;
   const int row_end = have_j ? d.n_rows : d.n_virt0;
   int k_splits = 1;
@@ -349,20 +361,31 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
     const int slabs = (row_end + 63) / 64 - row_begin / 64;
     k_splits = std::max(1, std::min(p.k_splits, slabs / 8));
   }
+  const char* saved = nullptr;
+  if (a->saved) {
+    if (a->saved_bytes < b200smpl_saved_bytes(m, B, a->slab_bodies)) return fail(B200SMPL_ERR_WORKSPACE, "saved buffer too small");
+    saved = (const char*)align_up((size_t)a->saved, 1024);
+  }
   for (int b0 = 0; b0 < B; b0 += S) {
     const int nb = std::min(S, B - b0);
     const int Sw = round_up(nb, 128);
-    if ((rc = launch_pose_fwd(d, a->betas, a->pose, aa, b0, nb, S, Sw, feat, featf, A_T, nullptr, nullptr, st)))
-      return rc;
-    if (a->mode == B200SMPL_MODE_FP32_SIMT)
-      rc = launch_blend_fwd_simt(d, featf, S, Sw, vpT, row_begin, d.n_pad, st);
-    else
-      rc = launch_blend_fwd_umma(d, a->mode, feat, S, Sw, vpT, row_begin, d.n_pad, st);
-    if (rc) return rc;
+    // the skinning / joint kernels accumulate dL/dA and dL/dtransl of this slab with fp32 REDs
+    B200_CUDA_TRY(cudaMemsetAsync(dA_part, 0, (size_t)(NJ * AELEMS + 3) * S * 4, st));
+    if (saved) {   // forward kept the transforms and the blend output of this slab: nothing to recompute
+      A_T = (float*)(saved + (size_t)(b0 / S) * p.saved_slab_bytes);
+      vpT = (float*)((char*)A_T + align_up((size_t)NJ * AELEMS * S * 4, 1024));
+    } else {
+      if ((rc = launch_pose_fwd(d, a->betas, a->pose, aa, b0, nb, S, Sw, feat, featf, A_T, nullptr, nullptr, st)))
+        return rc;
+      if (a->mode == B200SMPL_MODE_FP32_SIMT)
+        rc = launch_blend_fwd_simt(d, featf, S, Sw, vpT, row_begin, d.n_pad, st);
+      else
+        rc = launch_blend_fwd_umma(d, a->mode, feat, S, Sw, vpT, row_begin, d.n_pad, st);
+      if (rc) return rc;
+    }
     if (have_v)
-      if ((rc = launch_lbs_bwd(d, vpT, S, Sw, A_T, b0, nb, a->grad_vertices, dvp_hi, dvp_lo,
-                               dA_part + (size_t)jpart * NJ * AELEMS * S, dtr_part + (size_t)jpart * 3 * S,
-                               p.lbs_splits, st)))
+      if ((rc = launch_lbs_bwd(d, vpT, S, Sw, A_T, b0, nb, a->grad_vertices, dvp_hi, dvp_lo, dA_part, dtr_part,
+                               m->num_sms, st)))
         return rc;
     if (have_j)
       if ((rc = launch_joints_bwd(d, vpT, S, Sw, A_T, b0, nb, dJ, dvp_hi, dvp_lo, dA_part, dtr_part, st))) return rc;
@@ -371,7 +394,7 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
     else
       rc = launch_blend_bwd_umma(d, a->mode, dvp_hi, dvp_lo, S, Sw, dfeat_part, k_splits, row_begin, row_end, st);
     if (rc) return rc;
-    if ((rc = launch_pose_bwd(d, a->betas, a->pose, aa, b0, nb, S, dA_part, n_parts, dtr_part, dfeat_part, k_splits,
+    if ((rc = launch_pose_bwd(d, a->betas, a->pose, aa, b0, nb, S, dA_part, 1, dtr_part, dfeat_part, k_splits,
                               have_j ? dJ : nullptr, a->grad_betas, a->grad_pose, a->grad_transl, st)))
       return rc;
   }

@@ -257,6 +257,139 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, int nseg, int slab_begin
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Forward blend GEMM, W-stationary.  The generic kernel above re-reads both operands for every
+// 128x128 tile (1.9 GB of L2->SM traffic at B=4096: L2-bound).  Here a CTA keeps its 128-row slice
+// of the model operand (all K: up to 11 x 16 KB) resident in shared memory and streams only the
+// feature tiles of its share of the bodies through a 3-stage ring, accumulating in two alternating
+// TMEM buffers so the epilogue of body tile i overlaps the MMAs of tile i+1.
+//   vpB (group-blocked) [n][s] = sum_k Wf[n][k] * feat[s][k]
+// grid: (row tiles, body chunks); CTA = 6 warps (TMA, MMA, 4 epilogue).
+// ---------------------------------------------------------------------------------------------
+constexpr int WS_STAGES = 3;
+constexpr int WS_MAX_SLABS = 11;
+constexpr int WS_BN = 128;
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+blend_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_f, int nslab,
+                    int row0, int ntiles_n, int tiles_per_chunk, float* __restrict__ vpB, int G) {
+  constexpr int SLAB = BM * BK * 2;                 // 16 KB: 128 rows x 64 bf16 (both operands)
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* w_s = smem;                                          // [nslab][16 KB]
+  unsigned char* f_s = smem + WS_MAX_SLABS * SLAB;                    // [WS_STAGES][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(f_s + WS_STAGES * SLAB);
+  uint64_t* w_full = bars;
+  uint64_t* full_bar = bars + 1;
+  uint64_t* empty_bar = full_bar + WS_STAGES;
+  uint64_t* tfull_bar = empty_bar + WS_STAGES;      // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = row0 + blockIdx.x * BM;
+  const int nt_begin = blockIdx.y * tiles_per_chunk;
+  const int nt_end = min(ntiles_n, nt_begin + tiles_per_chunk);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_w);
+    prefetch_tmap(&map_f);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(w_full, 1);
+    for (int i = 0; i < WS_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);                 // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, 2 * WS_BN);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, (uint32_t)nslab * SLAB);
+      for (int s = 0; s < nslab; ++s) tma_load_2d(w_s + s * SLAB, &map_w, w_full, s * BK, m0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int nt = nt_begin; nt < nt_end; ++nt)
+        for (int s = 0; s < nslab; ++s) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], SLAB);
+          tma_load_2d(f_s + stage * SLAB, &map_f, &full_bar[stage], s * BK, nt * WS_BN);
+          if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, WS_BN);
+      mbar_wait(w_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tphase[2] = {0u, 0u};
+      int acc = 0;
+      for (int nt = nt_begin; nt < nt_end; ++nt, acc ^= 1) {
+        mbar_wait(&tempty_bar[acc], tphase[acc] ^ 1);   // epilogue has drained this accumulator
+        tphase[acc] ^= 1;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * WS_BN);
+        for (int s = 0; s < nslab; ++s) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_sw128_desc(smem_u32(w_s + s * SLAB));
+          const uint64_t db = make_sw128_desc(smem_u32(f_s + stage * SLAB));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (s | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (s == nslab - 1) umma_commit(&tfull_bar[acc]);
+          if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const long long n = (long long)m0 + q * 32 + lane;
+    float* rowbase = vpB + (n / 96) * (long long)G * 3072LL + (n % 96) * 32;
+    uint32_t tphase[2] = {0u, 0u};
+    int acc = 0;
+    for (int nt = nt_begin; nt < nt_end; ++nt, acc ^= 1) {
+      mbar_wait(&tfull_bar[acc], tphase[acc]);
+      tphase[acc] ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < WS_BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * WS_BN + c0), v);
+        float* o = rowbase + (long long)(nt * (WS_BN / 32) + c0 / 32) * 3072LL;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(o + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[acc])) : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * WS_BN);
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -295,18 +428,33 @@ constexpr int BWD_BN_MAX = 256, BWD_STAGES = 4;
 int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat, int S, int Sw, float* vpT,
                           int row_begin, int row_end, cudaStream_t st) {
   const int kuse = (mode == B200SMPL_MODE_BF16) ? m.fl.k_bf16x2 : m.fl.k_fp32;
-  GemmMaps maps;
-  memset(&maps, 0, sizeof(maps));
+  const int nslab = (kuse + BK - 1) / BK;
+  if (nslab > WS_MAX_SLABS) return fail(B200SMPL_ERR_INVALID, "feature pitch too large for the resident operand");
+  CUtensorMap map_w, map_f;
   int rc;
-  if ((rc = make_map(&maps.a[0], m.Wf, kuse, m.n_pad, m.fl.pitch, BM))) return rc;
-  if ((rc = make_map(&maps.b[0], feat, kuse, S, m.fl.pitch, FWD_BN))) return rc;
-  const int slabs = (kuse + BK - 1) / BK;
-  using SM = GemmSmem<FWD_BN, FWD_STAGES>;
-  auto kern = umma_gemm_kernel<FWD_BN, FWD_STAGES, 2, true>;
-  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-  dim3 grid((row_end - row_begin) / BM, Sw / FWD_BN, 1);
-  LaunchTimer _timer_291("blend_fwd_umma", st);
-  kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(maps, 1, 0, slabs, slabs, row_begin, 0, vpT, S / 32, 0LL);
+  if ((rc = make_map(&map_w, m.Wf, kuse, m.n_pad, m.fl.pitch, BM))) return rc;
+  if ((rc = make_map(&map_f, feat, kuse, S, m.fl.pitch, WS_BN))) return rc;
+  constexpr int smem = (WS_MAX_SLABS + WS_STAGES) * BM * BK * 2 + 1024 + 256;
+  B200_CUDA_TRY(cudaFuncSetAttribute(blend_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int mtiles = (row_end - row_begin) / BM;
+  const int ntiles_n = Sw / WS_BN;
+  // body chunks: enough CTAs for several waves, but at least 4 body tiles per CTA to amortise the W load
+  int chunks = 1;
+  {
+    double best = -1.0;
+    for (int c = 1; c <= ntiles_n; ++c) {
+      const int tpc = (ntiles_n + c - 1) / c;
+      if (tpc < 4 && c > 1) break;
+      const long long ctas = (long long)mtiles * ((ntiles_n + tpc - 1) / tpc);
+      const long long waves = (ctas + 147) / 148;
+      const double eff = (double)ctas / (double)(waves * 148);
+      if (eff > best + 1e-9) { best = eff; chunks = (ntiles_n + tpc - 1) / tpc; }
+    }
+  }
+  const int tpc = (ntiles_n + chunks - 1) / chunks;
+  LaunchTimer _timer("blend_fwd_umma", st);
+  blend_fwd_ws_kernel<<<dim3(mtiles, (ntiles_n + tpc - 1) / tpc), GEMM_THREADS, smem, st>>>(map_w, map_f, nslab, row_begin,
+                                                                                         ntiles_n, tpc, vpT, S / 32);
   B200_LAUNCH_CHECK("blend_fwd_umma");
   return 0;
 }

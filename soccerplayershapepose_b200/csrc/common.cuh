@@ -188,14 +188,12 @@ int blend_bwd_umma_splits(const DevModel& m, int mode, int S, int num_sms);
 
 int launch_lbs_fwd(const DevModel& m, const float* vpT, int S, const float* A_T, int b0, int nb,
                    const float* transl, float* verts, int num_sms, cudaStream_t st);
-int lbs_bwd_splits(const DevModel& m, int S, int num_sms);
 int launch_lbs_bwd(const DevModel& m, const float* vpT, int S, int Sw, const float* A_T, int b0, int nb,
-                   const float* grad_verts, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_part,
-                   float* dtr_part, int nsplit, cudaStream_t st);
+                   const float* grad_verts, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_acc,
+                   float* dtr_acc, int num_sms, cudaStream_t st);
 
 int launch_joints_fwd(const DevModel& m, const float* vpB, int S, const float* A_blk, int b0, int nb,
                       const float* transl, float* joints, cudaStream_t st);
-int joints_bwd_parts(const DevModel& m);
 int launch_joints_bwd(const DevModel& m, const float* vpB, int S, int Sw, const float* A_blk, int b0, int nb,
                       const float* dJ, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_part, float* dtr_part,
                       cudaStream_t st);

@@ -14,7 +14,7 @@
 
 namespace b200smpl {
 
-constexpr int JW = 4;                       // warps (= virtual tiles) per CTA
+constexpr int JW = 6;                       // warps per CTA; one CTA per body group, warps stride over the virtual tiles
 constexpr int JT = JW * 32;
 constexpr size_t JFWD_SMEM = (size_t)(AG_WORDS + JW * TTILE_WORDS) * 4 + 16;
 constexpr size_t JBWD_SMEM = (size_t)(2 * AG_WORDS + 96 + JW * 2 * TTILE_WORDS) * 4 + 16;
@@ -28,52 +28,54 @@ joints_fwd_kernel(DevModel m, const float* __restrict__ vpB, int G, const float*
   uint64_t* bar = reinterpret_cast<uint64_t*>(tiles + JW * TTILE_WORDS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x, col0 = g * 32, gb0 = b0 + col0;
-  const int tv = blockIdx.y * JW + warp;
   if (threadIdx.x == 0) fetch_group_transforms(A_s, A_blk, g, bar);
-  float q[96];
-  const bool active = tv < m.ntv;
-  if (active) {
-    const float* chunk = vpB + ((size_t)(m.ntiles + tv) * G + g) * CHUNK_WORDS + lane;
-#pragma unroll
-    for (int i = 0; i < 96; ++i) q[i] = ld_stream(chunk + i * 32);
-  }
   float tx = 0.f, ty = 0.f, tz = 0.f;
   if (transl != nullptr && col0 + lane < nb) {
     const float* t = transl + (size_t)(gb0 + lane) * 3;
     tx = t[0]; ty = t[1]; tz = t[2];
   }
   __syncthreads();
-  mbar_wait(bar, 0);
-  if (!active) return;
   float* out_s = tiles + warp * TTILE_WORDS;
   float* out_lane = out_s + lane;
-  const uint32_t* meta = m.qmeta + tv * 32;
-  const float* coef = m.qcoef + tv * 32;
-  float a[AELEMS];
-  float x = tx, y = ty, z = tz;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const uint32_t mt = __ldg(meta + i);
-    if (!(mt & (1u << 14))) continue;
-    if ((mt & (1u << 5)) || i == 0) load_slot(a, A_s, mt & 31, lane);
-    const float c = __ldg(coef + i);
-    const float qx = q[i * 3], qy = q[i * 3 + 1], qz = q[i * 3 + 2];
-    x += fmaf(a[0], qx, fmaf(a[1], qy, fmaf(a[2], qz, a[3] * c)));
-    y += fmaf(a[4], qx, fmaf(a[5], qy, fmaf(a[6], qz, a[7] * c)));
-    z += fmaf(a[8], qx, fmaf(a[9], qy, fmaf(a[10], qz, a[11] * c)));
-    if (mt & (1u << 13)) {                                 // last term of this joint
-      float* o = out_lane + ((mt >> 8) & 31) * (3 * TPITCH);
-      o[0] = x; o[TPITCH] = y; o[2 * TPITCH] = z;
-      x = tx; y = ty; z = tz;
-    }
-  }
-  __syncwarp();
-  const int ncols = m.vt_nj[tv] * 3;
   const int nrows = min(32, nb - col0);
   const size_t ncol_all = (size_t)m.njout * 3;
-  float* dst0 = joints + (size_t)gb0 * ncol_all + (size_t)(NJ + m.vt_j0[tv]) * 3;
-  for (int r = 0; r < nrows; ++r)
-    for (int c = lane; c < ncols; c += 32) dst0[(size_t)r * ncol_all + c] = out_s[c * TPITCH + r];
+  bool waited = false;
+  for (int tv = warp; tv < m.ntv; tv += JW) {
+    float q[96];
+    const float* chunk = vpB + ((size_t)(m.ntiles + tv) * G + g) * CHUNK_WORDS + lane;
+#pragma unroll
+    for (int i = 0; i < 96; ++i) q[i] = ld_stream(chunk + i * 32);
+    if (!waited) { mbar_wait(bar, 0); waited = true; }
+    const uint32_t* meta = m.qmeta + tv * 32;
+    const float* coef = m.qcoef + tv * 32;
+    float a[AELEMS];
+    float x = tx, y = ty, z = tz;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const uint32_t mt = __ldg(meta + i);
+      if (!(mt & (1u << 14))) continue;
+      if ((mt & (1u << 5)) || i == 0) load_slot(a, A_s, mt & 31, lane);
+      const float c = __ldg(coef + i);
+      const float qx = q[i * 3], qy = q[i * 3 + 1], qz = q[i * 3 + 2];
+      x += fmaf(a[0], qx, fmaf(a[1], qy, fmaf(a[2], qz, a[3] * c)));
+      y += fmaf(a[4], qx, fmaf(a[5], qy, fmaf(a[6], qz, a[7] * c)));
+      z += fmaf(a[8], qx, fmaf(a[9], qy, fmaf(a[10], qz, a[11] * c)));
+      if (mt & (1u << 13)) {                               // last term of this joint
+        float* o = out_lane + ((mt >> 8) & 31) * (3 * TPITCH);
+        o[0] = x; o[TPITCH] = y; o[2 * TPITCH] = z;
+        x = tx; y = ty; z = tz;
+      }
+    }
+    __syncwarp();
+    // flush the tile's joints: 3 nj contiguous floats per body row, flattened so that loads/stores pipeline
+    const int ncols = m.vt_nj[tv] * 3;
+    float* dst0 = joints + (size_t)gb0 * ncol_all + (size_t)(NJ + m.vt_j0[tv]) * 3;
+    for (int idx = lane; idx < nrows * ncols; idx += 32) {
+      const int r = idx / ncols, c = idx - r * ncols;
+      dst0[(size_t)r * ncol_all + c] = out_s[c * TPITCH + r];
+    }
+    __syncwarp();
+  }
 }
 
 // backward over virtual tiles.  dJ: total joint gradient (B, NJout, 3).
@@ -81,7 +83,7 @@ joints_fwd_kernel(DevModel m, const float* __restrict__ vpB, int G, const float*
 __global__ void __launch_bounds__(JT, 1)
 joints_bwd_kernel(DevModel m, const float* __restrict__ vpB, int G, const float* __restrict__ A_blk, int b0, int nb,
                   const float* __restrict__ dJ, __nv_bfloat16* __restrict__ dvp_hi,
-                  __nv_bfloat16* __restrict__ dvp_lo, float* __restrict__ dA_part, float* __restrict__ dtr_part) {
+                  __nv_bfloat16* __restrict__ dvp_lo, float* __restrict__ dA_acc, float* __restrict__ dtr_acc) {
   extern __shared__ __align__(128) float smem[];
   float* A_s = smem;
   float* dA_s = A_s + AG_WORDS;
@@ -90,32 +92,31 @@ joints_bwd_kernel(DevModel m, const float* __restrict__ vpB, int G, const float*
   uint64_t* bar = reinterpret_cast<uint64_t*>(tiles + JW * 2 * TTILE_WORDS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x, col0 = g * 32, gb0 = b0 + col0;
-  const int tv = blockIdx.y * JW + warp;
-  const bool active = tv < m.ntv;
   if (threadIdx.x == 0) fetch_group_transforms(A_s, A_blk, g, bar);
-  float q[96];
-  if (active) {
-    const float* chunk = vpB + ((size_t)(m.ntiles + tv) * G + g) * CHUNK_WORDS + lane;
-#pragma unroll
-    for (int i = 0; i < 96; ++i) q[i] = ld_stream(chunk + i * 32);
-  }
   for (int r = threadIdx.x; r < AG_WORDS; r += JT) dA_s[r] = 0.f;
   if (threadIdx.x < 96) dtr_s[threadIdx.x] = 0.f;
   __syncthreads();
-  mbar_wait(bar, 0);
-  if (active) {
-    float* g_s = tiles + warp * 2 * TTILE_WORDS;
-    uint32_t* q_s = reinterpret_cast<uint32_t*>(g_s + TTILE_WORDS);
+  float* g_s = tiles + warp * 2 * TTILE_WORDS;
+  uint32_t* q_s = reinterpret_cast<uint32_t*>(g_s + TTILE_WORDS);
+  const int nrows = min(32, nb - col0);
+  const size_t ncol_all = (size_t)m.njout * 3;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  bool waited = false;
+  for (int tv = warp; tv < m.ntv; tv += JW) {
+    float q[96];
+    const float* chunk = vpB + ((size_t)(m.ntiles + tv) * G + g) * CHUNK_WORDS + lane;
+#pragma unroll
+    for (int i = 0; i < 96; ++i) q[i] = ld_stream(chunk + i * 32);
     const int ncols = m.vt_nj[tv] * 3;
-    const int nrows = min(32, nb - col0);
-    const size_t ncol_all = (size_t)m.njout * 3;
-    // stage the gradients of this tile's joints: columns = 3 nj floats of each body row
+    // stage the gradients of this tile's joints (3 nj floats of each body row), flattened
     {
       const float* src0 = dJ + (size_t)gb0 * ncol_all + (size_t)(NJ + m.vt_j0[tv]) * 3;
-      for (int r = 0; r < 32; ++r)
-        for (int c = lane; c < ncols; c += 32)
-          g_s[c * TPITCH + r] = (r < nrows) ? ld_stream(src0 + (size_t)r * ncol_all + c) : 0.f;
+      for (int idx = lane; idx < 32 * ncols; idx += 32) {
+        const int r = idx / ncols, c = idx - r * ncols;
+        g_s[c * TPITCH + r] = (r < nrows) ? ld_stream(src0 + (size_t)r * ncol_all + c) : 0.f;
+      }
     }
+    if (!waited) { mbar_wait(bar, 0); waited = true; }
     __syncwarp();
     const uint32_t* meta = m.qmeta + tv * 32;
     const float* coef = m.qcoef + tv * 32;
@@ -123,7 +124,6 @@ joints_bwd_kernel(DevModel m, const float* __restrict__ vpB, int G, const float*
 #pragma unroll
     for (int e = 0; e < AELEMS; ++e) d[e] = 0.f;
     int jcur = 0;
-    float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const uint32_t mt = __ldg(meta + i);
@@ -150,16 +150,16 @@ joints_bwd_kernel(DevModel m, const float* __restrict__ vpB, int G, const float*
       if (mt & (1u << 13)) { sx += gx; sy += gy; sz += gz; }
     }
     flush_slot(d, dA_s, jcur, lane);
-    atomicAdd(&dtr_s[lane], sx);
-    atomicAdd(&dtr_s[32 + lane], sy);
-    atomicAdd(&dtr_s[64 + lane], sz);
     __syncwarp();
     flush_dvp_tile(q_s, dvp_hi, dvp_lo, (size_t)col0, m.n_pad, (size_t)m.n_virt0 + (size_t)tv * 96, lane);
+    __syncwarp();
   }
+  atomicAdd(&dtr_s[lane], sx);
+  atomicAdd(&dtr_s[32 + lane], sy);
+  atomicAdd(&dtr_s[64 + lane], sz);
   __syncthreads();
-  float* dA_out = dA_part + ((size_t)blockIdx.y * G + g) * AG_WORDS;
-  for (int r = threadIdx.x; r < AG_WORDS; r += JT) dA_out[r] = dA_s[r];
-  if (threadIdx.x < 96) dtr_part[((size_t)blockIdx.y * G + g) * 96 + threadIdx.x] = dtr_s[threadIdx.x];
+  accumulate_rows(dA_acc + (size_t)g * AG_WORDS, dA_s, NJ * AELEMS, warp, JW, lane);
+  if (warp < 3) atomicAdd(dtr_acc + (size_t)g * 96 + warp * 32 + lane, dtr_s[warp * 32 + lane]);
 }
 
 // total joint gradient when a 2D reprojection gradient is present:
@@ -193,14 +193,12 @@ joint_grad_total_kernel(const float* __restrict__ joints, const float* __restric
   if (gcam != nullptr && threadIdx.x < 3) gcam[b * 3 + threadIdx.x] = sh[threadIdx.x][0] + sh[threadIdx.x][1] + sh[threadIdx.x][2] + sh[threadIdx.x][3];
 }
 
-int joints_bwd_parts(const DevModel& m) { return (m.ntv + JW - 1) / JW; }
-
 int launch_joints_fwd(const DevModel& m, const float* vpB, int S, const float* A_blk, int b0, int nb,
                       const float* transl, float* joints, cudaStream_t st) {
   if (nb <= 0 || m.ntv == 0) return 0;
   B200_CUDA_TRY(cudaFuncSetAttribute(joints_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JFWD_SMEM));
   LaunchTimer _timer("joints_fwd", st);
-  joints_fwd_kernel<<<dim3((nb + 31) / 32, (m.ntv + JW - 1) / JW), JT, JFWD_SMEM, st>>>(m, vpB, S / 32, A_blk, b0, nb,
+  joints_fwd_kernel<<<(nb + 31) / 32, JT, JFWD_SMEM, st>>>(m, vpB, S / 32, A_blk, b0, nb,
                                                                                         transl, joints);
   B200_LAUNCH_CHECK("joints_fwd");
   return 0;
@@ -213,7 +211,7 @@ int launch_joints_bwd(const DevModel& m, const float* vpB, int S, int Sw, const 
   if (m.ntv == 0) return 0;
   B200_CUDA_TRY(cudaFuncSetAttribute(joints_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JBWD_SMEM));
   LaunchTimer _timer("joints_bwd", st);
-  joints_bwd_kernel<<<dim3(Sw / 32, (m.ntv + JW - 1) / JW), JT, JBWD_SMEM, st>>>(m, vpB, S / 32, A_blk, b0, nb, dJ,
+  joints_bwd_kernel<<<Sw / 32, JT, JBWD_SMEM, st>>>(m, vpB, S / 32, A_blk, b0, nb, dJ,
                                                                                  dvp_hi, dvp_lo, dA_part, dtr_part);
   B200_LAUNCH_CHECK("joints_bwd");
   return 0;

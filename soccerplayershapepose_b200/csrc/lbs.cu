@@ -35,7 +35,10 @@ __device__ __forceinline__ void fetch_vp(float (&P)[PF * 3], const float* __rest
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-constexpr int FWD_WARPS = 14;
+#ifndef B200_FWD_WARPS
+#define B200_FWD_WARPS 12
+#endif
+constexpr int FWD_WARPS = B200_FWD_WARPS;
 constexpr int FWD_THREADS = FWD_WARPS * 32;
 constexpr size_t FWD_SMEM = (size_t)(AG_WORDS + FWD_WARPS * TTILE_WORDS) * 4 + 16;
 
@@ -46,10 +49,17 @@ struct Slots {
 __device__ __forceinline__ void skin_fwd(const float (&P)[PF * 3], Slots& s, const float* A_s, int lane,
                                          const uint32_t* __restrict__ meta, const float4* __restrict__ wts,
                                          uint32_t force, float tx, float ty, float tz, float* out_lane) {
+  uint32_t mts[PF];
+  float4 ws[PF];
+#pragma unroll
+  for (int i = 0; i < PF; ++i) {               // warp-uniform plan words of the whole unit, issued together
+    mts[i] = __ldg(meta + i);
+    ws[i] = __ldg(wts + i);
+  }
 #pragma unroll
   for (int i = 0; i < PF; ++i) {
-    const uint32_t mt = __ldg(meta + i) | (i == 0 ? force : 0u);
-    const float4 w = __ldg(wts + i);
+    const uint32_t mt = mts[i] | (i == 0 ? force : 0u);
+    const float4 w = ws[i];
     if (mt & (0xFu << 20)) {
       if (mt & (1u << 20)) load_slot(s.a0, A_s, mt & 31, lane);
       if (mt & (1u << 21)) load_slot(s.a1, A_s, (mt >> 5) & 31, lane);
@@ -152,6 +162,8 @@ constexpr int BWD_WARPS = 12;
 constexpr int BWD_THREADS = BWD_WARPS * 32;
 constexpr size_t BWD_SMEM = (size_t)(2 * AG_WORDS + 96 + BWD_WARPS * TTILE_WORDS) * 4 + 16;
 
+constexpr int BPF = 4;   // backward prefetch unit: 4 vertices (12 loads in flight per lane) keeps the loop body in the I-cache
+
 struct BwdState {
   float a0[9], a1[9], a2[9], a3[9];                      // rotation parts of the 4 cached transforms
   float d0[AELEMS], d1[AELEMS], d2[AELEMS], d3[AELEMS];  // their gradient accumulators
@@ -159,12 +171,23 @@ struct BwdState {
   float sx, sy, sz;
 };
 
-__device__ __forceinline__ void skin_bwd(const float (&P)[PF * 3], BwdState& s, const float* A_s, float* dA_s,
+__device__ __forceinline__ void fetch_vp4(float (&P)[BPF * 3], const float* __restrict__ chunk_lane,
+                                          const uint32_t* __restrict__ meta) {
+#pragma unroll
+  for (int i = 0; i < BPF; ++i) {
+    const int c = ((__ldg(meta + i) >> 24) & 31) * 3;
+    P[i * 3 + 0] = ld_stream(chunk_lane + c * 32);
+    P[i * 3 + 1] = ld_stream(chunk_lane + c * 32 + 32);
+    P[i * 3 + 2] = ld_stream(chunk_lane + c * 32 + 64);
+  }
+}
+
+__device__ __forceinline__ void skin_bwd(const float (&P)[BPF * 3], BwdState& s, const float* A_s, float* dA_s,
                                          int lane, const uint32_t* __restrict__ meta,
                                          const float4* __restrict__ wts, bool first, float* g_lane) {
   uint32_t* g_lane_u = reinterpret_cast<uint32_t*>(g_lane);
 #pragma unroll
-  for (int i = 0; i < PF; ++i) {
+  for (int i = 0; i < BPF; ++i) {
     const bool force = first && i == 0;
     const uint32_t mt = __ldg(meta + i) | (force ? (0xFu << 20) : 0u);
     const int o = ((mt >> 24) & 31) * (3 * TPITCH);
@@ -206,12 +229,39 @@ __device__ __forceinline__ void skin_bwd(const float (&P)[PF * 3], BwdState& s, 
   }
 }
 
+// stage 8 body rows x 96 columns of dV into the transposition tile; FULL: no bounds needed
+template <bool FULL>
+__device__ __forceinline__ void stage_rows(const float* __restrict__ src0, size_t row_stride, float* dstc, int r0,
+                                           int nrows_valid, int ncols, int lane) {
+  float t[24];
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    const float* src = src0 + (size_t)(r0 + rr) * row_stride;
+    if (FULL) {
+      t[rr * 3 + 0] = ld_stream(src);
+      t[rr * 3 + 1] = ld_stream(src + 32);
+      t[rr * 3 + 2] = ld_stream(src + 64);
+    } else {
+      const bool rowok = r0 + rr < nrows_valid;
+      t[rr * 3 + 0] = (rowok && lane < ncols) ? ld_stream(src) : 0.f;
+      t[rr * 3 + 1] = (rowok && lane + 32 < ncols) ? ld_stream(src + 32) : 0.f;
+      t[rr * 3 + 2] = (rowok && lane + 64 < ncols) ? ld_stream(src + 64) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 8; ++rr) {
+    dstc[r0 + rr] = t[rr * 3 + 0];
+    dstc[32 * TPITCH + r0 + rr] = t[rr * 3 + 1];
+    dstc[64 * TPITCH + r0 + rr] = t[rr * 3 + 2];
+  }
+}
+
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 lbs_bwd_kernel(const float* __restrict__ vpB, int G, const float* __restrict__ A_blk, int b0, int nb,
                const float* __restrict__ grad_verts, int V, int ntiles, int tiles_per_split,
                const uint32_t* __restrict__ vmeta, const float4* __restrict__ vwts,
                __nv_bfloat16* __restrict__ dvp_hi, __nv_bfloat16* __restrict__ dvp_lo, int n_pad,
-               float* __restrict__ dA_part, float* __restrict__ dtr_part) {
+               float* __restrict__ dA_acc, float* __restrict__ dtr_acc) {
   extern __shared__ __align__(128) float smem[];
   float* A_s = smem;                                         // [288][32]
   float* dA_s = A_s + AG_WORDS;                              // [288][32]
@@ -226,11 +276,10 @@ lbs_bwd_kernel(const float* __restrict__ vpB, int G, const float* __restrict__ A
   const int tile_end = min(ntiles, tile_begin + tiles_per_split);
   if (threadIdx.x == 0) fetch_group_transforms(A_s, A_blk, g, bar);
 
-  float P[PF * 3], Q[PF * 3];
+  float P[BPF * 3], Q[BPF * 3];
   int tile = tile_begin + warp;
   const float* chunk0 = vpB + (size_t)g * CHUNK_WORDS + lane;
   const size_t tstride = (size_t)G * CHUNK_WORDS;
-  if (tile < tile_end) fetch_vp(P, chunk0 + tile * tstride, vmeta + tile * TILE_V);
   for (int r = threadIdx.x; r < AG_WORDS; r += BWD_THREADS) dA_s[r] = 0.f;
   if (threadIdx.x < 96) dtr_s[threadIdx.x] = 0.f;
   __syncthreads();
@@ -251,40 +300,31 @@ lbs_bwd_kernel(const float* __restrict__ vpB, int G, const float* __restrict__ A
     const uint32_t* meta = vmeta + vbase;
     const float4* wts = vwts + vbase;
     const float* chunk = chunk0 + tile * tstride;
+    fetch_vp4(P, chunk, meta);
     // ---- stage dV rows of this tile (coalesced 384 B per body row), 8 rows = 24 loads in flight ----
     {
       const float* src0 = grad_verts + ((size_t)gb0 * V + vbase) * 3 + lane;
       float* dstc = g_s + lane * TPITCH;
+      if (nrows_valid == 32 && ncols == TILE_V * 3) {
 #pragma unroll 1
-      for (int r0 = 0; r0 < 32; r0 += 8) {
-        float t[24];
-#pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-          const int r = r0 + rr;
-          const float* src = src0 + (size_t)r * V * 3;
-          const bool rowok = r < nrows_valid;
-          t[rr * 3 + 0] = (rowok && lane < ncols) ? ld_stream(src) : 0.f;
-          t[rr * 3 + 1] = (rowok && lane + 32 < ncols) ? ld_stream(src + 32) : 0.f;
-          t[rr * 3 + 2] = (rowok && lane + 64 < ncols) ? ld_stream(src + 64) : 0.f;
-        }
-#pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-          dstc[r0 + rr] = t[rr * 3 + 0];
-          dstc[32 * TPITCH + r0 + rr] = t[rr * 3 + 1];
-          dstc[64 * TPITCH + r0 + rr] = t[rr * 3 + 2];
-        }
+        for (int r0 = 0; r0 < 32; r0 += 8) stage_rows<true>(src0, (size_t)V * 3, dstc, r0, 32, 96, lane);
+      } else {
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += 8) stage_rows<false>(src0, (size_t)V * 3, dstc, r0, nrows_valid, ncols, lane);
       }
     }
     __syncwarp();
-    fetch_vp(Q, chunk, meta + PF);
+    // ---- arithmetic in place on the tile: 8 units of 4 vertices, v_posed prefetched one unit ahead ----
+    fetch_vp4(Q, chunk, meta + BPF);
     skin_bwd(P, st, A_s, dA_s, lane, meta, wts, true, g_lane);
-    fetch_vp(P, chunk, meta + 2 * PF);
-    skin_bwd(Q, st, A_s, dA_s, lane, meta + PF, wts + PF, false, g_lane);
-    fetch_vp(Q, chunk, meta + 3 * PF);
-    skin_bwd(P, st, A_s, dA_s, lane, meta + 2 * PF, wts + 2 * PF, false, g_lane);
-    const int next = tile + BWD_WARPS;
-    if (next < tile_end) fetch_vp(P, chunk0 + next * tstride, vmeta + next * TILE_V);
-    skin_bwd(Q, st, A_s, dA_s, lane, meta + 3 * PF, wts + 3 * PF, false, g_lane);
+#pragma unroll 1
+    for (int u = 1; u < TILE_V / BPF - 1; u += 2) {
+      fetch_vp4(P, chunk, meta + (u + 1) * BPF);
+      skin_bwd(Q, st, A_s, dA_s, lane, meta + u * BPF, wts + u * BPF, false, g_lane);
+      fetch_vp4(Q, chunk, meta + (u + 2) * BPF);
+      skin_bwd(P, st, A_s, dA_s, lane, meta + (u + 1) * BPF, wts + (u + 1) * BPF, false, g_lane);
+    }
+    skin_bwd(Q, st, A_s, dA_s, lane, meta + (TILE_V - BPF), wts + (TILE_V - BPF), false, g_lane);
     // every tile starts with all four slots reloaded: close this tile's accumulators now
     flush_slot(st.d0, dA_s, st.j0, lane);
     flush_slot(st.d1, dA_s, st.j1, lane);
@@ -298,10 +338,9 @@ lbs_bwd_kernel(const float* __restrict__ vpB, int G, const float* __restrict__ A
   atomicAdd(&dtr_s[32 + lane], st.sy);
   atomicAdd(&dtr_s[64 + lane], st.sz);
   __syncthreads();
-  // partials in the group-blocked layout [split][group][288][32] / [split][group][3][32]
-  float* dA_out = dA_part + ((size_t)blockIdx.y * G + g) * AG_WORDS;
-  for (int r = threadIdx.x; r < AG_WORDS; r += BWD_THREADS) dA_out[r] = dA_s[r];
-  if (threadIdx.x < 96) dtr_part[((size_t)blockIdx.y * G + g) * 96 + threadIdx.x] = dtr_s[threadIdx.x];
+  // accumulate into the slab-wide buffers [group][288][32] / [group][3][32]
+  accumulate_rows(dA_acc + (size_t)g * AG_WORDS, dA_s, NJ * AELEMS, warp, BWD_WARPS, lane);
+  if (warp < 3) atomicAdd(dtr_acc + (size_t)g * 96 + warp * 32 + lane, dtr_s[warp * 32 + lane]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -340,18 +379,13 @@ int launch_lbs_fwd(const DevModel& m, const float* vpB, int S, const float* A_bl
   return 0;
 }
 
-// number of dA / dtransl partials the backward skinning kernel writes per body for slab pitch S
-int lbs_bwd_splits(const DevModel& m, int S, int num_sms) {
-  int nsplit, tps;
-  split_plan(m.ntiles, (S + 31) / 32, num_sms, BWD_WARPS, nsplit, tps);
-  return nsplit;
-}
-
 // Sw = active slab width (multiple of 32, >= nb): rows of absent bodies get zero dvp / partials
+// dA_acc [S/32][288][32] and dtr_acc [S/32][3][32] must be zeroed by the caller; CTAs add into them
 int launch_lbs_bwd(const DevModel& m, const float* vpB, int S, int Sw, const float* A_blk, int b0, int nb,
                    const float* grad_verts, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_part,
-                   float* dtr_part, int nsplit, cudaStream_t st) {
-  const int tps = ((m.ntiles + nsplit - 1) / nsplit + BWD_WARPS - 1) / BWD_WARPS * BWD_WARPS;
+                   float* dtr_part, int num_sms, cudaStream_t st) {
+  int nsplit, tps;
+  split_plan(m.ntiles, Sw / 32, num_sms, BWD_WARPS, nsplit, tps);
   B200_CUDA_TRY(cudaFuncSetAttribute(lbs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
   LaunchTimer _timer("lbs_bwd", st);
   lbs_bwd_kernel<<<dim3(Sw / 32, nsplit), BWD_THREADS, BWD_SMEM, st>>>(vpB, S / 32, A_blk, b0, nb, grad_verts, m.V,

@@ -77,6 +77,15 @@ __device__ __forceinline__ void flush_slot(float (&d)[AELEMS], float* dA_s, int 
   }
 }
 
+// add a CTA's shared accumulators [rows][32] into the slab-wide buffer (fp32 RED, rows that stayed 0 skipped)
+__device__ __forceinline__ void accumulate_rows(float* __restrict__ dst, const float* src_s, int rows, int warp,
+                                                int nwarps, int lane) {
+  for (int r = warp; r < rows; r += nwarps) {
+    const float v = src_s[r * 32 + lane];
+    if (__any_sync(0xffffffffu, v != 0.f)) atomicAdd(dst + r * 32 + lane, v);
+  }
+}
+
 // x -> bf16 hi | bf16 lo << 16   (x ~ hi + lo to 16 mantissa bits)
 __device__ __forceinline__ uint32_t pack_hi_lo(float x) {
   const __nv_bfloat16 hi = __float2bfloat16_rn(x);

@@ -139,6 +139,12 @@ def test_backward_full(engine, oracle64, dev, mode, axis_angle):
     assert _rel(gp.cpu().double().reshape(rp.shape), rp) < tol
     assert _rel(gt.cpu().double(), rt) < tol
     assert _rel(gc.cpu().double(), rc) < tol
+    # same gradients when forward keeps the blend output for backward instead of recomputing it
+    out = engine.forward(d(betas), d(pose), d(trans), d(cam), axis_angle=axis_angle, mode=m, save=True)
+    sb, sp, st_, sc = engine.backward(d(betas), d(pose), d(trans), d(cam), out[1], d(dV), d(dJ), d(dJ2),
+                                      axis_angle=axis_angle, mode=m, saved=out[3])
+    for a_, b_ in ((sb, gb), (sp, gp), (st_, gt), (sc, gc)):
+        assert _rel(a_, b_) < 1e-5
 
 
 @pytest.mark.parametrize("mode", ["fp32_simt", "fp32"])
