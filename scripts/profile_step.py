@@ -22,7 +22,7 @@ dV, dJ = make_upstream_grads(B, 0)
 betas, rot, trans, dV, dJ = (t.to(dev) for t in (x["betas"], x["rotmats"], x["trans"], dV, dJ))
 m = _lib.MODES[mode]
 for _ in range(steps):
-    eng.forward(betas, rot, trans, None, mode=m)
-    eng.backward(betas, rot, trans, None, None, dV, dJ, None, mode=m)
+    sv = eng.forward(betas, rot, trans, None, mode=m, save=True)[3]
+    eng.backward(betas, rot, trans, None, None, dV, dJ, None, mode=m, saved=sv)
 torch.cuda.synchronize()
 print("ok")
