@@ -48,7 +48,7 @@ struct Plan {
   size_t off_feat, off_featf, off_A, off_jposed, off_vpT;
   size_t off_dvp_hi, off_dvp_lo, off_dA, off_dtr, off_dJtot, off_dfeat;
   size_t total;
-  size_t saved_slab_bytes;   // per slab: A_blk [S/32][288][32] then vpB [n_pad][S]
+  size_t saved_slab_bytes;   // per slab: A_blk [S/32][24][3][32][4] then vpB [n_pad/4][S][4]
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -383,6 +383,13 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
         rc = launch_blend_fwd_umma(d, a->mode, feat, S, Sw, vpT, row_begin, d.n_pad, st);
       if (rc) return rc;
     }
+    {  // the gradient GEMM reads whole 64-row K slabs: rows between row_end and the slab boundary must be finite
+      const size_t c0 = (size_t)row_end / 8, c1 = (size_t)round_up(row_end, 64) / 8;
+      if (c1 > c0) {
+        B200_CUDA_TRY(cudaMemsetAsync(dvp_hi + c0 * S * 8, 0, (c1 - c0) * S * 16, st));
+        if (dvp_lo) B200_CUDA_TRY(cudaMemsetAsync(dvp_lo + c0 * S * 8, 0, (c1 - c0) * S * 16, st));
+      }
+    }
     if (have_v)
       if ((rc = launch_lbs_bwd(d, vpT, S, Sw, A_T, b0, nb, a->grad_vertices, dvp_hi, dvp_lo, dA_part, dtr_part,
                                m->num_sms, st)))
@@ -390,7 +397,7 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
     if (have_j)
       if ((rc = launch_joints_bwd(d, vpT, S, Sw, A_T, b0, nb, dJ, dvp_hi, dvp_lo, dA_part, dtr_part, st))) return rc;
     if (a->mode == B200SMPL_MODE_FP32_SIMT)
-      rc = launch_blend_bwd_simt(d, dvp_hi, dvp_lo, Sw, dfeat_part, row_begin, row_end, st);
+      rc = launch_blend_bwd_simt(d, dvp_hi, dvp_lo, S, Sw, dfeat_part, row_begin, row_end, st);
     else
       rc = launch_blend_bwd_umma(d, a->mode, dvp_hi, dvp_lo, S, Sw, dfeat_part, k_splits, row_begin, row_end, st);
     if (rc) return rc;

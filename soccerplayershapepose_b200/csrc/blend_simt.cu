@@ -38,9 +38,9 @@ blend_fwd_simt_kernel(const float* __restrict__ W32, int n_pad, int nf, const fl
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {   // group-blocked layout: chunk (n / 96, group), line n % 96
+  for (int i = 0; i < 4; ++i) {   // vpB [n/4][S][4] (skin_common.cuh)
     const size_t n = (size_t)(n0 + ty * 4 + i);
-    vpT[((n / 96) * (S / 32) + (s0 >> 5)) * (size_t)(96 * 32) + (n % 96) * 32 + tx] = acc[i];
+    vpT[((n >> 2) * (size_t)S + s0 + tx) * 4 + (n & 3)] = acc[i];
   }
 }
 
@@ -58,7 +58,7 @@ int launch_blend_fwd_simt(const DevModel& m, const float* featf, int S, int Sw, 
 // one block per (8 features, 32 bodies); threads reduce over n with a shared-memory tile.
 __global__ void __launch_bounds__(256)
 blend_bwd_simt_kernel(const float* __restrict__ W32, int n_pad, int nf, const __nv_bfloat16* __restrict__ dvp_hi,
-                      const __nv_bfloat16* __restrict__ dvp_lo, float* __restrict__ dfeat, int nf_pad,
+                      const __nv_bfloat16* __restrict__ dvp_lo, int S, float* __restrict__ dfeat, int nf_pad,
                       int row_begin, int row_end) {
   __shared__ float sD[32][33];   // [s][n]
   __shared__ float sW[8][33];    // [f][n]
@@ -70,7 +70,8 @@ blend_bwd_simt_kernel(const float* __restrict__ W32, int n_pad, int nf, const __
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int s = ty * 4 + i;
-      const size_t o = (size_t)(s0 + s) * n_pad + n0 + tx;
+      const size_t nn = (size_t)(n0 + tx);   // dvp [n/8][S][8] (skin_common.cuh)
+      const size_t o = ((nn >> 3) * (size_t)S + s0 + s) * 8 + (nn & 7);
       float v = 0.f;
       if (n0 + tx < row_end) {
         v = __bfloat162float(dvp_hi[o]);
@@ -87,11 +88,11 @@ blend_bwd_simt_kernel(const float* __restrict__ W32, int n_pad, int nf, const __
   if (f < nf_pad) dfeat[(size_t)(s0 + tx) * nf_pad + f] = (f < nf) ? acc : 0.f;
 }
 
-int launch_blend_bwd_simt(const DevModel& m, const __nv_bfloat16* dvp_hi, const __nv_bfloat16* dvp_lo, int Sw,
+int launch_blend_bwd_simt(const DevModel& m, const __nv_bfloat16* dvp_hi, const __nv_bfloat16* dvp_lo, int S, int Sw,
                           float* dfeat, int row_begin, int row_end, cudaStream_t st) {
   dim3 grid(m.fl.nf_pad / 8, Sw / 32);
   LaunchTimer _timer_88("blend_bwd_simt", st);
-  blend_bwd_simt_kernel<<<grid, dim3(32, 8), 0, st>>>(m.W32, m.n_pad, m.fl.nf, dvp_hi, dvp_lo, dfeat,
+  blend_bwd_simt_kernel<<<grid, dim3(32, 8), 0, st>>>(m.W32, m.n_pad, m.fl.nf, dvp_hi, dvp_lo, S, dfeat,
                                                       m.fl.nf_pad, row_begin, row_end);
   B200_LAUNCH_CHECK("blend_bwd_simt");
   return 0;

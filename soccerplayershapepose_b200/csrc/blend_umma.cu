@@ -1,13 +1,14 @@
 // Blend-shape contractions on the 5th-gen tensor cores (tcgen05 + TMEM, operands staged by TMA).
 //
-//   forward : vpT[n][b]   = sum_k Wf[n][k]   * feat[b][k]      (SURVEY.md section 8 rows a4 + a7:
+//   forward : vp[b][n]    = sum_k feat[b][k]  * Wf[n][k]       (SURVEY.md section 8 rows a4 + a7:
 //             shape blend + pose-corrective blend + template, all folded into one K axis)
 //   backward: dfeat[b][f] = sum_n dvp[b][n]  * Wb[f][n]        (data gradient, split-K over n)
 //
-// Both are the same kernel: D[m][n] (fp32, row-major) = sum_seg sum_k A_seg[m][k] * B_seg[n][k] with
-// bf16 K-major operands.  fp32 accuracy comes from the bf16x3 error-compensated split laid out
-// along K (see FeatLayout in common.cuh), so the tensor pipe only ever sees kind::f16 MMAs with
-// fp32 accumulation in TMEM.
+// In both the M axis (= TMEM lane = epilogue thread) is the BODY, so the skinning kernels on either
+// side (lane = body) exchange data with the GEMMs in layouts where a warp moves 512 contiguous bytes
+// per instruction (skin_common.cuh).  bf16 K-major operands; fp32 accuracy comes from the bf16x3
+// error-compensated split laid out along K (see FeatLayout in common.cuh), so the tensor pipe only
+// ever sees kind::f16 MMAs with fp32 accumulation in TMEM.
 //
 // CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2-5 epilogue
 // (tcgen05.ld -> registers -> 16-byte global stores).  One 128 x BN output tile per CTA; smem ring
@@ -25,8 +26,10 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
 constexpr int MAX_SEG = 3;
 
-struct GemmMaps {
-  CUtensorMap a[MAX_SEG];
+// backward operands: A = dvp chunks [n/8][S][8] (plain pointers, pulled with bulk copies into the
+// no-swizzle core-matrix layout), B = Wb rows through a 128-byte-swizzle tensor map
+struct GemmOps {
+  const __nv_bfloat16* a[MAX_SEG];
   CUtensorMap b[MAX_SEG];
 };
 
@@ -64,6 +67,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// global -> shared bulk-async copy (TMA unit, no tensor map), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -114,6 +123,13 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
          (2ull << 61);
 }
 
+// K-major, no-swizzle descriptor: core matrix = 8 rows x 16 bytes, contiguous (128 B); LBO = byte distance
+// between core matrices adjacent along K, SBO = between core matrices adjacent along M/N
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46);
+}
+
 // cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b format BF16 [7,10)=[10,13)=1, K-major both,
 // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
@@ -128,14 +144,13 @@ struct GemmSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-// grid: (m tiles, n tiles, k splits)
-// BLOCKED = false: D is row-major with leading dimension ldd (+ blockIdx.z * split_stride).
-// BLOCKED = true : D is the group-blocked blend output: element (row n, column s) lives at
-//                  ((n / 96) * ldd + s / 32) * 3072 + (n % 96) * 32 + s % 32   with ldd = groups per slab.
-template <int BN, int STAGES, int MIN_CTAS, bool BLOCKED>
-__global__ void __launch_bounds__(GEMM_THREADS, MIN_CTAS)
-umma_gemm_kernel(const __grid_constant__ GemmMaps maps, int nseg, int slab_begin, int slab_end, int slabs_per_split,
-                 int a_row0, int b_row0, float* __restrict__ D, int ldd, long long split_stride) {
+// Backward (data-gradient) GEMM.  grid: (body tiles of 128, 1, k splits)
+//   D[split][body][f] = sum_seg sum_{n in split} A_seg[body][n] * B_seg[f][n],   D row-major, ld = ldd
+// A stage = 8 chunks x (128 bodies x 16 B): chunk c at +2048 B  ->  LBO = 2048, SBO = 128.
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ GemmOps ops, int nseg, int S, int slab_begin, int slab_end,
+                 int slabs_per_split, float* __restrict__ D, int ldd, long long split_stride) {
   using SM = GemmSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   extern __shared__ unsigned char smem_dyn[];
@@ -146,17 +161,14 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, int nseg, int slab_begin
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int m0 = blockIdx.x * BM;
   const int s_begin = slab_begin + blockIdx.z * slabs_per_split;
   const int s_end = min(slab_end, s_begin + slabs_per_split);
   const int slabs = max(0, s_end - s_begin);
   const int total_iters = slabs * nseg;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < nseg; ++s) {
-      prefetch_tmap(&maps.a[s]);
-      prefetch_tmap(&maps.b[s]);
-    }
+    for (int s = 0; s < nseg; ++s) prefetch_tmap(&ops.b[s]);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -176,7 +188,7 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, int nseg, int slab_begin
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== producer: 8 bulk copies (A chunks) + one tensor-map load (B) per stage =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -186,8 +198,10 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, int nseg, int slab_begin
         unsigned char* sa = smem + stage * SM::STAGE_BYTES;
         unsigned char* sb = sa + SM::A_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
-        tma_load_2d(sa, &maps.a[seg], &full_bar[stage], slab * BK, a_row0 + m0);
-        tma_load_2d(sb, &maps.b[seg], &full_bar[stage], slab * BK, b_row0 + n0);
+        const __nv_bfloat16* asrc = ops.a[seg] + ((size_t)slab * 8 * S + m0) * 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) bulk_g2s(sa + c * 2048, asrc + (size_t)c * S * 8, 2048, &full_bar[stage]);
+        tma_load_2d(sb, &ops.b[seg], &full_bar[stage], slab * BK, 0);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -204,11 +218,11 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, int nseg, int slab_begin
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * SM::STAGE_BYTES);
-        const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + SM::A_BYTES);
+        const uint64_t da = make_nosw_desc(sa, 2048, 128), db = make_sw128_desc(sa + SM::A_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 32 bytes (16 bf16) along K inside the swizzle row: +2 in 16-byte units
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+          // A: two 16-byte chunks per UMMA_K -> +4096 B; B: +32 bytes inside the swizzle row (16-byte units)
+          umma_bf16(tmem_base, da + (uint64_t)(k * (4096 >> 4)), db + 2 * k, idesc, (it | k) != 0);
         }
         umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
         if (it == total_iters - 1) umma_commit(tmem_full_bar);
@@ -222,16 +236,7 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, int nseg, int slab_begin
     // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
-    float* drow;
-    long long cstep;                       // pointer step per 32 output columns
-    if (BLOCKED) {
-      const long long n = (long long)a_row0 + row;
-      drow = D + ((n / 96) * ldd + n0 / 32) * 3072LL + (n % 96) * 32;
-      cstep = 3072;
-    } else {
-      drow = D + (long long)blockIdx.z * split_stride + (long long)row * ldd + n0;
-      cstep = 32;
-    }
+    float* drow = D + (long long)blockIdx.z * split_stride + (long long)row * ldd;
     if (total_iters > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
@@ -239,12 +244,12 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, int nseg, int slab_begin
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        float* o = drow + (long long)(c0 / 32) * cstep;
+        float* o = drow + c0;
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
           *reinterpret_cast<uint4*>(o + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
-    } else if (!BLOCKED) {
+    } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 4) *reinterpret_cast<uint4*>(drow + c0) = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -258,12 +263,11 @@ umma_gemm_kernel(const __grid_constant__ GemmMaps maps, int nseg, int slab_begin
 }
 
 // ---------------------------------------------------------------------------------------------
-// Forward blend GEMM, W-stationary.  The generic kernel above re-reads both operands for every
-// 128x128 tile (1.9 GB of L2->SM traffic at B=4096: L2-bound).  Here a CTA keeps its 128-row slice
-// of the model operand (all K: up to 11 x 16 KB) resident in shared memory and streams only the
-// feature tiles of its share of the bodies through a 3-stage ring, accumulating in two alternating
-// TMEM buffers so the epilogue of body tile i overlaps the MMAs of tile i+1.
-//   vpB (group-blocked) [n][s] = sum_k Wf[n][k] * feat[s][k]
+// Forward blend GEMM, W-stationary.  A CTA keeps its 128-row slice of the model operand (all K: up to
+// 11 x 16 KB) resident in shared memory and streams only the feature tiles of its share of the bodies
+// through a 3-stage ring, accumulating in two alternating TMEM buffers so the epilogue of body tile i
+// overlaps the MMAs of tile i+1.  M = 128 bodies (A operand = streamed features), N = 128 model rows
+// (B operand = resident slice): the epilogue thread owns one body and writes float4s of vpB [n/4][S][4].
 // grid: (row tiles, body chunks); CTA = 6 warps (TMA, MMA, 4 epilogue).
 // ---------------------------------------------------------------------------------------------
 constexpr int WS_STAGES = 3;
@@ -272,7 +276,7 @@ constexpr int WS_BN = 128;
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 blend_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_f, int nslab,
-                    int row0, int ntiles_n, int tiles_per_chunk, float* __restrict__ vpB, int G) {
+                    int row0, int ntiles_n, int tiles_per_chunk, float4* __restrict__ vpB, int S) {
   constexpr int SLAB = BM * BK * 2;                 // 16 KB: 128 rows x 64 bf16 (both operands)
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -346,8 +350,8 @@ blend_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
         for (int s = 0; s < nslab; ++s) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = make_sw128_desc(smem_u32(w_s + s * SLAB));
-          const uint64_t db = make_sw128_desc(smem_u32(f_s + stage * SLAB));
+          const uint64_t da = make_sw128_desc(smem_u32(f_s + stage * SLAB));   // A: 128 bodies x 64 features
+          const uint64_t db = make_sw128_desc(smem_u32(w_s + s * SLAB));       // B: 128 model rows x 64
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (s | k) != 0);
           umma_commit(&empty_bar[stage]);
@@ -358,8 +362,7 @@ blend_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     }
   } else {
     const int q = warp & 3;
-    const long long n = (long long)m0 + q * 32 + lane;
-    float* rowbase = vpB + (n / 96) * (long long)G * 3072LL + (n % 96) * 32;
+    float4* colbase = vpB + (size_t)(m0 >> 2) * S + q * 32 + lane;     // this lane's body column, chunk m0/4
     uint32_t tphase[2] = {0u, 0u};
     int acc = 0;
     for (int nt = nt_begin; nt < nt_end; ++nt, acc ^= 1) {
@@ -367,13 +370,14 @@ blend_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       tphase[acc] ^= 1;
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < WS_BN; c0 += 32) {
+      for (int c0 = 0; c0 < BM; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * WS_BN + c0), v);
-        float* o = rowbase + (long long)(nt * (WS_BN / 32) + c0 / 32) * 3072LL;
+        float4* o = colbase + (size_t)(c0 >> 2) * S + (size_t)nt * WS_BN;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<uint4*>(o + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < 8; ++i)
+          o[(size_t)i * S] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
       }
       tc_fence_before();
       __syncwarp();
@@ -453,8 +457,8 @@ int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat
   }
   const int tpc = (ntiles_n + chunks - 1) / chunks;
   LaunchTimer _timer("blend_fwd_umma", st);
-  blend_fwd_ws_kernel<<<dim3(mtiles, (ntiles_n + tpc - 1) / tpc), GEMM_THREADS, smem, st>>>(map_w, map_f, nslab, row_begin,
-                                                                                         ntiles_n, tpc, vpT, S / 32);
+  blend_fwd_ws_kernel<<<dim3(mtiles, (ntiles_n + tpc - 1) / tpc), GEMM_THREADS, smem, st>>>(
+      map_w, map_f, nslab, row_begin, ntiles_n, tpc, reinterpret_cast<float4*>(vpT), S);
   B200_LAUNCH_CHECK("blend_fwd_umma");
   return 0;
 }
@@ -470,46 +474,46 @@ int blend_bwd_umma_splits(const DevModel& m, int mode, int S, int num_sms) {
 }
 
 template <int BN>
-static int launch_bwd_bn(const GemmMaps& maps, int nseg, int slab_begin, int slab_end, int nsplit, int Sw,
+static int launch_bwd_bn(const GemmOps& ops, int nseg, int S, int slab_begin, int slab_end, int nsplit, int Sw,
                          float* dfeat_part, int nf_pad, long long split_stride, cudaStream_t st) {
   using SM = GemmSmem<BN, BWD_STAGES>;
-  auto kern = umma_gemm_kernel<BN, BWD_STAGES, 1, false>;
+  auto kern = umma_gemm_kernel<BN, BWD_STAGES>;
   B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
   const int slabs = slab_end - slab_begin;
   const int sps = (slabs + nsplit - 1) / nsplit;
   dim3 grid(Sw / BM, 1, nsplit);
   LaunchTimer _timer_316("blend_bwd_umma", st);
-  kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(maps, nseg, slab_begin, slab_end, sps, 0, 0, dfeat_part, nf_pad,
-                                              split_stride);
+  kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(ops, nseg, S, slab_begin, slab_end, sps, dfeat_part, nf_pad, split_stride);
   B200_LAUNCH_CHECK("blend_bwd_umma");
   return 0;
 }
 
-// dfeat_part[nsplit][S][nf_pad]; rows [0, Sw) of every split are written
+// dfeat_part[nsplit][S][nf_pad]; rows [0, Sw) of every split are written.  dvp rows in
+// [row_end, round_up(row_end, 64)) must be finite (the api zeroes them): the model operand is zero there.
 int launch_blend_bwd_umma(const DevModel& m, int mode, const __nv_bfloat16* dvp_hi, const __nv_bfloat16* dvp_lo,
                           int S, int Sw, float* dfeat_part, int nsplit, int row_begin, int row_end,
                           cudaStream_t st) {
-  GemmMaps maps;
-  memset(&maps, 0, sizeof(maps));
+  GemmOps ops;
+  memset(&ops, 0, sizeof(ops));
   const int nf_pad = m.fl.nf_pad;
   int rc;
   const bool split3 = (mode != B200SMPL_MODE_BF16) && dvp_lo != nullptr;
   const int nseg = split3 ? 3 : 1;
-  // K extent = row_end: columns beyond it are never read (TMA zero-fills out-of-bounds)
-  if ((rc = make_map(&maps.a[0], dvp_hi, row_end, Sw, m.n_pad, BM))) return rc;
-  if ((rc = make_map(&maps.b[0], m.Wb_hi, row_end, nf_pad, m.n_pad, nf_pad))) return rc;
+  // K extent = row_end: model columns beyond it are never read (TMA zero-fills out-of-bounds)
+  ops.a[0] = dvp_hi;
+  if ((rc = make_map(&ops.b[0], m.Wb_hi, row_end, nf_pad, m.n_pad, nf_pad))) return rc;
   if (split3) {
-    if ((rc = make_map(&maps.a[1], dvp_lo, row_end, Sw, m.n_pad, BM))) return rc;
-    if ((rc = make_map(&maps.b[1], m.Wb_hi, row_end, nf_pad, m.n_pad, nf_pad))) return rc;
-    if ((rc = make_map(&maps.a[2], dvp_hi, row_end, Sw, m.n_pad, BM))) return rc;
-    if ((rc = make_map(&maps.b[2], m.Wb_lo, row_end, nf_pad, m.n_pad, nf_pad))) return rc;
+    ops.a[1] = dvp_lo;
+    if ((rc = make_map(&ops.b[1], m.Wb_hi, row_end, nf_pad, m.n_pad, nf_pad))) return rc;
+    ops.a[2] = dvp_hi;
+    if ((rc = make_map(&ops.b[2], m.Wb_lo, row_end, nf_pad, m.n_pad, nf_pad))) return rc;
   }
   const int slab_begin = row_begin / BK, slab_end = (row_end + BK - 1) / BK;
   const long long split_stride = (long long)S * nf_pad;
   switch (nf_pad) {
-    case 224: return launch_bwd_bn<224>(maps, nseg, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
-    case 208: return launch_bwd_bn<208>(maps, nseg, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
-    case 240: return launch_bwd_bn<240>(maps, nseg, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
+    case 224: return launch_bwd_bn<224>(ops, nseg, S, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
+    case 208: return launch_bwd_bn<208>(ops, nseg, S, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
+    case 240: return launch_bwd_bn<240>(ops, nseg, S, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
     default: return fail(B200SMPL_ERR_INVALID, "unsupported num_betas for the tensor-core backward (nf_pad=" + std::to_string(nf_pad) + ")");
   }
 }

@@ -177,7 +177,7 @@ int launch_pose_bwd(const DevModel& m, const float* betas, const float* pose, bo
 
 int launch_blend_fwd_simt(const DevModel& m, const float* featf, int S, int Sw, float* vpT, int row_begin,
                           int row_end, cudaStream_t st);
-int launch_blend_bwd_simt(const DevModel& m, const __nv_bfloat16* dvp_hi, const __nv_bfloat16* dvp_lo, int Sw,
+int launch_blend_bwd_simt(const DevModel& m, const __nv_bfloat16* dvp_hi, const __nv_bfloat16* dvp_lo, int S, int Sw,
                           float* dfeat, int row_begin, int row_end, cudaStream_t st);
 int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat, int S, int Sw, float* vpT,
                           int row_begin, int row_end, cudaStream_t st);

@@ -6,46 +6,50 @@
 //   sum_i  A_i . [ q_ji ; c_ji ],   q_ji = sum_v Jr[j][v] w_vi p_v  (linear in the blend features),
 // so the q_ji are extra "virtual" rows of the blend GEMM, grouped 32 q-groups (96 rows) per virtual
 // tile, and a joint costs a handful of 3x4 transforms.  These kernels are the skinning kernels of
-// lbs.cu specialised to virtual tiles: lane = body, group transforms in shared memory via one TMA
-// bulk copy, q rows prefetched from the group-blocked blend output, results transposed through a
-// [96][33] shared tile and written as contiguous row segments of joints (B, 90, 3) / dvp.
-// The 24 chain joints are written by the pose kernel; reprojection is the orthographic kernel.
+// lbs.cu specialised to virtual tiles: lane = body, every warp owns a contiguous run of the flat
+// (body group, virtual tile) list, transforms come straight from A_blk (L1/L2), q rows are read as
+// float4 from the blend output, results are transposed through a per-warp shared tile and written as
+// contiguous row segments of joints (B, 90, 3); the backward emits dq as 16-byte dvp chunks and adds
+// dA / dtransl with fp32 REDs.  The 24 chain joints are written by the pose kernel; reprojection is
+// the orthographic kernel.
 #include "skin_common.cuh"
 
 namespace b200smpl {
 
-constexpr int JW = 6;                       // warps per CTA; one CTA per body group, warps stride over the virtual tiles
+constexpr int JW = 8;                       // warps per CTA
 constexpr int JT = JW * 32;
-constexpr size_t JFWD_SMEM = (size_t)(AG_WORDS + JW * TTILE_WORDS) * 4 + 16;
-constexpr size_t JBWD_SMEM = (size_t)(2 * AG_WORDS + 96 + JW * 2 * TTILE_WORDS) * 4 + 16;
+constexpr int JROW = 97;                    // staging tile [32 bodies][97]: scalar accesses only, odd pitch
+constexpr size_t J_SMEM = (size_t)JW * 32 * JROW * 4;
+
+__device__ __forceinline__ void load_q96(float (&q)[96], const float4* __restrict__ p, size_t S) {
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    const float4 v = ld_stream4(p + i * S);
+    q[i * 4] = v.x; q[i * 4 + 1] = v.y; q[i * 4 + 2] = v.z; q[i * 4 + 3] = v.w;
+  }
+}
 
 __global__ void __launch_bounds__(JT, 1)
-joints_fwd_kernel(DevModel m, const float* __restrict__ vpB, int G, const float* __restrict__ A_blk, int b0, int nb,
-                  const float* __restrict__ transl, float* __restrict__ joints) {
+joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int S, const float4* __restrict__ A_blk, int b0, int nb,
+                  int ngroups, const float* __restrict__ transl, float* __restrict__ joints) {
   extern __shared__ __align__(128) float smem[];
-  float* A_s = smem;
-  float* tiles = smem + AG_WORDS;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(tiles + JW * TTILE_WORDS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x, col0 = g * 32, gb0 = b0 + col0;
-  if (threadIdx.x == 0) fetch_group_transforms(A_s, A_blk, g, bar);
-  float tx = 0.f, ty = 0.f, tz = 0.f;
-  if (transl != nullptr && col0 + lane < nb) {
-    const float* t = transl + (size_t)(gb0 + lane) * 3;
-    tx = t[0]; ty = t[1]; tz = t[2];
-  }
-  __syncthreads();
-  float* out_s = tiles + warp * TTILE_WORDS;
-  float* out_lane = out_s + lane;
-  const int nrows = min(32, nb - col0);
+  float* tile = smem + warp * 32 * JROW;
+  float* my_row = tile + lane * JROW;
+  const long long total = (long long)ngroups * m.ntv;
+  const int gw = blockIdx.x * JW + warp, nw = gridDim.x * JW;
+  const int item0 = (int)(total * gw / nw), item1 = (int)(total * (gw + 1) / nw);
   const size_t ncol_all = (size_t)m.njout * 3;
-  bool waited = false;
-  for (int tv = warp; tv < m.ntv; tv += JW) {
+  for (int item = item0; item < item1; ++item) {
+    const int g = item / m.ntv, tv = item - g * m.ntv;
     float q[96];
-    const float* chunk = vpB + ((size_t)(m.ntiles + tv) * G + g) * CHUNK_WORDS + lane;
-#pragma unroll
-    for (int i = 0; i < 96; ++i) q[i] = ld_stream(chunk + i * 32);
-    if (!waited) { mbar_wait(bar, 0); waited = true; }
+    load_q96(q, vpB + (size_t)((m.ntiles + tv) * 24) * S + (size_t)g * 32 + lane, S);
+    const float4* A_g = A_blk + (size_t)g * (AG_WORDS / 4);
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    if (transl != nullptr && g * 32 + lane < nb) {
+      const float* t = transl + (size_t)(b0 + g * 32 + lane) * 3;
+      tx = t[0]; ty = t[1]; tz = t[2];
+    }
     const uint32_t* meta = m.qmeta + tv * 32;
     const float* coef = m.qcoef + tv * 32;
     float a[AELEMS];
@@ -54,112 +58,109 @@ joints_fwd_kernel(DevModel m, const float* __restrict__ vpB, int G, const float*
     for (int i = 0; i < 32; ++i) {
       const uint32_t mt = __ldg(meta + i);
       if (!(mt & (1u << 14))) continue;
-      if ((mt & (1u << 5)) || i == 0) load_slot(a, A_s, mt & 31, lane);
+      if ((mt & (1u << 5)) || i == 0) load_slot_g(a, A_g, mt & 31, lane);
       const float c = __ldg(coef + i);
       const float qx = q[i * 3], qy = q[i * 3 + 1], qz = q[i * 3 + 2];
       x += fmaf(a[0], qx, fmaf(a[1], qy, fmaf(a[2], qz, a[3] * c)));
       y += fmaf(a[4], qx, fmaf(a[5], qy, fmaf(a[6], qz, a[7] * c)));
       z += fmaf(a[8], qx, fmaf(a[9], qy, fmaf(a[10], qz, a[11] * c)));
       if (mt & (1u << 13)) {                               // last term of this joint
-        float* o = out_lane + ((mt >> 8) & 31) * (3 * TPITCH);
-        o[0] = x; o[TPITCH] = y; o[2 * TPITCH] = z;
+        float* o = my_row + ((mt >> 8) & 31) * 3;
+        o[0] = x; o[1] = y; o[2] = z;
         x = tx; y = ty; z = tz;
       }
     }
     __syncwarp();
-    // flush the tile's joints: 3 nj contiguous floats per body row, flattened so that loads/stores pipeline
+    // flush the tile's joints: 3 nj contiguous floats per body row
+    const int nrows = min(32, nb - g * 32);
     const int ncols = m.vt_nj[tv] * 3;
-    float* dst0 = joints + (size_t)gb0 * ncol_all + (size_t)(NJ + m.vt_j0[tv]) * 3;
+    float* dst0 = joints + (size_t)(b0 + g * 32) * ncol_all + (size_t)(NJ + m.vt_j0[tv]) * 3;
     for (int idx = lane; idx < nrows * ncols; idx += 32) {
       const int r = idx / ncols, c = idx - r * ncols;
-      dst0[(size_t)r * ncol_all + c] = out_s[c * TPITCH + r];
+      dst0[(size_t)r * ncol_all + c] = tile[r * JROW + c];
     }
     __syncwarp();
   }
 }
 
 // backward over virtual tiles.  dJ: total joint gradient (B, NJout, 3).
-//   dq -> virtual columns of dvp ; dA -> dA_part[blockIdx.y] ; dtransl partial = sum over the tile's joints
+//   dq -> virtual rows of dvp ; dA, dtransl -> fp32 REDs into the slab accumulators
 __global__ void __launch_bounds__(JT, 1)
-joints_bwd_kernel(DevModel m, const float* __restrict__ vpB, int G, const float* __restrict__ A_blk, int b0, int nb,
-                  const float* __restrict__ dJ, __nv_bfloat16* __restrict__ dvp_hi,
+joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int S, const float4* __restrict__ A_blk, int b0, int nb,
+                  int ngroups, const float* __restrict__ dJ, __nv_bfloat16* __restrict__ dvp_hi,
                   __nv_bfloat16* __restrict__ dvp_lo, float* __restrict__ dA_acc, float* __restrict__ dtr_acc) {
   extern __shared__ __align__(128) float smem[];
-  float* A_s = smem;
-  float* dA_s = A_s + AG_WORDS;
-  float* dtr_s = dA_s + AG_WORDS;
-  float* tiles = dtr_s + 96;                               // [JW][2][96][33]: joint gradients | packed dq
-  uint64_t* bar = reinterpret_cast<uint64_t*>(tiles + JW * 2 * TTILE_WORDS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x, col0 = g * 32, gb0 = b0 + col0;
-  if (threadIdx.x == 0) fetch_group_transforms(A_s, A_blk, g, bar);
-  for (int r = threadIdx.x; r < AG_WORDS; r += JT) dA_s[r] = 0.f;
-  if (threadIdx.x < 96) dtr_s[threadIdx.x] = 0.f;
-  __syncthreads();
-  float* g_s = tiles + warp * 2 * TTILE_WORDS;
-  uint32_t* q_s = reinterpret_cast<uint32_t*>(g_s + TTILE_WORDS);
-  const int nrows = min(32, nb - col0);
+  float* tile = smem + warp * 32 * JROW;
+  const float* my_row = tile + lane * JROW;
+  const long long total = (long long)ngroups * m.ntv;
+  const int gw = blockIdx.x * JW + warp, nw = gridDim.x * JW;
+  const int item0 = (int)(total * gw / nw), item1 = (int)(total * (gw + 1) / nw);
   const size_t ncol_all = (size_t)m.njout * 3;
-  float sx = 0.f, sy = 0.f, sz = 0.f;
-  bool waited = false;
-  for (int tv = warp; tv < m.ntv; tv += JW) {
+  for (int item = item0; item < item1; ++item) {
+    const int g = item / m.ntv, tv = item - g * m.ntv;
     float q[96];
-    const float* chunk = vpB + ((size_t)(m.ntiles + tv) * G + g) * CHUNK_WORDS + lane;
-#pragma unroll
-    for (int i = 0; i < 96; ++i) q[i] = ld_stream(chunk + i * 32);
+    load_q96(q, vpB + (size_t)((m.ntiles + tv) * 24) * S + (size_t)g * 32 + lane, S);
+    const float4* A_g = A_blk + (size_t)g * (AG_WORDS / 4);
+    float* dA_g = dA_acc + (size_t)g * AG_WORDS;
+    const int nrows = max(0, min(32, nb - g * 32));
     const int ncols = m.vt_nj[tv] * 3;
-    // stage the gradients of this tile's joints (3 nj floats of each body row), flattened
+    // stage the gradients of this tile's joints (3 nj floats of each body row)
     {
-      const float* src0 = dJ + (size_t)gb0 * ncol_all + (size_t)(NJ + m.vt_j0[tv]) * 3;
+      const float* src0 = dJ + (size_t)(b0 + g * 32) * ncol_all + (size_t)(NJ + m.vt_j0[tv]) * 3;
       for (int idx = lane; idx < 32 * ncols; idx += 32) {
         const int r = idx / ncols, c = idx - r * ncols;
-        g_s[c * TPITCH + r] = (r < nrows) ? ld_stream(src0 + (size_t)r * ncol_all + c) : 0.f;
+        tile[r * JROW + c] = (r < nrows) ? ld_stream(src0 + (size_t)r * ncol_all + c) : 0.f;
       }
     }
-    if (!waited) { mbar_wait(bar, 0); waited = true; }
     __syncwarp();
     const uint32_t* meta = m.qmeta + tv * 32;
     const float* coef = m.qcoef + tv * 32;
-    float a[9], d[AELEMS];
+    float a[9];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    const size_t chunk0 = (size_t)((m.ntiles + tv) * 12);
+    __nv_bfloat16* hi_p = dvp_hi + (chunk0 * S + (size_t)g * 32 + lane) * 8;
+    __nv_bfloat16* lo_p = dvp_lo ? dvp_lo + (chunk0 * S + (size_t)g * 32 + lane) * 8 : nullptr;
 #pragma unroll
-    for (int e = 0; e < AELEMS; ++e) d[e] = 0.f;
-    int jcur = 0;
+    for (int blk = 0; blk < 4; ++blk) {                    // 8 q-groups = 24 rows = 3 chunks of dvp
+      float dq[24];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const uint32_t mt = __ldg(meta + i);
-      uint32_t* qo = q_s + (i * 3) * TPITCH + lane;
-      if (!(mt & (1u << 14))) {                            // dummy slot: its dvp columns must be 0
-        qo[0] = 0u; qo[TPITCH] = 0u; qo[2 * TPITCH] = 0u;
-        continue;
+      for (int ii = 0; ii < 8; ++ii) {
+        const int i = blk * 8 + ii;
+        const uint32_t mt = __ldg(meta + i);
+        if (!(mt & (1u << 14))) {                          // dummy slot: its dvp rows must be 0
+          dq[ii * 3] = dq[ii * 3 + 1] = dq[ii * 3 + 2] = 0.f;
+          continue;
+        }
+        const int joint = mt & 31;
+        if ((mt & (1u << 5)) || i == 0) load_rot_g(a, A_g, joint, lane);
+        const float c = __ldg(coef + i);
+        const float* gj = my_row + ((mt >> 8) & 31) * 3;
+        const float gx = gj[0], gy = gj[1], gz = gj[2];
+        const float qx = q[i * 3], qy = q[i * 3 + 1], qz = q[i * 3 + 2];
+        dq[ii * 3] = fmaf(a[0], gx, fmaf(a[3], gy, a[6] * gz));
+        dq[ii * 3 + 1] = fmaf(a[1], gx, fmaf(a[4], gy, a[7] * gz));
+        dq[ii * 3 + 2] = fmaf(a[2], gx, fmaf(a[5], gy, a[8] * gz));
+        float* dp = dA_g + (size_t)joint * AELEMS * 32 + lane;
+        red_add(dp, gx * qx); red_add(dp + 32, gx * qy); red_add(dp + 64, gx * qz); red_add(dp + 96, gx * c);
+        red_add(dp + 128, gy * qx); red_add(dp + 160, gy * qy); red_add(dp + 192, gy * qz); red_add(dp + 224, gy * c);
+        red_add(dp + 256, gz * qx); red_add(dp + 288, gz * qy); red_add(dp + 320, gz * qz); red_add(dp + 352, gz * c);
+        if (mt & (1u << 13)) { sx += gx; sy += gy; sz += gz; }
       }
-      if ((mt & (1u << 5)) || i == 0) {
-        if (i) flush_slot(d, dA_s, jcur, lane);
-        jcur = mt & 31;
-        load_rot(a, A_s, jcur, lane);
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        const float ch[8] = {dq[cc * 8], dq[cc * 8 + 1], dq[cc * 8 + 2], dq[cc * 8 + 3],
+                             dq[cc * 8 + 4], dq[cc * 8 + 5], dq[cc * 8 + 6], dq[cc * 8 + 7]};
+        const size_t off = (size_t)(blk * 3 + cc) * S * 8;
+        store_dvp_chunk(ch, hi_p + off, lo_p ? lo_p + off : nullptr);
       }
-      const float c = __ldg(coef + i);
-      const float* gj = g_s + ((mt >> 8) & 31) * (3 * TPITCH) + lane;
-      const float gx = gj[0], gy = gj[TPITCH], gz = gj[2 * TPITCH];
-      const float qx = q[i * 3], qy = q[i * 3 + 1], qz = q[i * 3 + 2];
-      qo[0] = pack_hi_lo(fmaf(a[0], gx, fmaf(a[3], gy, a[6] * gz)));
-      qo[TPITCH] = pack_hi_lo(fmaf(a[1], gx, fmaf(a[4], gy, a[7] * gz)));
-      qo[2 * TPITCH] = pack_hi_lo(fmaf(a[2], gx, fmaf(a[5], gy, a[8] * gz)));
-      d[0] = fmaf(gx, qx, d[0]); d[1] = fmaf(gx, qy, d[1]); d[2] = fmaf(gx, qz, d[2]); d[3] = fmaf(gx, c, d[3]);
-      d[4] = fmaf(gy, qx, d[4]); d[5] = fmaf(gy, qy, d[5]); d[6] = fmaf(gy, qz, d[6]); d[7] = fmaf(gy, c, d[7]);
-      d[8] = fmaf(gz, qx, d[8]); d[9] = fmaf(gz, qy, d[9]); d[10] = fmaf(gz, qz, d[10]); d[11] = fmaf(gz, c, d[11]);
-      if (mt & (1u << 13)) { sx += gx; sy += gy; sz += gz; }
     }
-    flush_slot(d, dA_s, jcur, lane);
-    __syncwarp();
-    flush_dvp_tile(q_s, dvp_hi, dvp_lo, (size_t)col0, m.n_pad, (size_t)m.n_virt0 + (size_t)tv * 96, lane);
+    float* dtr_g = dtr_acc + (size_t)g * 96;
+    red_add(dtr_g + lane, sx);
+    red_add(dtr_g + 32 + lane, sy);
+    red_add(dtr_g + 64 + lane, sz);
     __syncwarp();
   }
-  atomicAdd(&dtr_s[lane], sx);
-  atomicAdd(&dtr_s[32 + lane], sy);
-  atomicAdd(&dtr_s[64 + lane], sz);
-  __syncthreads();
-  accumulate_rows(dA_acc + (size_t)g * AG_WORDS, dA_s, NJ * AELEMS, warp, JW, lane);
-  if (warp < 3) atomicAdd(dtr_acc + (size_t)g * 96 + warp * 32 + lane, dtr_s[warp * 32 + lane]);
 }
 
 // total joint gradient when a 2D reprojection gradient is present:
@@ -193,26 +194,35 @@ joint_grad_total_kernel(const float* __restrict__ joints, const float* __restric
   if (gcam != nullptr && threadIdx.x < 3) gcam[b * 3 + threadIdx.x] = sh[threadIdx.x][0] + sh[threadIdx.x][1] + sh[threadIdx.x][2] + sh[threadIdx.x][3];
 }
 
+static int joints_grid(int ngroups, int ntv) {
+  const long long total = (long long)ngroups * ntv;
+  return (int)std::max<long long>(1, std::min<long long>(148 * 2, (total + JW - 1) / JW));
+}
+
 int launch_joints_fwd(const DevModel& m, const float* vpB, int S, const float* A_blk, int b0, int nb,
                       const float* transl, float* joints, cudaStream_t st) {
   if (nb <= 0 || m.ntv == 0) return 0;
-  B200_CUDA_TRY(cudaFuncSetAttribute(joints_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JFWD_SMEM));
+  const int groups = (nb + 31) / 32;
+  B200_CUDA_TRY(cudaFuncSetAttribute(joints_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)J_SMEM));
   LaunchTimer _timer("joints_fwd", st);
-  joints_fwd_kernel<<<(nb + 31) / 32, JT, JFWD_SMEM, st>>>(m, vpB, S / 32, A_blk, b0, nb,
-                                                                                        transl, joints);
+  joints_fwd_kernel<<<joints_grid(groups, m.ntv), JT, J_SMEM, st>>>(m, reinterpret_cast<const float4*>(vpB), S,
+                                                                   reinterpret_cast<const float4*>(A_blk), b0, nb,
+                                                                   groups, transl, joints);
   B200_LAUNCH_CHECK("joints_fwd");
   return 0;
 }
 
-// Sw: active slab width (multiple of 32); absent bodies get zero dvp columns / partials.
+// Sw: active slab width (multiple of 32); absent bodies get zero dvp rows.
 int launch_joints_bwd(const DevModel& m, const float* vpB, int S, int Sw, const float* A_blk, int b0, int nb,
-                      const float* dJ, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_part, float* dtr_part,
+                      const float* dJ, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_acc, float* dtr_acc,
                       cudaStream_t st) {
   if (m.ntv == 0) return 0;
-  B200_CUDA_TRY(cudaFuncSetAttribute(joints_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JBWD_SMEM));
+  const int groups = Sw / 32;
+  B200_CUDA_TRY(cudaFuncSetAttribute(joints_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)J_SMEM));
   LaunchTimer _timer("joints_bwd", st);
-  joints_bwd_kernel<<<Sw / 32, JT, JBWD_SMEM, st>>>(m, vpB, S / 32, A_blk, b0, nb, dJ,
-                                                                                 dvp_hi, dvp_lo, dA_part, dtr_part);
+  joints_bwd_kernel<<<joints_grid(groups, m.ntv), JT, J_SMEM, st>>>(m, reinterpret_cast<const float4*>(vpB), S,
+                                                                   reinterpret_cast<const float4*>(A_blk), b0, nb,
+                                                                   groups, dJ, dvp_hi, dvp_lo, dA_acc, dtr_acc);
   B200_LAUNCH_CHECK("joints_bwd");
   return 0;
 }

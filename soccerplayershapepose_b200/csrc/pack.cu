@@ -237,32 +237,14 @@ int pack_model(const b200smpl_model_desc* d, HostArrays& h, DevModel& dm, std::s
     }
   }
 
-  // ---- skinning plan ----
+  // ---- skinning plan: vertices in their original order; four joint "slots" persist along the whole
+  // vertex sequence (a warp walks a contiguous run of tiles and forces a reload of all four slots at
+  // its first vertex), so a slot is (re)loaded only where a vertex needs a joint that is not resident
   h.vmeta.assign((size_t)ntiles * TILE_V, 0u);
   h.vwts.assign((size_t)ntiles * TILE_V * 4, 0.f);
-  int slot_joint[4] = {0, 0, 0, 0};
-  for (int t = 0; t < ntiles; ++t) {
-    // processing order inside the tile: sort by joint set so that consecutive vertices share slots
-    std::vector<int> order;
-    for (int ol = 0; ol < TILE_V; ++ol) order.push_back(ol);
-    auto key = [&](int ol) {
-      const int v = t * TILE_V + ol;
-      std::array<int, 4> k{99, 99, 99, 99};
-      if (v < V) {
-        std::vector<std::pair<float, int>> byw;
-        for (int i = 0; i < infl[v].n; ++i) byw.push_back({-infl[v].w[i], infl[v].j[i]});
-        std::sort(byw.begin(), byw.end());
-        std::array<int, 4> js{99, 99, 99, 99};
-        for (size_t i = 0; i < byw.size(); ++i) js[i] = byw[i].second;
-        std::sort(js.begin(), js.end());
-        k = js;
-      }
-      return k;
-    };
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
-    for (int i = 0; i < TILE_V; ++i) {
-      const int ol = order[i];
-      const int v = t * TILE_V + ol;
+  {
+    int slot_joint[4] = {0, 0, 0, 0};
+    for (int v = 0; v < ntiles * TILE_V; ++v) {
       uint32_t meta = 0;
       float w4[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t reload = 0;
@@ -277,20 +259,28 @@ int pack_model(const b200smpl_model_desc* d, HostArrays& h, DevModel& dm, std::s
             }
         for (int a = 0; a < I.n; ++a) {
           if (placed[a]) continue;
-          for (int s = 0; s < 4; ++s)
-            if (!slot_used[s]) {
-              slot_used[s] = true; placed[a] = true;
-              slot_joint[s] = I.j[a]; w4[s] = I.w[a]; reload |= 1u << s;
-              break;
+          // evict the resident joint whose next use is farthest away
+          int pick = -1, pick_dist = -1;
+          for (int s = 0; s < 4; ++s) {
+            if (slot_used[s]) continue;
+            int dist = 1 << 30;
+            for (int u = v + 1; u < V && u < v + 256; ++u) {
+              bool uses = false;
+              for (int b = 0; b < infl[u].n; ++b) uses |= (infl[u].j[b] == slot_joint[s]);
+              if (uses) { dist = u - v; break; }
             }
+            if (dist > pick_dist) { pick_dist = dist; pick = s; }
+          }
+          slot_used[pick] = true; placed[a] = true;
+          slot_joint[pick] = I.j[a]; w4[pick] = I.w[a]; reload |= 1u << pick;
         }
         meta |= VMETA_VALID;
       }
       for (int s = 0; s < 4; ++s) meta |= (uint32_t)slot_joint[s] << (5 * s);
       meta |= reload << 20;
-      meta |= (uint32_t)ol << 24;
-      h.vmeta[(size_t)t * TILE_V + i] = meta;
-      for (int s = 0; s < 4; ++s) h.vwts[((size_t)t * TILE_V + i) * 4 + s] = w4[s];
+      meta |= (uint32_t)(v % TILE_V) << 24;
+      h.vmeta[v] = meta;
+      for (int s = 0; s < 4; ++s) h.vwts[(size_t)v * 4 + s] = w4[s];
     }
   }
 

@@ -236,10 +236,13 @@ pose_fwd_kernel(DevModel m, const float* __restrict__ betas, const float* __rest
     __syncwarp();
   }
   __syncthreads();
-  // group-blocked output A_blk[group][288][32] (one contiguous 36 KB block per 32 bodies)
+  // group-blocked output A_blk[group][joint][row][lane][4] (one contiguous 36 KB block per 32 bodies;
+  // a float4 = one row of [R | t] of one body)
   (void)S;
-  for (int r = warp; r < NJ * AELEMS; r += POSE_WARPS)
-    A_T[((size_t)blockIdx.x * NJ * AELEMS + r) * 32 + lane] = sOut[r * OUT_PITCH + lane];
+  for (int idx = threadIdx.x; idx < NJ * AELEMS * 32; idx += POSE_THREADS) {
+    const int c = idx & 3, bl = (idx >> 2) & 31, jr = idx >> 7;          // jr = joint * 3 + row
+    A_T[(size_t)blockIdx.x * NJ * AELEMS * 32 + idx] = sOut[(jr * 4 + c) * OUT_PITCH + bl];
+  }
   // the 24 posed chain joints (+ transl) go straight into joints[:, 0:24] as 288 B row segments
   if (joints != nullptr) {
     const size_t ncol_all = (size_t)m.njout * 3;

@@ -1,14 +1,22 @@
 // Helpers shared by the skinning kernels (lbs.cu: real vertex tiles; joints.cu: virtual joint tiles).
+//
+// Slab-local layouts (S = slab pitch in bodies, a multiple of 128; lane = body everywhere):
+//   vpB   [n_pad/4][S][4] fp32   blend output: element (row n, body s) at ((n >> 2) * S + s) * 4 + (n & 3);
+//                                a warp (32 consecutive bodies) reads / writes 512 contiguous bytes per float4
+//   dvp   [n_pad/8][S][8] bf16   gradient-GEMM operand (hi and lo arrays): element (body s, row n) at
+//                                ((n >> 3) * S + s) * 8 + (n & 7) -- 16-byte chunks = rows of the UMMA
+//                                no-swizzle K-major core matrices, so the GEMM pulls 2 KB per (chunk, 128 bodies)
+//   A_blk [S/32][24][3][32][4]   skinning transforms: one float4 = row r of [R | t] of one body
+//   dA    [S/32][24*12][32]      gradient of A, accumulated with fp32 REDs
 #pragma once
 
 #include "common.cuh"
 
 namespace b200smpl {
 
-constexpr int CHUNK_WORDS = TILE_V * 3 * 32;     // 3072 floats = 12 KB: one (tile, group) block of the blend output
 constexpr int AG_WORDS = NJ * AELEMS * 32;       // 9216 floats = 36 KB: one group's skinning transforms
-constexpr int TPITCH = 33;                       // transposition tile [96 columns][33]: (33 c + r) % 32 = (c + r) % 32,
-constexpr int TTILE_WORDS = TILE_V * 3 * TPITCH; // conflict-free both for lane = body (fixed c) and lane = column (fixed r)
+constexpr int TROW = 100;                        // staging tile [32 bodies][100]: 96 floats + 4 pad; rows stay 16-byte
+constexpr int TTILE_WORDS = 32 * TROW;           // aligned and (25 * lane + k) % 8 spreads a quarter-warp over all banks
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -38,7 +46,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-// one thread: initialise the barrier and pull the group's A[24][12][32] (36 KB, contiguous) into smem
+// one thread: initialise the barrier and pull the group's transforms (36 KB, contiguous) into smem
 __device__ __forceinline__ void fetch_group_transforms(float* A_s, const float* A_blk, int g, uint64_t* bar) {
   mbar_init(bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -52,64 +60,95 @@ __device__ __forceinline__ float ld_stream(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ float2 ld_stream2(const float* p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void st_stream(float* p, float v) {
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
-__device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) {
-  asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_stream2(float* p, float2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream_u4(void* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+// fire-and-forget fp32 add into global memory (resolved in L2)
+__device__ __forceinline__ void red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-__device__ __forceinline__ void load_slot(float (&a)[AELEMS], const float* A_s, int joint, int lane) {
+// ---- transforms: [joint][row r][lane] float4 = row r of [R | t] of that lane's body --------------------
+// (the same indexing serves the shared-memory copy of one group and the global A_blk + group offset)
+__device__ __forceinline__ void load_slot(float (&a)[AELEMS], const float* A, int joint, int lane) {
+  const float4* p = reinterpret_cast<const float4*>(A) + joint * 96 + lane;
 #pragma unroll
-  for (int e = 0; e < AELEMS; ++e) a[e] = A_s[(joint * AELEMS + e) * 32 + lane];
+  for (int r = 0; r < 3; ++r) {
+    const float4 v = p[r * 32];
+    a[r * 4 + 0] = v.x; a[r * 4 + 1] = v.y; a[r * 4 + 2] = v.z; a[r * 4 + 3] = v.w;
+  }
 }
-__device__ __forceinline__ void load_rot(float (&a)[9], const float* A_s, int joint, int lane) {
+__device__ __forceinline__ void load_rot(float (&a)[9], const float* A, int joint, int lane) {
+  const float4* p = reinterpret_cast<const float4*>(A) + joint * 96 + lane;
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) a[r * 3 + c] = A_s[(joint * AELEMS + r * 4 + c) * 32 + lane];
+  for (int r = 0; r < 3; ++r) {
+    const float4 v = p[r * 32];
+    a[r * 3 + 0] = v.x; a[r * 3 + 1] = v.y; a[r * 3 + 2] = v.z;
+  }
 }
-__device__ __forceinline__ void flush_slot(float (&d)[AELEMS], float* dA_s, int joint, int lane) {
+// same, through the read-only path of global memory (L1-allocating: the warps of a CTA share a group)
+__device__ __forceinline__ void load_slot_g(float (&a)[AELEMS], const float4* A_g, int joint, int lane) {
+  const float4* p = A_g + joint * 96 + lane;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float4 v = __ldg(p + r * 32);
+    a[r * 4 + 0] = v.x; a[r * 4 + 1] = v.y; a[r * 4 + 2] = v.z; a[r * 4 + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void load_rot_g(float (&a)[9], const float4* A_g, int joint, int lane) {
+  const float4* p = A_g + joint * 96 + lane;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float4 v = __ldg(p + r * 32);
+    a[r * 3 + 0] = v.x; a[r * 3 + 1] = v.y; a[r * 3 + 2] = v.z;
+  }
+}
+// add a slot's gradient accumulators into the group's dA rows [joint * 12 + e][32] and clear them
+__device__ __forceinline__ void flush_slot_g(float (&d)[AELEMS], float* dA_g, int joint, int lane) {
+  float* p = dA_g + (size_t)joint * AELEMS * 32 + lane;
 #pragma unroll
   for (int e = 0; e < AELEMS; ++e) {
-    atomicAdd(&dA_s[(joint * AELEMS + e) * 32 + lane], d[e]);
+    red_add(p + e * 32, d[e]);
     d[e] = 0.f;
   }
 }
 
-// add a CTA's shared accumulators [rows][32] into the slab-wide buffer (fp32 RED, rows that stayed 0 skipped)
-__device__ __forceinline__ void accumulate_rows(float* __restrict__ dst, const float* src_s, int rows, int warp,
-                                                int nwarps, int lane) {
-  for (int r = warp; r < rows; r += nwarps) {
-    const float v = src_s[r * 32 + lane];
-    if (__any_sync(0xffffffffu, v != 0.f)) atomicAdd(dst + r * 32 + lane, v);
-  }
+// x -> bf16 hi, bf16 lo   (x ~ hi + lo to 16 mantissa bits); two values per 32-bit word, low half first
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+  const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+  const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+  hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
 }
-
-// x -> bf16 hi | bf16 lo << 16   (x ~ hi + lo to 16 mantissa bits)
-__device__ __forceinline__ uint32_t pack_hi_lo(float x) {
-  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-  return (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
-}
-
-// flush a transposition tile of packed (hi | lo<<16) words into the K-major bf16 operand rows
-// dvp_{hi,lo}[row0 + r][col_base .. col_base + 96): even lanes store two columns per 32-bit word
-__device__ __forceinline__ void flush_dvp_tile(const uint32_t* tile_u, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo,
-                                               size_t row0, int n_pad, size_t col_base, int lane) {
-#pragma unroll 4
-  for (int r = 0; r < 32; ++r) {
-    const size_t o = (row0 + r) * (size_t)n_pad + col_base + lane;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const uint32_t u0 = tile_u[(lane + 32 * k) * TPITCH + r];
-      const uint32_t u1 = __shfl_down_sync(0xffffffffu, u0, 1);
-      if (!(lane & 1)) {
-        st_stream_u32(dvp_hi + o + 32 * k, (u0 & 0xFFFFu) | (u1 << 16));
-        if (dvp_lo != nullptr) st_stream_u32(dvp_lo + o + 32 * k, (u0 >> 16) | (u1 & 0xFFFF0000u));
-      }
-    }
-  }
+// eight consecutive gradient rows of one body -> one 16-byte chunk of dvp_hi (and dvp_lo)
+__device__ __forceinline__ void store_dvp_chunk(const float (&q)[8], __nv_bfloat16* hi_p, __nv_bfloat16* lo_p) {
+  uint4 h, l;
+  split2(q[0], q[1], h.x, l.x);
+  split2(q[2], q[3], h.y, l.y);
+  split2(q[4], q[5], h.z, l.z);
+  split2(q[6], q[7], h.w, l.w);
+  st_stream_u4(hi_p, h);
+  if (lo_p != nullptr) st_stream_u4(lo_p, l);
 }
 
 }  // namespace b200smpl
