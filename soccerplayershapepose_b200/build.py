@@ -59,7 +59,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("B200_NVCC_EXTRA", "").split() + ["-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(BUILD, os.path.basename(o) + ".log")
         with open(log, "w") as f:

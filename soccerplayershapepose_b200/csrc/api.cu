@@ -48,7 +48,7 @@ struct Plan {
   size_t off_feat, off_featf, off_A, off_jposed, off_vpT;
   size_t off_dvp_hi, off_dvp_lo, off_dA, off_dtr, off_dJtot, off_dfeat;
   size_t total;
-  size_t saved_slab_bytes;   // per slab: A_blk [S/32][24][3][32][4] then vpB [n_pad/4][S][4]
+  size_t saved_slab_bytes;   // per slab: A_blk [S/32][24][3][32][4] then vpB [S/32][n_pad/4][32][4]
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -385,9 +385,10 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
     }
     {  // the gradient GEMM reads whole 64-row K slabs: rows between row_end and the slab boundary must be finite
       const size_t c0 = (size_t)row_end / 8, c1 = (size_t)round_up(row_end, 64) / 8;
-      if (c1 > c0) {
-        B200_CUDA_TRY(cudaMemsetAsync(dvp_hi + c0 * S * 8, 0, (c1 - c0) * S * 16, st));
-        if (dvp_lo) B200_CUDA_TRY(cudaMemsetAsync(dvp_lo + c0 * S * 8, 0, (c1 - c0) * S * 16, st));
+      if (c1 > c0) {   // dvp [S/128][n_pad/8][128][8]: the same chunk range of every 128-body tile
+        const size_t pitch = (size_t)(d.n_pad / 8) * 2048, width = (c1 - c0) * 2048;
+        B200_CUDA_TRY(cudaMemset2DAsync(dvp_hi + c0 * 1024, pitch, 0, width, (size_t)Sw / 128, st));
+        if (dvp_lo) B200_CUDA_TRY(cudaMemset2DAsync(dvp_lo + c0 * 1024, pitch, 0, width, (size_t)Sw / 128, st));
       }
     }
     if (have_v)

@@ -38,9 +38,9 @@ blend_fwd_simt_kernel(const float* __restrict__ W32, int n_pad, int nf, const fl
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {   // vpB [n/4][S][4] (skin_common.cuh)
+  for (int i = 0; i < 4; ++i) {   // vpB [S/32][n_pad/4][32][4] (skin_common.cuh)
     const size_t n = (size_t)(n0 + ty * 4 + i);
-    vpT[((n >> 2) * (size_t)S + s0 + tx) * 4 + (n & 3)] = acc[i];
+    vpT[(((size_t)(s0 >> 5) * (n_pad >> 2) + (n >> 2)) * 32 + tx) * 4 + (n & 3)] = acc[i];
   }
 }
 
@@ -70,8 +70,8 @@ blend_bwd_simt_kernel(const float* __restrict__ W32, int n_pad, int nf, const __
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int s = ty * 4 + i;
-      const size_t nn = (size_t)(n0 + tx);   // dvp [n/8][S][8] (skin_common.cuh)
-      const size_t o = ((nn >> 3) * (size_t)S + s0 + s) * 8 + (nn & 7);
+      const size_t nn = (size_t)(n0 + tx);   // dvp [S/128][n_pad/8][128][8] (skin_common.cuh)
+      const size_t o = (((size_t)(s0 >> 7) * (n_pad >> 3) + (nn >> 3)) * 128 + (s0 & 127) + s) * 8 + (nn & 7);
       float v = 0.f;
       if (n0 + tx < row_end) {
         v = __bfloat162float(dvp_hi[o]);

@@ -26,8 +26,8 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
 constexpr int MAX_SEG = 3;
 
-// backward operands: A = dvp chunks [n/8][S][8] (plain pointers, pulled with bulk copies into the
-// no-swizzle core-matrix layout), B = Wb rows through a 128-byte-swizzle tensor map
+// backward operands: A = dvp chunks [S/128][n/8][128][8] (plain pointers, one 16 KB bulk copy per stage
+// straight into the no-swizzle core-matrix layout), B = Wb rows through a 128-byte-swizzle tensor map
 struct GemmOps {
   const __nv_bfloat16* a[MAX_SEG];
   CUtensorMap b[MAX_SEG];
@@ -149,7 +149,7 @@ struct GemmSmem {
 // A stage = 8 chunks x (128 bodies x 16 B): chunk c at +2048 B  ->  LBO = 2048, SBO = 128.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-umma_gemm_kernel(const __grid_constant__ GemmOps ops, int nseg, int S, int slab_begin, int slab_end,
+umma_gemm_kernel(const __grid_constant__ GemmOps ops, int nseg, int nc8, int slab_begin, int slab_end,
                  int slabs_per_split, float* __restrict__ D, int ldd, long long split_stride) {
   using SM = GemmSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
@@ -198,9 +198,8 @@ umma_gemm_kernel(const __grid_constant__ GemmOps ops, int nseg, int S, int slab_
         unsigned char* sa = smem + stage * SM::STAGE_BYTES;
         unsigned char* sb = sa + SM::A_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
-        const __nv_bfloat16* asrc = ops.a[seg] + ((size_t)slab * 8 * S + m0) * 8;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) bulk_g2s(sa + c * 2048, asrc + (size_t)c * S * 8, 2048, &full_bar[stage]);
+        // dvp [S/128][n/8][128][8]: the 8 chunks of this K slab for the 128 bodies are 16 contiguous KB
+        bulk_g2s(sa, ops.a[seg] + (((size_t)blockIdx.x * nc8 + (size_t)slab * 8) * 128) * 8, SM::A_BYTES, &full_bar[stage]);
         tma_load_2d(sb, &ops.b[seg], &full_bar[stage], slab * BK, 0);
         if (++stage == STAGES) {
           stage = 0;
@@ -267,7 +266,7 @@ umma_gemm_kernel(const __grid_constant__ GemmOps ops, int nseg, int S, int slab_
 // 11 x 16 KB) resident in shared memory and streams only the feature tiles of its share of the bodies
 // through a 3-stage ring, accumulating in two alternating TMEM buffers so the epilogue of body tile i
 // overlaps the MMAs of tile i+1.  M = 128 bodies (A operand = streamed features), N = 128 model rows
-// (B operand = resident slice): the epilogue thread owns one body and writes float4s of vpB [n/4][S][4].
+// (B operand = resident slice): the epilogue thread owns one body and writes float4s of the group-blocked vpB.
 // grid: (row tiles, body chunks); CTA = 6 warps (TMA, MMA, 4 epilogue).
 // ---------------------------------------------------------------------------------------------
 constexpr int WS_STAGES = 3;
@@ -276,7 +275,7 @@ constexpr int WS_BN = 128;
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 blend_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_f, int nslab,
-                    int row0, int ntiles_n, int tiles_per_chunk, float4* __restrict__ vpB, int S) {
+                    int row0, int ntiles_n, int tiles_per_chunk, float4* __restrict__ vpB, int nc4) {
   constexpr int SLAB = BM * BK * 2;                 // 16 KB: 128 rows x 64 bf16 (both operands)
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -362,7 +361,7 @@ blend_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     }
   } else {
     const int q = warp & 3;
-    float4* colbase = vpB + (size_t)(m0 >> 2) * S + q * 32 + lane;     // this lane's body column, chunk m0/4
+    float4* colbase = vpB + ((size_t)q * nc4 + (m0 >> 2)) * 32 + lane;   // group q of the body tile, chunk m0/4
     uint32_t tphase[2] = {0u, 0u};
     int acc = 0;
     for (int nt = nt_begin; nt < nt_end; ++nt, acc ^= 1) {
@@ -373,10 +372,10 @@ blend_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       for (int c0 = 0; c0 < BM; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * WS_BN + c0), v);
-        float4* o = colbase + (size_t)(c0 >> 2) * S + (size_t)nt * WS_BN;
+        float4* o = colbase + ((size_t)nt * 4 * nc4 + (c0 >> 2)) * 32;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          o[(size_t)i * S] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+          o[i * 32] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
                                          __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
       }
       tc_fence_before();
@@ -458,7 +457,7 @@ int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat
   const int tpc = (ntiles_n + chunks - 1) / chunks;
   LaunchTimer _timer("blend_fwd_umma", st);
   blend_fwd_ws_kernel<<<dim3(mtiles, (ntiles_n + tpc - 1) / tpc), GEMM_THREADS, smem, st>>>(
-      map_w, map_f, nslab, row_begin, ntiles_n, tpc, reinterpret_cast<float4*>(vpT), S);
+      map_w, map_f, nslab, row_begin, ntiles_n, tpc, reinterpret_cast<float4*>(vpT), m.n_pad / 4);
   B200_LAUNCH_CHECK("blend_fwd_umma");
   return 0;
 }
@@ -474,7 +473,7 @@ int blend_bwd_umma_splits(const DevModel& m, int mode, int S, int num_sms) {
 }
 
 template <int BN>
-static int launch_bwd_bn(const GemmOps& ops, int nseg, int S, int slab_begin, int slab_end, int nsplit, int Sw,
+static int launch_bwd_bn(const GemmOps& ops, int nseg, int nc8, int slab_begin, int slab_end, int nsplit, int Sw,
                          float* dfeat_part, int nf_pad, long long split_stride, cudaStream_t st) {
   using SM = GemmSmem<BN, BWD_STAGES>;
   auto kern = umma_gemm_kernel<BN, BWD_STAGES>;
@@ -483,7 +482,7 @@ static int launch_bwd_bn(const GemmOps& ops, int nseg, int S, int slab_begin, in
   const int sps = (slabs + nsplit - 1) / nsplit;
   dim3 grid(Sw / BM, 1, nsplit);
   LaunchTimer _timer_316("blend_bwd_umma", st);
-  kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(ops, nseg, S, slab_begin, slab_end, sps, dfeat_part, nf_pad, split_stride);
+  kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(ops, nseg, nc8, slab_begin, slab_end, sps, dfeat_part, nf_pad, split_stride);
   B200_LAUNCH_CHECK("blend_bwd_umma");
   return 0;
 }
@@ -511,9 +510,9 @@ int launch_blend_bwd_umma(const DevModel& m, int mode, const __nv_bfloat16* dvp_
   const int slab_begin = row_begin / BK, slab_end = (row_end + BK - 1) / BK;
   const long long split_stride = (long long)S * nf_pad;
   switch (nf_pad) {
-    case 224: return launch_bwd_bn<224>(ops, nseg, S, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
-    case 208: return launch_bwd_bn<208>(ops, nseg, S, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
-    case 240: return launch_bwd_bn<240>(ops, nseg, S, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
+    case 224: return launch_bwd_bn<224>(ops, nseg, m.n_pad / 8, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
+    case 208: return launch_bwd_bn<208>(ops, nseg, m.n_pad / 8, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
+    case 240: return launch_bwd_bn<240>(ops, nseg, m.n_pad / 8, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
     default: return fail(B200SMPL_ERR_INVALID, "unsupported num_betas for the tensor-core backward (nf_pad=" + std::to_string(nf_pad) + ")");
   }
 }

@@ -21,16 +21,16 @@ constexpr int JT = JW * 32;
 constexpr int JROW = 97;                    // staging tile [32 bodies][97]: scalar accesses only, odd pitch
 constexpr size_t J_SMEM = (size_t)JW * 32 * JROW * 4;
 
-__device__ __forceinline__ void load_q96(float (&q)[96], const float4* __restrict__ p, size_t S) {
+__device__ __forceinline__ void load_q96(float (&q)[96], const float4* __restrict__ p) {
 #pragma unroll
   for (int i = 0; i < 24; ++i) {
-    const float4 v = ld_stream4(p + i * S);
+    const float4 v = ld_stream4(p + i * 32);
     q[i * 4] = v.x; q[i * 4 + 1] = v.y; q[i * 4 + 2] = v.z; q[i * 4 + 3] = v.w;
   }
 }
 
 __global__ void __launch_bounds__(JT, 1)
-joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int S, const float4* __restrict__ A_blk, int b0, int nb,
+joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const float4* __restrict__ A_blk, int b0, int nb,
                   int ngroups, const float* __restrict__ transl, float* __restrict__ joints) {
   extern __shared__ __align__(128) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -43,7 +43,7 @@ joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int S, const float
   for (int item = item0; item < item1; ++item) {
     const int g = item / m.ntv, tv = item - g * m.ntv;
     float q[96];
-    load_q96(q, vpB + (size_t)((m.ntiles + tv) * 24) * S + (size_t)g * 32 + lane, S);
+    load_q96(q, vpB + ((size_t)g * nc4 + (m.ntiles + tv) * 24) * 32 + lane);
     const float4* A_g = A_blk + (size_t)g * (AG_WORDS / 4);
     float tx = 0.f, ty = 0.f, tz = 0.f;
     if (transl != nullptr && g * 32 + lane < nb) {
@@ -86,7 +86,7 @@ joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int S, const float
 // backward over virtual tiles.  dJ: total joint gradient (B, NJout, 3).
 //   dq -> virtual rows of dvp ; dA, dtransl -> fp32 REDs into the slab accumulators
 __global__ void __launch_bounds__(JT, 1)
-joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int S, const float4* __restrict__ A_blk, int b0, int nb,
+joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const float4* __restrict__ A_blk, int b0, int nb,
                   int ngroups, const float* __restrict__ dJ, __nv_bfloat16* __restrict__ dvp_hi,
                   __nv_bfloat16* __restrict__ dvp_lo, float* __restrict__ dA_acc, float* __restrict__ dtr_acc) {
   extern __shared__ __align__(128) float smem[];
@@ -100,7 +100,7 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int S, const float
   for (int item = item0; item < item1; ++item) {
     const int g = item / m.ntv, tv = item - g * m.ntv;
     float q[96];
-    load_q96(q, vpB + (size_t)((m.ntiles + tv) * 24) * S + (size_t)g * 32 + lane, S);
+    load_q96(q, vpB + ((size_t)g * nc4 + (m.ntiles + tv) * 24) * 32 + lane);
     const float4* A_g = A_blk + (size_t)g * (AG_WORDS / 4);
     float* dA_g = dA_acc + (size_t)g * AG_WORDS;
     const int nrows = max(0, min(32, nb - g * 32));
@@ -118,9 +118,9 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int S, const float
     const float* coef = m.qcoef + tv * 32;
     float a[9];
     float sx = 0.f, sy = 0.f, sz = 0.f;
-    const size_t chunk0 = (size_t)((m.ntiles + tv) * 12);
-    __nv_bfloat16* hi_p = dvp_hi + (chunk0 * S + (size_t)g * 32 + lane) * 8;
-    __nv_bfloat16* lo_p = dvp_lo ? dvp_lo + (chunk0 * S + (size_t)g * 32 + lane) * 8 : nullptr;
+    const size_t chunk0 = (size_t)(g >> 2) * (nc4 >> 1) + (size_t)((m.ntiles + tv) * 12);
+    __nv_bfloat16* hi_p = dvp_hi + (chunk0 * 128 + (g & 3) * 32 + lane) * 8;
+    __nv_bfloat16* lo_p = dvp_lo ? dvp_lo + (chunk0 * 128 + (g & 3) * 32 + lane) * 8 : nullptr;
 #pragma unroll
     for (int blk = 0; blk < 4; ++blk) {                    // 8 q-groups = 24 rows = 3 chunks of dvp
       float dq[24];
@@ -151,7 +151,7 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int S, const float
       for (int cc = 0; cc < 3; ++cc) {
         const float ch[8] = {dq[cc * 8], dq[cc * 8 + 1], dq[cc * 8 + 2], dq[cc * 8 + 3],
                              dq[cc * 8 + 4], dq[cc * 8 + 5], dq[cc * 8 + 6], dq[cc * 8 + 7]};
-        const size_t off = (size_t)(blk * 3 + cc) * S * 8;
+        const size_t off = (size_t)(blk * 3 + cc) * 128 * 8;
         store_dvp_chunk(ch, hi_p + off, lo_p ? lo_p + off : nullptr);
       }
     }
@@ -205,7 +205,7 @@ int launch_joints_fwd(const DevModel& m, const float* vpB, int S, const float* A
   const int groups = (nb + 31) / 32;
   B200_CUDA_TRY(cudaFuncSetAttribute(joints_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)J_SMEM));
   LaunchTimer _timer("joints_fwd", st);
-  joints_fwd_kernel<<<joints_grid(groups, m.ntv), JT, J_SMEM, st>>>(m, reinterpret_cast<const float4*>(vpB), S,
+  joints_fwd_kernel<<<joints_grid(groups, m.ntv), JT, J_SMEM, st>>>(m, reinterpret_cast<const float4*>(vpB), m.n_pad / 4,
                                                                    reinterpret_cast<const float4*>(A_blk), b0, nb,
                                                                    groups, transl, joints);
   B200_LAUNCH_CHECK("joints_fwd");
@@ -220,7 +220,7 @@ int launch_joints_bwd(const DevModel& m, const float* vpB, int S, int Sw, const 
   const int groups = Sw / 32;
   B200_CUDA_TRY(cudaFuncSetAttribute(joints_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)J_SMEM));
   LaunchTimer _timer("joints_bwd", st);
-  joints_bwd_kernel<<<joints_grid(groups, m.ntv), JT, J_SMEM, st>>>(m, reinterpret_cast<const float4*>(vpB), S,
+  joints_bwd_kernel<<<joints_grid(groups, m.ntv), JT, J_SMEM, st>>>(m, reinterpret_cast<const float4*>(vpB), m.n_pad / 4,
                                                                    reinterpret_cast<const float4*>(A_blk), b0, nb,
                                                                    groups, dJ, dvp_hi, dvp_lo, dA_acc, dtr_acc);
   B200_LAUNCH_CHECK("joints_bwd");

@@ -1,87 +1,247 @@
 // Linear blend skinning of the 6890 vertices, forward and backward (SURVEY.md section 8 row a9;
 // smplx.lbs.lbs tail: T = W.A ; v = T.[v_posed;1]).  HBM-roofline kernels.
 //
-// Mapping: lane = body.  The work is the flat list of (body group, 32-vertex tile) items; every WARP
-// owns one contiguous run of that list (no CTA-level coupling, no barriers), so the load is balanced to
-// one tile per warp whatever the batch is.  Everything per-vertex (4 joint ids, 4 weights) is
+// Mapping: lane = body.  The work is the flat list of (body group, HV-vertex item) units; every CTA owns a
+// contiguous range of it, walks it one body group at a time and gives each warp a contiguous run of the
+// group's items, so the load is balanced to one item per warp whatever the batch is.  Everything per-vertex (4 joint ids, 4 weights) is
 // warp-uniform; everything per-body lives in registers: the 4 cached joint transforms ("slots") are
 // (re)loaded -- three coalesced 512-byte float4 loads from A_blk, L1/L2 resident -- only where the packed
 // plan says a slot's joint changes (8 times per 32 vertices on the SMPL mesh order).
 //
-// Data movement: v_posed comes from the blend GEMM as [n/4][S][4] (a warp reads 512 contiguous bytes per
-// float4) straight into registers, 8 vertices ahead of the arithmetic.  The tensors whose layout the
+// Data movement: v_posed comes from the blend GEMM group-blocked, [S/32][n/4][32][4]: a warp's run is one
+// contiguous stream (512 bytes per float4 and chunk).  The tensors whose layout the
 // caller fixes -- (B, 6890, 3) vertices / vertex gradients -- are transposed through a per-warp
 // shared-memory tile [32 bodies][100]: the lane = body side uses 128-bit accesses on its own row, the
 // global side moves each 384-byte row segment as 8-byte accesses (two rows per three warp
 // instructions), every byte read or written exactly once with streaming accesses.  The backward writes
-// dv_posed as bf16 hi/lo 16-byte chunks [n/8][S][8] (512 contiguous bytes per warp store, the operand
+// dv_posed as bf16 hi/lo 16-byte chunks [S/128][n/8][128][8] (512 contiguous bytes per warp store, the operand
 // layout of the gradient GEMM) and adds dA / dtransl into the slab accumulators with fp32 REDs.
 #include "skin_common.cuh"
 
 namespace b200smpl {
 
-struct WarpRun {
-  int item, end, g, t;
+// Pipeline: every warp keeps TWO staging buffers and fills the one of item k+1 with cp.async (v_posed: 16
+// bytes per lane and chunk into the lane's own row; vertex gradients: 8-byte pieces of the (B, V, 3) rows,
+// zero-filled outside the batch / mesh) while it works on item k, so a whole item per warp (3-6 KB) is in
+// flight at any time without holding registers.
+template <int HV>
+struct ItemShape {
+  static constexpr int ROWS = HV * 3;             // blend rows (floats per body) of one item
+  static constexpr int HROW = ROWS + 4;           // staging row pitch: 16-byte aligned, HROW / 4 odd -> a quarter-warp
+  static constexpr int TILE_WORDS = 32 * HROW;    // of 128-bit row accesses (lane = row) covers all banks
+  static constexpr int NCH4 = ROWS / 4;           // float4 chunks of v_posed per body
+  static constexpr int NCH8 = ROWS / 8;           // 8-row chunks of dvp per body
+  static constexpr int PAIRS = ROWS / 2;          // 8-byte pieces per body row
+  static constexpr int STASH_WORDS = HV * 5;      // plan words of one item: HV metas + HV float4 weights
+  static_assert((HROW / 4) % 2 == 1 && ROWS % 8 == 0, "item shape");
 };
-// contiguous run of (group, tile) items of warp `gw` out of `nw`
-__device__ __forceinline__ WarpRun make_run(int ngroups, int ntiles, int gw, int nw) {
-  const long long total = (long long)ngroups * ntiles;
-  WarpRun r;
-  r.item = (int)(total * gw / nw);
-  r.end = (int)(total * (gw + 1) / nw);
-  r.g = r.item / ntiles;
-  r.t = r.item - r.g * ntiles;
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8_zfill(void* dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global.L2::256B [%0], [%1], 8, %2;" ::"r"(smem_addr(dst_smem)), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// contiguous range of the flat (group, item) list owned by this CTA; it is walked one group at a time
+struct CtaRange {
+  int begin, end;
+};
+__device__ __forceinline__ CtaRange make_cta_range(int ngroups, int nitems) {
+  const long long total = (long long)ngroups * nitems;
+  CtaRange r;
+  r.begin = (int)(total * blockIdx.x / gridDim.x);
+  r.end = (int)(total * (blockIdx.x + 1) / gridDim.x);
   return r;
 }
 
-// the 24 v_posed rows (8 vertices) of one body: 6 float4, chunk stride S
-__device__ __forceinline__ void fetch_vp8(float (&P)[24], const float4* __restrict__ p, size_t S) {
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    const float4 v = ld_stream4(p + i * S);
-    P[i * 4 + 0] = v.x; P[i * 4 + 1] = v.y; P[i * 4 + 2] = v.z; P[i * 4 + 3] = v.w;
+// plan words of one item, held by lanes 0..HV-1 between the global load and the stash store
+struct PlanRegs {
+  uint32_t m;
+  float4 w;
+};
+template <int HV>
+__device__ __forceinline__ PlanRegs plan_load(const uint32_t* __restrict__ vmeta, const float4* __restrict__ vwts,
+                                              int vbase, int lane) {
+  PlanRegs r;
+  r.m = 0u;
+  r.w = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane < HV) {
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r.m) : "l"(vmeta + vbase + lane));
+    r.w = ld_stream4(vwts + vbase + lane);
+  }
+  return r;
+}
+template <int HV>
+__device__ __forceinline__ void plan_store(uint32_t* stash, const PlanRegs& r, int lane) {
+  if (lane < HV) {
+    stash[lane] = r.m;
+    reinterpret_cast<float4*>(stash + HV)[lane] = r.w;
   }
 }
-__device__ __forceinline__ void fetch_vp4(float (&P)[12], const float4* __restrict__ p, size_t S) {
+
+// v_posed of one item: NCH4 float4 per body, straight into the lane's own row (no cross-lane traffic)
+template <int HV>
+__device__ __forceinline__ void issue_vp_rows(float* my_row, const float4* __restrict__ vp_item_lane) {
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const float4 v = ld_stream4(p + i * S);
-    P[i * 4 + 0] = v.x; P[i * 4 + 1] = v.y; P[i * 4 + 2] = v.z; P[i * 4 + 3] = v.w;
+  for (int c = 0; c < ItemShape<HV>::NCH4; ++c) cp_async16(my_row + c * 4, vp_item_lane + c * 32);
+}
+// ... or into a dense [chunk][lane] float4 array
+template <int HV>
+__device__ __forceinline__ void issue_vp_dense(float4* vbuf, const float4* __restrict__ vp_item_lane, int lane) {
+#pragma unroll
+  for (int c = 0; c < ItemShape<HV>::NCH4; ++c) cp_async16(vbuf + c * 32 + lane, vp_item_lane + c * 32);
+}
+// 32 row segments of a (B, V, 3) tensor <-> staging tile in 8-byte pieces.  The 32 * PAIRS pieces are taken
+// 32 per warp instruction: piece = k * 32 + lane -> row = piece / PAIRS, column pair = piece % PAIRS.  Since
+// 96 = RPP * PAIRS the (row offset, column) of a lane repeats every 3 instructions, RPP rows further down, so
+// a lane keeps 3 global pointers and adds a constant stride.
+template <int HV>
+__device__ __forceinline__ void issue_rows_full(float* tile, const float* __restrict__ src0, size_t row_stride, int lane) {
+  using SH = ItemShape<HV>;
+  constexpr int RPP = 96 / SH::PAIRS, J = 32 / RPP;
+  const float* gp[3];
+  float* sp[3];
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk) {
+    const int piece = kk * 32 + lane, rr = piece / SH::PAIRS, c = (piece - rr * SH::PAIRS) * 2;
+    gp[kk] = src0 + (size_t)rr * row_stride + c;
+    sp[kk] = tile + rr * SH::HROW + c;
   }
+  const size_t step = (size_t)RPP * row_stride;
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+      cp_async8_zfill(sp[kk] + j * RPP * SH::HROW, gp[kk], 8);
+      gp[kk] += step;
+    }
+}
+// general version: zero-filled outside [nrows) x [ncols)
+template <int HV>
+__device__ __forceinline__ void issue_rows(float* tile, const float* __restrict__ src0, size_t row_stride, int nrows,
+                                           int ncols, int lane) {
+  using SH = ItemShape<HV>;
+  if (nrows == 32 && ncols == SH::ROWS) {
+    issue_rows_full<HV>(tile, src0, row_stride, lane);
+    return;
+  }
+#pragma unroll 1
+  for (int k = 0; k < SH::PAIRS; ++k) {
+    const int piece = k * 32 + lane;
+    const int r = piece / SH::PAIRS;
+    const int c = (piece - r * SH::PAIRS) * 2;
+    const bool ok = r < nrows && c < ncols;
+    const int bytes = ok ? (c + 1 < ncols ? 8 : 4) : 0;
+    cp_async8_zfill(tile + r * SH::HROW + c, ok ? src0 + (size_t)r * row_stride + c : src0, bytes);
+  }
+}
+
+// rows of the staging tile -> row segments of a (B, V, 3) tensor (8-byte stores)
+template <int HV>
+__device__ __forceinline__ void tile_to_global_full(const float* tile, float* dst0, size_t row_stride, int lane) {
+  using SH = ItemShape<HV>;
+  constexpr int RPP = 96 / SH::PAIRS, J = 32 / RPP;
+  float* gp[3];
+  const float* sp[3];
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk) {
+    const int piece = kk * 32 + lane, rr = piece / SH::PAIRS, c = (piece - rr * SH::PAIRS) * 2;
+    gp[kk] = dst0 + (size_t)rr * row_stride + c;
+    sp[kk] = tile + rr * SH::HROW + c;
+  }
+  const size_t step = (size_t)RPP * row_stride;
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+      st_stream2(gp[kk], *reinterpret_cast<const float2*>(sp[kk] + j * RPP * SH::HROW));
+      gp[kk] += step;
+    }
+}
+template <int HV>
+__device__ __forceinline__ void tile_to_global(const float* tile, float* dst0, size_t row_stride, int nrows,
+                                               int ncols, int lane) {
+  using SH = ItemShape<HV>;
+  if (nrows == 32 && ncols == SH::ROWS) {
+    tile_to_global_full<HV>(tile, dst0, row_stride, lane);
+    return;
+  }
+#pragma unroll 1
+  for (int k = 0; k < SH::PAIRS; ++k) {
+    const int piece = k * 32 + lane;
+    const int r = piece / SH::PAIRS;
+    const int c = (piece - r * SH::PAIRS) * 2;
+    const float2 v = *reinterpret_cast<const float2*>(tile + r * SH::HROW + c);
+    float* dst = dst0 + (size_t)r * row_stride + c;
+    if (r < nrows) {
+      if (c + 1 < ncols) st_stream2(dst, v);
+      else if (c < ncols) st_stream(dst, v.x);
+    }
+  }
+}
+// element-wise fallbacks (odd V or a base pointer that is not 8-byte aligned)
+template <int HV>
+__device__ __forceinline__ void tile_to_global_scalar(const float* tile, float* dst0, size_t row_stride, int nrows,
+                                                      int ncols, int lane) {
+  for (int r = 0; r < nrows; ++r)
+    for (int c = lane; c < ncols; c += 32) dst0[(size_t)r * row_stride + c] = tile[r * ItemShape<HV>::HROW + c];
+}
+template <int HV>
+__device__ __forceinline__ void global_to_tile_scalar(float* tile, const float* src0, size_t row_stride, int nrows,
+                                                      int ncols, int lane) {
+  for (int r = 0; r < 32; ++r)
+    for (int c = lane; c < ItemShape<HV>::ROWS; c += 32)
+      tile[r * ItemShape<HV>::HROW + c] = (r < nrows && c < ncols) ? src0[(size_t)r * row_stride + c] : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-constexpr int FWD_WARPS = 12;
+#ifndef B200_FWD_HV
+#define B200_FWD_HV 16
+#endif
+#ifndef B200_FWD_WARPS
+#define B200_FWD_WARPS 12
+#endif
+constexpr int FWD_HV = B200_FWD_HV;
+constexpr int FWD_WARPS = B200_FWD_WARPS;
 constexpr int FWD_THREADS = FWD_WARPS * 32;
-constexpr size_t FWD_SMEM = (size_t)FWD_WARPS * TTILE_WORDS * 4;
+constexpr int FWD_WARP_WORDS = 2 * ItemShape<FWD_HV>::TILE_WORDS + 2 * ItemShape<FWD_HV>::STASH_WORDS;
+constexpr size_t FWD_SMEM = (size_t)(AG_WORDS + FWD_WARPS * FWD_WARP_WORDS) * 4 + 16;
 
 struct Slots {
   float a0[AELEMS], a1[AELEMS], a2[AELEMS], a3[AELEMS];
 };
 
-// 8 vertices: P -> skinned coordinates -> 6 float4 stores into the lane's own row of the staging tile
-__device__ __forceinline__ void skin_fwd8(const float (&P)[24], Slots& s, const float4* __restrict__ A_g, int lane,
-                                          const uint32_t* __restrict__ meta, const float4* __restrict__ wts,
-                                          uint32_t force, float tx, float ty, float tz, float* row_out) {
-  uint32_t mts[8];
-  {
-    const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(meta));
-    const uint4 m1 = __ldg(reinterpret_cast<const uint4*>(meta) + 1);
-    mts[0] = m0.x | force; mts[1] = m0.y; mts[2] = m0.z; mts[3] = m0.w;
-    mts[4] = m1.x; mts[5] = m1.y; mts[6] = m1.z; mts[7] = m1.w;
-  }
-  float o[24];
+// 4 vertices, in place on the lane's own row: v_posed -> skinned coordinates
+__device__ __forceinline__ void skin_fwd4(Slots& s, const float* A_s, int lane, const uint32_t* meta_s,
+                                          const float4* wts_s, uint32_t force, float tx, float ty, float tz,
+                                          float* row_io) {
+  const uint4 m4 = *reinterpret_cast<const uint4*>(meta_s);
+  const uint32_t mts[4] = {m4.x | force, m4.y, m4.z, m4.w};
+  float4 ws[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) ws[i] = wts_s[i];
+  float P[12], o[12];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(row_io + i * 4);
+    P[i * 4] = v.x; P[i * 4 + 1] = v.y; P[i * 4 + 2] = v.z; P[i * 4 + 3] = v.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
     const uint32_t mt = mts[i];
-    const float4 w = __ldg(wts + i);
+    const float4 w = ws[i];
     if (mt & (0xFu << 20)) {
-      if (mt & (1u << 20)) load_slot_g(s.a0, A_g, mt & 31, lane);
-      if (mt & (1u << 21)) load_slot_g(s.a1, A_g, (mt >> 5) & 31, lane);
-      if (mt & (1u << 22)) load_slot_g(s.a2, A_g, (mt >> 10) & 31, lane);
-      if (mt & (1u << 23)) load_slot_g(s.a3, A_g, (mt >> 15) & 31, lane);
+      if (mt & (1u << 20)) load_slot(s.a0, A_s, mt & 31, lane);
+      if (mt & (1u << 21)) load_slot(s.a1, A_s, (mt >> 5) & 31, lane);
+      if (mt & (1u << 22)) load_slot(s.a2, A_s, (mt >> 10) & 31, lane);
+      if (mt & (1u << 23)) load_slot(s.a3, A_s, (mt >> 15) & 31, lane);
     }
     const float px = P[i * 3], py = P[i * 3 + 1], pz = P[i * 3 + 2];
     float ox = tx, oy = ty, oz = tz;
@@ -97,146 +257,91 @@ __device__ __forceinline__ void skin_fwd8(const float (&P)[24], Slots& s, const 
     o[i * 3] = ox; o[i * 3 + 1] = oy; o[i * 3 + 2] = oz;
   }
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
-    *reinterpret_cast<float4*>(row_out + i * 4) = make_float4(o[i * 4], o[i * 4 + 1], o[i * 4 + 2], o[i * 4 + 3]);
-}
-
-// rows of the staging tile <-> 384-byte row segments of a (B, V, 3) tensor.  Three warp instructions move
-// two rows: slot = k * 32 + lane in [0, 96) -> row = slot / 48, column pair = slot % 48.
-template <bool FULL>
-__device__ __forceinline__ void tile_to_global(const float* tile, float* dst0, size_t row_stride, int nrows,
-                                               int ncols, int lane) {
-#pragma unroll 4
-  for (int r2 = 0; r2 < 32; r2 += 2) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int slot = k * 32 + lane;
-      const int rr = slot >= 48 ? 1 : 0;
-      const int c = (slot - 48 * rr) * 2;
-      const int r = r2 + rr;
-      const float2 v = *reinterpret_cast<const float2*>(tile + r * TROW + c);
-      float* dst = dst0 + (size_t)r * row_stride + c;
-      if (FULL) {
-        st_stream2(dst, v);
-      } else if (r < nrows) {
-        if (c + 1 < ncols) st_stream2(dst, v);
-        else if (c < ncols) st_stream(dst, v.x);
-      }
-    }
-  }
-}
-template <bool FULL>
-__device__ __forceinline__ void global_to_tile(float* tile, const float* src0, size_t row_stride, int nrows, int ncols,
-                                               int lane) {
-#pragma unroll 1
-  for (int r8 = 0; r8 < 32; r8 += 8) {   // 12 eight-byte loads in flight per lane, then 12 shared stores
-    float2 v[12];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int slot = k * 32 + lane;
-        const int rr = slot >= 48 ? 1 : 0;
-        const int c = (slot - 48 * rr) * 2;
-        const int r = r8 + q * 2 + rr;
-        const float* src = src0 + (size_t)r * row_stride + c;
-        if (FULL) {
-          v[q * 3 + k] = ld_stream2(src);
-        } else {
-          float2 x = make_float2(0.f, 0.f);
-          if (r < nrows) {
-            if (c + 1 < ncols) x = ld_stream2(src);
-            else if (c < ncols) x.x = ld_stream(src);
-          }
-          v[q * 3 + k] = x;
-        }
-      }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int slot = k * 32 + lane;
-        const int rr = slot >= 48 ? 1 : 0;
-        const int c = (slot - 48 * rr) * 2;
-        *reinterpret_cast<float2*>(tile + (r8 + q * 2 + rr) * TROW + c) = v[q * 3 + k];
-      }
-  }
-}
-// element-wise fallbacks (odd V or a base pointer that is not 8-byte aligned)
-__device__ __forceinline__ void tile_to_global_scalar(const float* tile, float* dst0, size_t row_stride, int nrows,
-                                                      int ncols, int lane) {
-  for (int r = 0; r < nrows; ++r)
-    for (int c = lane; c < ncols; c += 32) dst0[(size_t)r * row_stride + c] = tile[r * TROW + c];
-}
-__device__ __forceinline__ void global_to_tile_scalar(float* tile, const float* src0, size_t row_stride, int nrows,
-                                                      int ncols, int lane) {
-  for (int r = 0; r < 32; ++r)
-    for (int c = lane; c < 96; c += 32)
-      tile[r * TROW + c] = (r < nrows && c < ncols) ? src0[(size_t)r * row_stride + c] : 0.f;
+  for (int i = 0; i < 3; ++i)
+    *reinterpret_cast<float4*>(row_io + i * 4) = make_float4(o[i * 4], o[i * 4 + 1], o[i * 4 + 2], o[i * 4 + 3]);
 }
 
 __global__ void __launch_bounds__(FWD_THREADS, 1)
-lbs_fwd_kernel(const float4* __restrict__ vpB, int S, const float4* __restrict__ A_blk, int b0, int nb, int ngroups,
-               const float* __restrict__ transl, float* __restrict__ verts, int V, int ntiles, int vec_ok,
+lbs_fwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict__ A_blk, int b0, int nb, int ngroups,
+               const float* __restrict__ transl, float* __restrict__ verts, int V, int nitems, int vec_ok,
                const uint32_t* __restrict__ vmeta, const float4* __restrict__ vwts) {
+  constexpr int HV = FWD_HV;
+  using SH = ItemShape<HV>;
   extern __shared__ __align__(128) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* tile = smem + warp * TTILE_WORDS;
-  float* my_row = tile + lane * TROW;
-  WarpRun run = make_run(ngroups, ntiles, blockIdx.x * FWD_WARPS + warp, gridDim.x * FWD_WARPS);
-  if (run.item >= run.end) return;
-
-  float P[24], Q[24];
-  int g = run.g, t = run.t;
-  const float4* vp_lane = vpB + (size_t)g * 32 + lane;            // + chunk * S
-  fetch_vp8(P, vp_lane + (size_t)(t * 24) * S, S);
-  Slots sl;
-  int cur_g = -1;
-  const float4* A_g = nullptr;
-  float tx = 0.f, ty = 0.f, tz = 0.f;
-  for (int item = run.item; item < run.end; ++item) {
-    uint32_t force = 0u;
-    if (g != cur_g) {                                             // new body group: translation + all four slots
-      cur_g = g;
-      A_g = A_blk + (size_t)g * (AG_WORDS / 4);
-      tx = ty = tz = 0.f;
+  float* A_s = smem;                                               // [24][3][32] float4: the group's transforms
+  float* wbase = smem + AG_WORDS + warp * FWD_WARP_WORDS;
+  float* tiles = wbase;                                            // [2][32][HROW]
+  uint32_t* stash = reinterpret_cast<uint32_t*>(wbase + 2 * SH::TILE_WORDS);   // [2][STASH_WORDS]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + AG_WORDS + FWD_WARPS * FWD_WARP_WORDS);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t a_phase = 0;
+  const CtaRange cta = make_cta_range(ngroups, nitems);
+  for (int seg0 = cta.begin; seg0 < cta.end;) {
+    // ---- one body group at a time per CTA: its 36 KB of transforms come in with one TMA bulk copy ----
+    const int g = seg0 / nitems;
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, AG_WORDS * 4);
+      bulk_g2s(A_s, A_blk + (size_t)g * (AG_WORDS / 4), AG_WORDS * 4, bar);
+    }
+    const int seg1 = min(cta.end, (g + 1) * nitems);
+    const int len = seg1 - seg0;
+    const int it0 = seg0 - g * nitems + len * warp / FWD_WARPS;    // this warp's contiguous items of the group
+    const int it1 = seg0 - g * nitems + len * (warp + 1) / FWD_WARPS;
+    if (it0 < it1) {
+      const float4* vp_g = vpB + (size_t)g * nc4 * 32 + lane;
+      float tx = 0.f, ty = 0.f, tz = 0.f;
       if (transl != nullptr && g * 32 + lane < nb) {
         const float* tp = transl + (size_t)(b0 + g * 32 + lane) * 3;
         tx = tp[0]; ty = tp[1]; tz = tp[2];
       }
-      force = 0xFu << 20;
-    } else if (item == run.item) {
-      force = 0xFu << 20;
-    }
-    const int vbase = t * TILE_V;
-    const uint32_t* meta = vmeta + vbase;
-    const float4* wts = vwts + vbase;
-    const float4* vp_t = vp_lane + (size_t)(t * 24) * S;
-    // next item (for the prefetch that crosses the tile boundary)
-    int ng = g, nt = t + 1;
-    if (nt == ntiles) { nt = 0; ++ng; }
-    fetch_vp8(Q, vp_t + 6 * S, S);
-    skin_fwd8(P, sl, A_g, lane, meta, wts, force, tx, ty, tz, my_row);
-    fetch_vp8(P, vp_t + 12 * S, S);
-    skin_fwd8(Q, sl, A_g, lane, meta + 8, wts + 8, 0u, tx, ty, tz, my_row + 24);
-    fetch_vp8(Q, vp_t + 18 * S, S);
-    skin_fwd8(P, sl, A_g, lane, meta + 16, wts + 16, 0u, tx, ty, tz, my_row + 48);
-    const float4* vp_next = vpB + (size_t)ng * 32 + lane;
-    if (item + 1 < run.end) fetch_vp8(P, vp_next + (size_t)(nt * 24) * S, S);
-    skin_fwd8(Q, sl, A_g, lane, meta + 24, wts + 24, 0u, tx, ty, tz, my_row + 72);
-    __syncwarp();
-    // flush: each body row of the tile is 96 contiguous floats of the (B, V, 3) output
-    {
       const int nrows = min(32, nb - g * 32);
-      const int ncols = min(TILE_V, V - vbase) * 3;
-      float* dst0 = verts + ((size_t)(b0 + g * 32) * V + vbase) * 3;
-      if (!vec_ok) tile_to_global_scalar(tile, dst0, (size_t)V * 3, nrows, ncols, lane);
-      else if (nrows == 32 && ncols == 96) tile_to_global<true>(tile, dst0, (size_t)V * 3, 32, 96, lane);
-      else tile_to_global<false>(tile, dst0, (size_t)V * 3, nrows, ncols, lane);
+      float* v_g = verts + (size_t)(b0 + g * 32) * V * 3;
+      plan_store<HV>(stash, plan_load<HV>(vmeta, vwts, it0 * HV, lane), lane);
+      issue_vp_rows<HV>(tiles + lane * SH::HROW, vp_g + (size_t)(it0 * SH::NCH4) * 32);
+      cp_async_commit();
+      Slots sl;
+      int buf = 0;
+      __syncwarp();
+      mbar_wait(bar, a_phase);
+      for (int t = it0; t < it1; ++t) {
+        const bool more = t + 1 < it1;
+        float* tile = tiles + buf * SH::TILE_WORDS;
+        float* my_row = tile + lane * SH::HROW;
+        PlanRegs nplan;
+        if (more) {                                                // next item: v_posed into the other buffer
+          nplan = plan_load<HV>(vmeta, vwts, (t + 1) * HV, lane);
+          issue_vp_rows<HV>(tiles + (buf ^ 1) * SH::TILE_WORDS + lane * SH::HROW, vp_g + (size_t)((t + 1) * SH::NCH4) * 32);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();                                        // this item's rows have landed (own row only)
+        const uint32_t* meta_s = stash + buf * SH::STASH_WORDS;
+        const float4* wts_s = reinterpret_cast<const float4*>(meta_s + HV);
+#pragma unroll 1
+        for (int u = 0; u < HV / 4; ++u)
+          skin_fwd4(sl, A_s, lane, meta_s + u * 4, wts_s + u * 4, (u == 0 && t == it0) ? (0xFu << 20) : 0u, tx, ty, tz,
+                    my_row + u * 12);
+        if (more) plan_store<HV>(stash + (buf ^ 1) * SH::STASH_WORDS, nplan, lane);
+        __syncwarp();
+        // flush: each body row of the item is ROWS contiguous floats of the (B, V, 3) output
+        {
+          const int vbase = t * HV;
+          const int ncols = max(0, min(HV, V - vbase)) * 3;
+          float* dst0 = v_g + (size_t)vbase * 3;
+          if (!vec_ok) tile_to_global_scalar<HV>(tile, dst0, (size_t)V * 3, nrows, ncols, lane);
+          else tile_to_global<HV>(tile, dst0, (size_t)V * 3, nrows, ncols, lane);
+        }
+        __syncwarp();                                              // rows are re-filled two items later
+        buf ^= 1;
+      }
     }
-    __syncwarp();
-    if (ng != g) vp_lane = vp_next;
-    g = ng; t = nt;
+    seg0 = seg1;
+    a_phase ^= 1;
+    if (seg0 < cta.end) __syncthreads();                           // group switch is CTA-wide: A_s is re-filled
   }
 }
 
@@ -246,9 +351,18 @@ lbs_fwd_kernel(const float4* __restrict__ vpB, int S, const float4* __restrict__
 //   dA_j    += w_s [dV (x) p | dV]           -> per-slot register accumulators -> fp32 RED into dA_acc
 //   dtransl += dV                            -> fp32 RED into dtr_acc
 // ---------------------------------------------------------------------------------------------
-constexpr int BWD_WARPS = 12;
+#ifndef B200_BWD_HV
+#define B200_BWD_HV 8
+#endif
+#ifndef B200_BWD_WARPS
+#define B200_BWD_WARPS 12
+#endif
+constexpr int BWD_HV = B200_BWD_HV;
+constexpr int BWD_WARPS = B200_BWD_WARPS;
 constexpr int BWD_THREADS = BWD_WARPS * 32;
-constexpr size_t BWD_SMEM = (size_t)BWD_WARPS * TTILE_WORDS * 4;
+constexpr int BWD_WARP_WORDS = 2 * ItemShape<BWD_HV>::TILE_WORDS + 2 * ItemShape<BWD_HV>::NCH4 * 128 +
+                               2 * ItemShape<BWD_HV>::STASH_WORDS;
+constexpr size_t BWD_SMEM = (size_t)(AG_WORDS + BWD_WARPS * BWD_WARP_WORDS) * 4 + 16;
 
 struct BwdState {
   float a0[9], a1[9], a2[9], a3[9];                      // rotation parts of the 4 cached transforms
@@ -257,29 +371,34 @@ struct BwdState {
   float sx, sy, sz;
 };
 
-// 4 vertices: P (v_posed), staged dV from the lane's row -> q[12] (dv_posed rows), accumulators updated
-__device__ __forceinline__ void skin_bwd4(const float (&P)[12], BwdState& s, const float4* __restrict__ A_g,
-                                          float* __restrict__ dA_g, int lane, const uint32_t* __restrict__ meta,
-                                          const float4* __restrict__ wts, uint32_t force, const float* row_in,
-                                          float (&q)[12]) {
-  const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(meta));
+// 4 vertices: v_posed from the dense buffer, staged dV of the lane's row -> dv_posed written back in place
+// (fp32), accumulators updated
+__device__ __forceinline__ void skin_bwd4(BwdState& s, const float* A_s, float* __restrict__ dA_g,
+                                          int lane, const uint32_t* meta_s, const float4* wts_s, uint32_t force,
+                                          const float4* vp_s, float* row_io) {
+  const uint4 m4 = *reinterpret_cast<const uint4*>(meta_s);
   const uint32_t mts[4] = {m4.x | force, m4.y, m4.z, m4.w};
-  float G[12];
+  float4 ws[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ws[i] = wts_s[i];
+  float P[12], G[12], q[12];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const float4 v = *reinterpret_cast<const float4*>(row_in + i * 4);
-    G[i * 4] = v.x; G[i * 4 + 1] = v.y; G[i * 4 + 2] = v.z; G[i * 4 + 3] = v.w;
+    const float4 v = vp_s[i * 32];
+    P[i * 4] = v.x; P[i * 4 + 1] = v.y; P[i * 4 + 2] = v.z; P[i * 4 + 3] = v.w;
+    const float4 h = *reinterpret_cast<const float4*>(row_io + i * 4);
+    G[i * 4] = h.x; G[i * 4 + 1] = h.y; G[i * 4 + 2] = h.z; G[i * 4 + 3] = h.w;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t mt = mts[i];
-    const float4 w = __ldg(wts + i);
+    const float4 w = ws[i];
     if (mt & (0xFu << 20)) {
       const uint32_t pv = s.prev;
-      if (mt & (1u << 20)) { flush_slot_g(s.d0, dA_g, pv & 31, lane); load_rot_g(s.a0, A_g, mt & 31, lane); }
-      if (mt & (1u << 21)) { flush_slot_g(s.d1, dA_g, (pv >> 5) & 31, lane); load_rot_g(s.a1, A_g, (mt >> 5) & 31, lane); }
-      if (mt & (1u << 22)) { flush_slot_g(s.d2, dA_g, (pv >> 10) & 31, lane); load_rot_g(s.a2, A_g, (mt >> 10) & 31, lane); }
-      if (mt & (1u << 23)) { flush_slot_g(s.d3, dA_g, (pv >> 15) & 31, lane); load_rot_g(s.a3, A_g, (mt >> 15) & 31, lane); }
+      if (mt & (1u << 20)) { flush_slot_g(s.d0, dA_g, pv & 31, lane); load_rot(s.a0, A_s, mt & 31, lane); }
+      if (mt & (1u << 21)) { flush_slot_g(s.d1, dA_g, (pv >> 5) & 31, lane); load_rot(s.a1, A_s, (mt >> 5) & 31, lane); }
+      if (mt & (1u << 22)) { flush_slot_g(s.d2, dA_g, (pv >> 10) & 31, lane); load_rot(s.a2, A_s, (mt >> 10) & 31, lane); }
+      if (mt & (1u << 23)) { flush_slot_g(s.d3, dA_g, (pv >> 15) & 31, lane); load_rot(s.a3, A_s, (mt >> 15) & 31, lane); }
     }
     s.prev = mt;
     const float px = P[i * 3], py = P[i * 3 + 1], pz = P[i * 3 + 2];
@@ -303,6 +422,9 @@ __device__ __forceinline__ void skin_bwd4(const float (&P)[12], BwdState& s, con
 #undef B200_SKIN_BWD
     q[i * 3] = qx; q[i * 3 + 1] = qy; q[i * 3 + 2] = qz;
   }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    *reinterpret_cast<float4*>(row_io + i * 4) = make_float4(q[i * 4], q[i * 4 + 1], q[i * 4 + 2], q[i * 4 + 3]);
 }
 
 // close the accumulators of the current group: 4 slots -> dA, translation sums -> dtransl
@@ -318,81 +440,107 @@ __device__ __forceinline__ void bwd_close_group(BwdState& s, float* dA_g, float*
 }
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
-lbs_bwd_kernel(const float4* __restrict__ vpB, int S, const float4* __restrict__ A_blk, int b0, int nb, int ngroups,
-               const float* __restrict__ grad_verts, int V, int ntiles, int vec_ok,
+lbs_bwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict__ A_blk, int b0, int nb, int ngroups,
+               const float* __restrict__ grad_verts, int V, int nitems, int vec_ok,
                const uint32_t* __restrict__ vmeta, const float4* __restrict__ vwts,
                __nv_bfloat16* __restrict__ dvp_hi, __nv_bfloat16* __restrict__ dvp_lo,
                float* __restrict__ dA_acc, float* __restrict__ dtr_acc) {
+  constexpr int HV = BWD_HV;
+  using SH = ItemShape<HV>;
   extern __shared__ __align__(128) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* tile = smem + warp * TTILE_WORDS;
-  const float* my_row = tile + lane * TROW;
-  WarpRun run = make_run(ngroups, ntiles, blockIdx.x * BWD_WARPS + warp, gridDim.x * BWD_WARPS);
-  if (run.item >= run.end) return;
-
-  float P[12], Q[12];
-  int g = run.g, t = run.t;
-  BwdState st;
-#pragma unroll
-  for (int e = 0; e < AELEMS; ++e) st.d0[e] = st.d1[e] = st.d2[e] = st.d3[e] = 0.f;
-  st.prev = 0u;
-  st.sx = st.sy = st.sz = 0.f;
-  int cur_g = -1;
-  const float4* A_g = nullptr;
-  float* dA_g = nullptr;
-  const float4* vp_lane = nullptr;
-  for (int item = run.item; item < run.end; ++item) {
-    uint32_t force = 0u;
-    if (g != cur_g) {
-      if (cur_g >= 0) bwd_close_group(st, dA_g, dtr_acc + (size_t)cur_g * 96, lane);
-      cur_g = g;
-      A_g = A_blk + (size_t)g * (AG_WORDS / 4);
-      dA_g = dA_acc + (size_t)g * AG_WORDS;
-      vp_lane = vpB + (size_t)g * 32 + lane;
-      force = 0xFu << 20;     // the accumulators are zero here, so the flushes this triggers add nothing
-    }
-    const int vbase = t * TILE_V;
-    const uint32_t* meta = vmeta + vbase;
-    const float4* wts = vwts + vbase;
-    const float4* vp_t = vp_lane + (size_t)(t * 24) * S;
-    fetch_vp4(P, vp_t, S);
-    // ---- stage dV rows of this tile (384 contiguous bytes per body row) ----
-    {
-      const int nrows = min(32, nb - g * 32);
-      const int ncols = min(TILE_V, V - vbase) * 3;
-      const float* src0 = grad_verts + ((size_t)(b0 + g * 32) * V + vbase) * 3;
-      if (!vec_ok) global_to_tile_scalar(tile, src0, (size_t)V * 3, nrows, ncols, lane);
-      else if (nrows == 32 && ncols == 96) global_to_tile<true>(tile, src0, (size_t)V * 3, 32, 96, lane);
-      else global_to_tile<false>(tile, src0, (size_t)V * 3, max(nrows, 0), ncols, lane);
-    }
-    __syncwarp();
-    // ---- 4 x (4 + 4 vertices): v_posed prefetched one unit ahead; 8 vertices = 24 rows = 3 chunks of dvp ----
-    const size_t chunk_stride = (size_t)S * 8;                                  // elements between 8-row chunks
-    __nv_bfloat16* hi_p = dvp_hi + ((size_t)(t * 12) * S + (size_t)g * 32 + lane) * 8;
-    __nv_bfloat16* lo_p = dvp_lo ? dvp_lo + ((size_t)(t * 12) * S + (size_t)g * 32 + lane) * 8 : nullptr;
-#pragma unroll 1
-    for (int u = 0; u < 4; ++u) {
-      float qa[12], qb[12];
-      fetch_vp4(Q, vp_t + (size_t)(u * 6 + 3) * S, S);
-      skin_bwd4(P, st, A_g, dA_g, lane, meta + u * 8, wts + u * 8, u == 0 ? force : 0u, my_row + u * 24, qa);
-      if (u < 3) fetch_vp4(P, vp_t + (size_t)(u * 6 + 6) * S, S);
-      skin_bwd4(Q, st, A_g, dA_g, lane, meta + u * 8 + 4, wts + u * 8 + 4, 0u, my_row + u * 24 + 12, qb);
-      const float c0[8] = {qa[0], qa[1], qa[2], qa[3], qa[4], qa[5], qa[6], qa[7]};
-      const float c1[8] = {qa[8], qa[9], qa[10], qa[11], qb[0], qb[1], qb[2], qb[3]};
-      const float c2[8] = {qb[4], qb[5], qb[6], qb[7], qb[8], qb[9], qb[10], qb[11]};
-      store_dvp_chunk(c0, hi_p + (size_t)(u * 3) * chunk_stride, lo_p ? lo_p + (size_t)(u * 3) * chunk_stride : nullptr);
-      store_dvp_chunk(c1, hi_p + (size_t)(u * 3 + 1) * chunk_stride, lo_p ? lo_p + (size_t)(u * 3 + 1) * chunk_stride : nullptr);
-      store_dvp_chunk(c2, hi_p + (size_t)(u * 3 + 2) * chunk_stride, lo_p ? lo_p + (size_t)(u * 3 + 2) * chunk_stride : nullptr);
-    }
-    __syncwarp();
-    if (++t == ntiles) { t = 0; ++g; }
+  float* A_s = smem;                                                           // the group's transforms
+  float* wbase = smem + AG_WORDS + warp * BWD_WARP_WORDS;
+  float* tiles = wbase;                                                        // [2][32][HROW]   dV in / dv_posed out
+  float4* vbufs = reinterpret_cast<float4*>(wbase + 2 * SH::TILE_WORDS);       // [2][NCH4][32]   v_posed
+  uint32_t* stash = reinterpret_cast<uint32_t*>(wbase + 2 * SH::TILE_WORDS + 2 * SH::NCH4 * 128);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + AG_WORDS + BWD_WARPS * BWD_WARP_WORDS);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  bwd_close_group(st, dA_g, dtr_acc + (size_t)cur_g * 96, lane);
+  __syncthreads();
+  uint32_t a_phase = 0;
+  const size_t row_stride = (size_t)V * 3;
+  const CtaRange cta = make_cta_range(ngroups, nitems);
+  for (int seg0 = cta.begin; seg0 < cta.end;) {
+    const int g = seg0 / nitems;
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, AG_WORDS * 4);
+      bulk_g2s(A_s, A_blk + (size_t)g * (AG_WORDS / 4), AG_WORDS * 4, bar);
+    }
+    const int seg1 = min(cta.end, (g + 1) * nitems);
+    const int len = seg1 - seg0;
+    const int it0 = seg0 - g * nitems + len * warp / BWD_WARPS;
+    const int it1 = seg0 - g * nitems + len * (warp + 1) / BWD_WARPS;
+    if (it0 < it1) {
+      float* dA_g = dA_acc + (size_t)g * AG_WORDS;
+      const float4* vp_g = vpB + (size_t)g * nc4 * 32 + lane;
+      const float* dv_g = grad_verts + (size_t)(b0 + g * 32) * V * 3;
+      const int nrows = max(0, min(32, nb - g * 32));
+      plan_store<HV>(stash, plan_load<HV>(vmeta, vwts, it0 * HV, lane), lane);
+      issue_vp_dense<HV>(vbufs, vp_g + (size_t)(it0 * SH::NCH4) * 32, lane);
+      if (vec_ok) issue_rows<HV>(tiles, dv_g + (size_t)it0 * HV * 3, row_stride, nrows, max(0, min(HV, V - it0 * HV)) * 3, lane);
+      cp_async_commit();
+      BwdState st;
+#pragma unroll
+      for (int e = 0; e < AELEMS; ++e) st.d0[e] = st.d1[e] = st.d2[e] = st.d3[e] = 0.f;
+      st.prev = 0u;
+      st.sx = st.sy = st.sz = 0.f;
+      int buf = 0;
+      mbar_wait(bar, a_phase);
+      for (int t = it0; t < it1; ++t) {
+        const bool more = t + 1 < it1;
+        float* tile = tiles + buf * SH::TILE_WORDS;
+        float* my_row = tile + lane * SH::HROW;
+        const float4* vp_s = vbufs + buf * (SH::NCH4 * 32) + lane;
+        PlanRegs nplan;
+        if (more) {
+          nplan = plan_load<HV>(vmeta, vwts, (t + 1) * HV, lane);
+          issue_vp_dense<HV>(vbufs + (buf ^ 1) * (SH::NCH4 * 32), vp_g + (size_t)((t + 1) * SH::NCH4) * 32, lane);
+          if (vec_ok)
+            issue_rows<HV>(tiles + (buf ^ 1) * SH::TILE_WORDS, dv_g + (size_t)(t + 1) * HV * 3, row_stride, nrows,
+                           max(0, min(HV, V - (t + 1) * HV)) * 3, lane);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        if (!vec_ok)
+          global_to_tile_scalar<HV>(tile, dv_g + (size_t)t * HV * 3, row_stride, nrows, max(0, min(HV, V - t * HV)) * 3, lane);
+        __syncwarp();                                              // the dV rows were written by other lanes
+        const uint32_t* meta_s = stash + buf * SH::STASH_WORDS;
+        const float4* wts_s = reinterpret_cast<const float4*>(meta_s + HV);
+        // the first vertex of the run (re)loads all four slots; the accumulators are zero there
+#pragma unroll 1
+        for (int u = 0; u < HV / 4; ++u)
+          skin_bwd4(st, A_s, dA_g, lane, meta_s + u * 4, wts_s + u * 4, (u == 0 && t == it0) ? (0xFu << 20) : 0u,
+                    vp_s + u * 96, my_row + u * 12);
+        if (more) plan_store<HV>(stash + (buf ^ 1) * SH::STASH_WORDS, nplan, lane);
+        // ---- the lane's gradient rows -> bf16 hi/lo chunks of dvp (512 contiguous bytes per warp store) ----
+        {
+          // dvp [S/128][n_pad/8][128][8]: chunk stride 1024 elements, this body at ((g & 3) * 32 + lane) * 8
+          const size_t o0 = (((size_t)(g >> 2) * (nc4 >> 1) + t * SH::NCH8) * 128 + (g & 3) * 32 + lane) * 8;
+#pragma unroll
+          for (int c = 0; c < SH::NCH8; ++c) {
+            const float4 x = *reinterpret_cast<const float4*>(my_row + c * 8);
+            const float4 y = *reinterpret_cast<const float4*>(my_row + c * 8 + 4);
+            const float ch[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+            store_dvp_chunk(ch, dvp_hi + o0 + c * 1024, dvp_lo ? dvp_lo + o0 + c * 1024 : nullptr);
+          }
+        }
+        __syncwarp();                                              // buffers are re-filled two items later
+        buf ^= 1;
+      }
+      bwd_close_group(st, dA_g, dtr_acc + (size_t)g * 96, lane);
+    }
+    seg0 = seg1;
+    a_phase ^= 1;
+    if (seg0 < cta.end) __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
-static int run_grid(int ngroups, int ntiles, int warps, int num_sms) {
-  const long long total = (long long)ngroups * ntiles;
+static int run_grid(int ngroups, int nitems, int warps, int num_sms) {
+  const long long total = (long long)ngroups * nitems;
   return (int)std::max<long long>(1, std::min<long long>(num_sms, (total + warps - 1) / warps));
 }
 
@@ -400,12 +548,13 @@ int launch_lbs_fwd(const DevModel& m, const float* vpB, int S, const float* A_bl
                    const float* transl, float* verts, int num_sms, cudaStream_t st) {
   if (nb <= 0) return 0;
   const int groups = (nb + 31) / 32;
+  const int nitems = m.ntiles * (TILE_V / FWD_HV);
   const int vec_ok = ((m.V & 1) == 0 && (reinterpret_cast<uintptr_t>(verts) & 7) == 0) ? 1 : 0;
   B200_CUDA_TRY(cudaFuncSetAttribute(lbs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
   LaunchTimer _timer("lbs_fwd", st);
-  lbs_fwd_kernel<<<run_grid(groups, m.ntiles, FWD_WARPS, num_sms), FWD_THREADS, FWD_SMEM, st>>>(
-      reinterpret_cast<const float4*>(vpB), S, reinterpret_cast<const float4*>(A_blk), b0, nb, groups, transl, verts,
-      m.V, m.ntiles, vec_ok, m.vmeta, m.vwts);
+  lbs_fwd_kernel<<<run_grid(groups, nitems, FWD_WARPS, num_sms), FWD_THREADS, FWD_SMEM, st>>>(
+      reinterpret_cast<const float4*>(vpB), m.n_pad / 4, reinterpret_cast<const float4*>(A_blk), b0, nb, groups, transl, verts,
+      m.V, nitems, vec_ok, m.vmeta, m.vwts);
   B200_LAUNCH_CHECK("lbs_fwd");
   return 0;
 }
@@ -416,12 +565,13 @@ int launch_lbs_bwd(const DevModel& m, const float* vpB, int S, int Sw, const flo
                    const float* grad_verts, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_acc,
                    float* dtr_acc, int num_sms, cudaStream_t st) {
   const int groups = Sw / 32;
+  const int nitems = m.ntiles * (TILE_V / BWD_HV);
   const int vec_ok = ((m.V & 1) == 0 && (reinterpret_cast<uintptr_t>(grad_verts) & 7) == 0) ? 1 : 0;
   B200_CUDA_TRY(cudaFuncSetAttribute(lbs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
   LaunchTimer _timer("lbs_bwd", st);
-  lbs_bwd_kernel<<<run_grid(groups, m.ntiles, BWD_WARPS, num_sms), BWD_THREADS, BWD_SMEM, st>>>(
-      reinterpret_cast<const float4*>(vpB), S, reinterpret_cast<const float4*>(A_blk), b0, nb, groups, grad_verts, m.V,
-      m.ntiles, vec_ok, m.vmeta, m.vwts, dvp_hi, dvp_lo, dA_acc, dtr_acc);
+  lbs_bwd_kernel<<<run_grid(groups, nitems, BWD_WARPS, num_sms), BWD_THREADS, BWD_SMEM, st>>>(
+      reinterpret_cast<const float4*>(vpB), m.n_pad / 4, reinterpret_cast<const float4*>(A_blk), b0, nb, groups, grad_verts, m.V,
+      nitems, vec_ok, m.vmeta, m.vwts, dvp_hi, dvp_lo, dA_acc, dtr_acc);
   B200_LAUNCH_CHECK("lbs_bwd");
   return 0;
 }

@@ -1,11 +1,13 @@
 // Helpers shared by the skinning kernels (lbs.cu: real vertex tiles; joints.cu: virtual joint tiles).
 //
-// Slab-local layouts (S = slab pitch in bodies, a multiple of 128; lane = body everywhere):
-//   vpB   [n_pad/4][S][4] fp32   blend output: element (row n, body s) at ((n >> 2) * S + s) * 4 + (n & 3);
-//                                a warp (32 consecutive bodies) reads / writes 512 contiguous bytes per float4
-//   dvp   [n_pad/8][S][8] bf16   gradient-GEMM operand (hi and lo arrays): element (body s, row n) at
-//                                ((n >> 3) * S + s) * 8 + (n & 7) -- 16-byte chunks = rows of the UMMA
-//                                no-swizzle K-major core matrices, so the GEMM pulls 2 KB per (chunk, 128 bodies)
+// Slab-local layouts, all blocked by body group (32 consecutive bodies; lane = body everywhere) so that a
+// warp streams through one contiguous block per group:
+//   vpB   [S/32][n_pad/4][32][4] fp32   blend output: element (row n, body s) at
+//                                ((s >> 5) * (n_pad/4) + (n >> 2)) * 128 + (s & 31) * 4 + (n & 3)
+//   dvp   [S/128][n_pad/8][128][8] bf16 gradient-GEMM operand (hi and lo arrays): element (body s, row n) at
+//                                ((s >> 7) * (n_pad/8) + (n >> 3)) * 1024 + (s & 127) * 8 + (n & 7) -- 16-byte
+//                                chunks = rows of the UMMA no-swizzle K-major core matrices; a K slab of 64 rows
+//                                of one 128-body tile is 16 contiguous KB = one bulk copy of the GEMM
 //   A_blk [S/32][24][3][32][4]   skinning transforms: one float4 = row r of [R | t] of one body
 //   dA    [S/32][24*12][32]      gradient of A, accumulated with fp32 REDs
 #pragma once
@@ -132,13 +134,12 @@ __device__ __forceinline__ void flush_slot_g(float (&d)[AELEMS], float* dA_g, in
   }
 }
 
-// x -> bf16 hi, bf16 lo   (x ~ hi + lo to 16 mantissa bits); two values per 32-bit word, low half first
+// (x0, x1) -> packed bf16 hi pair and bf16 lo pair (x ~ hi + lo to 16 mantissa bits); low half = x0
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-  const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-  const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-  hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-  lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float r0 = x0 - __uint_as_float(hi << 16);
+  const float r1 = x1 - __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
 }
 // eight consecutive gradient rows of one body -> one 16-byte chunk of dvp_hi (and dvp_lo)
 __device__ __forceinline__ void store_dvp_chunk(const float (&q)[8], __nv_bfloat16* hi_p, __nv_bfloat16* lo_p) {
