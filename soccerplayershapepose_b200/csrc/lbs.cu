@@ -59,28 +59,17 @@ __device__ __forceinline__ CtaRange make_cta_range(int ngroups, int nitems) {
   return r;
 }
 
-// plan words of one item, held by lanes 0..HV-1 between the global load and the stash store
-struct PlanRegs {
-  uint32_t m;
-  float4 w;
-};
-template <int HV>
-__device__ __forceinline__ PlanRegs plan_load(const uint32_t* __restrict__ vmeta, const float4* __restrict__ vwts,
-                                              int vbase, int lane) {
-  PlanRegs r;
-  r.m = 0u;
-  r.w = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (lane < HV) {
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r.m) : "l"(vmeta + vbase + lane));
-    r.w = ld_stream4(vwts + vbase + lane);
-  }
-  return r;
+// plan words of one item (HV metas + HV float4 weights, warp-uniform data): lanes 0..HV-1 copy them into the
+// warp's stash with cp.async, in the same group as the item's data
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
 }
 template <int HV>
-__device__ __forceinline__ void plan_store(uint32_t* stash, const PlanRegs& r, int lane) {
+__device__ __forceinline__ void issue_plan(uint32_t* stash, const uint32_t* __restrict__ vmeta,
+                                           const float4* __restrict__ vwts, int vbase, int lane) {
   if (lane < HV) {
-    stash[lane] = r.m;
-    reinterpret_cast<float4*>(stash + HV)[lane] = r.w;
+    cp_async4(stash + lane, vmeta + vbase + lane);
+    cp_async16(reinterpret_cast<float4*>(stash + HV) + lane, vwts + vbase + lane);
   }
 }
 
@@ -208,15 +197,37 @@ __device__ __forceinline__ void global_to_tile_scalar(float* tile, const float* 
 #ifndef B200_FWD_WARPS
 #define B200_FWD_WARPS 12
 #endif
+#ifndef B200_FWD_RUN
+#define B200_FWD_RUN 2
+#endif
+constexpr int FWD_RUN = B200_FWD_RUN;       // consecutive items per warp and round (slots persist inside a run)
 constexpr int FWD_HV = B200_FWD_HV;
 constexpr int FWD_WARPS = B200_FWD_WARPS;
 constexpr int FWD_THREADS = FWD_WARPS * 32;
 constexpr int FWD_WARP_WORDS = 2 * ItemShape<FWD_HV>::TILE_WORDS + 2 * ItemShape<FWD_HV>::STASH_WORDS;
 constexpr size_t FWD_SMEM = (size_t)(AG_WORDS + FWD_WARPS * FWD_WARP_WORDS) * 4 + 16;
 
-struct Slots {
-  float a0[AELEMS], a1[AELEMS], a2[AELEMS], a3[AELEMS];
+// The four cached transforms ("slots") as packed pairs: x/y rows of a slot are (r0c, r1c) pairs, the z rows of
+// two slots share pairs (lo = slots 0 / 2, hi = slots 1 / 3), so a vertex costs 25 FFMA2-class instructions
+// instead of 48 scalar FFMA.
+struct SlotXY {
+  f2 c0, c1, c2, t;          // (r00 r10) (r01 r11) (r02 r12) (t0 t1)
 };
+struct SlotZ2 {
+  f2 r20, r21, r22, t2;      // z row of two slots
+};
+struct Slots {
+  SlotXY s0, s1, s2, s3;
+  SlotZ2 zA, zB;
+};
+template <bool HI>
+__device__ __forceinline__ void load_slot2(SlotXY& s, SlotZ2& z, const float* A_s, int joint, int lane) {
+  const float4* p = reinterpret_cast<const float4*>(A_s) + joint * 96 + lane;
+  const float4 q0 = p[0], q1 = p[32], q2 = p[64];
+  s.c0 = mk2(q0.x, q0.y); s.c1 = mk2(q0.z, q0.w); s.c2 = mk2(q1.x, q1.y); s.t = mk2(q1.z, q1.w);
+  z.r20 = set_half<HI>(z.r20, q2.x); z.r21 = set_half<HI>(z.r21, q2.y);
+  z.r22 = set_half<HI>(z.r22, q2.z); z.t2 = set_half<HI>(z.t2, q2.w);
+}
 
 // 4 vertices, in place on the lane's own row: v_posed -> skinned coordinates
 __device__ __forceinline__ void skin_fwd4(Slots& s, const float* A_s, int lane, const uint32_t* meta_s,
@@ -233,28 +244,28 @@ __device__ __forceinline__ void skin_fwd4(Slots& s, const float* A_s, int lane, 
     const float4 v = *reinterpret_cast<const float4*>(row_io + i * 4);
     P[i * 4] = v.x; P[i * 4 + 1] = v.y; P[i * 4 + 2] = v.z; P[i * 4 + 3] = v.w;
   }
+  const f2 txy = mk2(tx, ty), tz0 = mk2(tz, 0.f);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t mt = mts[i];
     const float4 w = ws[i];
     if (mt & (0xFu << 20)) {
-      if (mt & (1u << 20)) load_slot(s.a0, A_s, mt & 31, lane);
-      if (mt & (1u << 21)) load_slot(s.a1, A_s, (mt >> 5) & 31, lane);
-      if (mt & (1u << 22)) load_slot(s.a2, A_s, (mt >> 10) & 31, lane);
-      if (mt & (1u << 23)) load_slot(s.a3, A_s, (mt >> 15) & 31, lane);
+      if (mt & (1u << 20)) load_slot2<false>(s.s0, s.zA, A_s, mt & 31, lane);
+      if (mt & (1u << 21)) load_slot2<true>(s.s1, s.zA, A_s, (mt >> 5) & 31, lane);
+      if (mt & (1u << 22)) load_slot2<false>(s.s2, s.zB, A_s, (mt >> 10) & 31, lane);
+      if (mt & (1u << 23)) load_slot2<true>(s.s3, s.zB, A_s, (mt >> 15) & 31, lane);
     }
-    const float px = P[i * 3], py = P[i * 3 + 1], pz = P[i * 3 + 2];
-    float ox = tx, oy = ty, oz = tz;
-#define B200_SKIN(a, wk)                                                        \
-  ox = fmaf(wk, fmaf(a[0], px, fmaf(a[1], py, fmaf(a[2], pz, a[3]))), ox);      \
-  oy = fmaf(wk, fmaf(a[4], px, fmaf(a[5], py, fmaf(a[6], pz, a[7]))), oy);      \
-  oz = fmaf(wk, fmaf(a[8], px, fmaf(a[9], py, fmaf(a[10], pz, a[11]))), oz);
-    B200_SKIN(s.a0, w.x)
-    B200_SKIN(s.a1, w.y)
-    B200_SKIN(s.a2, w.z)
-    B200_SKIN(s.a3, w.w)
-#undef B200_SKIN
-    o[i * 3] = ox; o[i * 3 + 1] = oy; o[i * 3 + 2] = oz;
+    const f2 px = bc2(P[i * 3]), py = bc2(P[i * 3 + 1]), pz = bc2(P[i * 3 + 2]);
+    f2 oxy = txy;
+#define B200_SKIN_XY(sl, wk) oxy = fma2(bc2(wk), fma2(sl.c0, px, fma2(sl.c1, py, fma2(sl.c2, pz, sl.t))), oxy);
+    B200_SKIN_XY(s.s0, w.x)
+    B200_SKIN_XY(s.s1, w.y)
+    B200_SKIN_XY(s.s2, w.z)
+    B200_SKIN_XY(s.s3, w.w)
+#undef B200_SKIN_XY
+    f2 oz = fma2(mk2(w.x, w.y), fma2(s.zA.r20, px, fma2(s.zA.r21, py, fma2(s.zA.r22, pz, s.zA.t2))), tz0);
+    oz = fma2(mk2(w.z, w.w), fma2(s.zB.r20, px, fma2(s.zB.r21, py, fma2(s.zB.r22, pz, s.zB.t2))), oz);
+    o[i * 3] = lo2(oxy); o[i * 3 + 1] = hi2(oxy); o[i * 3 + 2] = lo2(oz) + hi2(oz);
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -290,9 +301,12 @@ lbs_fwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
     }
     const int seg1 = min(cta.end, (g + 1) * nitems);
     const int len = seg1 - seg0;
-    const int it0 = seg0 - g * nitems + len * warp / FWD_WARPS;    // this warp's contiguous items of the group
-    const int it1 = seg0 - g * nitems + len * (warp + 1) / FWD_WARPS;
-    if (it0 < it1) {
+    // the CTA sweeps the group's items in rounds of FWD_WARPS * FWD_RUN consecutive items, FWD_RUN consecutive
+    // items per warp: at any time its warps read / write neighbouring pieces of the same 32 body rows
+    const int sb = seg0 - g * nitems;
+    auto off_at = [&](int n) { const int r = n / FWD_RUN; return (r * FWD_WARPS + warp) * FWD_RUN + (n - r * FWD_RUN); };
+    if (off_at(0) < len) {
+      const int it0 = sb + off_at(0);
       const float4* vp_g = vpB + (size_t)g * nc4 * 32 + lane;
       float tx = 0.f, ty = 0.f, tz = 0.f;
       if (transl != nullptr && g * 32 + lane < nb) {
@@ -301,31 +315,34 @@ lbs_fwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
       }
       const int nrows = min(32, nb - g * 32);
       float* v_g = verts + (size_t)(b0 + g * 32) * V * 3;
-      plan_store<HV>(stash, plan_load<HV>(vmeta, vwts, it0 * HV, lane), lane);
+      issue_plan<HV>(stash, vmeta, vwts, it0 * HV, lane);
       issue_vp_rows<HV>(tiles + lane * SH::HROW, vp_g + (size_t)(it0 * SH::NCH4) * 32);
       cp_async_commit();
       Slots sl;
+      sl.zA.r20 = sl.zA.r21 = sl.zA.r22 = sl.zA.t2 = sl.zB.r20 = sl.zB.r21 = sl.zB.r22 = sl.zB.t2 = mk2(0.f, 0.f);
       int buf = 0;
       __syncwarp();
       mbar_wait(bar, a_phase);
-      for (int t = it0; t < it1; ++t) {
-        const bool more = t + 1 < it1;
+      for (int n = 0;; ++n) {
+        const int t = sb + off_at(n);
+        if (t >= sb + len) break;
+        const int tn = sb + off_at(n + 1);
+        const bool more = tn < sb + len;
         float* tile = tiles + buf * SH::TILE_WORDS;
         float* my_row = tile + lane * SH::HROW;
-        PlanRegs nplan;
-        if (more) {                                                // next item: v_posed into the other buffer
-          nplan = plan_load<HV>(vmeta, vwts, (t + 1) * HV, lane);
-          issue_vp_rows<HV>(tiles + (buf ^ 1) * SH::TILE_WORDS + lane * SH::HROW, vp_g + (size_t)((t + 1) * SH::NCH4) * 32);
+        if (more) {                                                // next item: plan + v_posed into the other buffers
+          issue_plan<HV>(stash + (buf ^ 1) * SH::STASH_WORDS, vmeta, vwts, tn * HV, lane);
+          issue_vp_rows<HV>(tiles + (buf ^ 1) * SH::TILE_WORDS + lane * SH::HROW, vp_g + (size_t)(tn * SH::NCH4) * 32);
         }
         cp_async_commit();
-        cp_async_wait<1>();                                        // this item's rows have landed (own row only)
+        cp_async_wait<1>();                                        // this item's rows and plan words have landed
+        __syncwarp();                                              // (the plan words were copied by lanes 0..HV-1)
         const uint32_t* meta_s = stash + buf * SH::STASH_WORDS;
         const float4* wts_s = reinterpret_cast<const float4*>(meta_s + HV);
 #pragma unroll 1
         for (int u = 0; u < HV / 4; ++u)
-          skin_fwd4(sl, A_s, lane, meta_s + u * 4, wts_s + u * 4, (u == 0 && t == it0) ? (0xFu << 20) : 0u, tx, ty, tz,
+          skin_fwd4(sl, A_s, lane, meta_s + u * 4, wts_s + u * 4, (u == 0 && n % FWD_RUN == 0) ? (0xFu << 20) : 0u, tx, ty, tz,
                     my_row + u * 12);
-        if (more) plan_store<HV>(stash + (buf ^ 1) * SH::STASH_WORDS, nplan, lane);
         __syncwarp();
         // flush: each body row of the item is ROWS contiguous floats of the (B, V, 3) output
         {
@@ -364,12 +381,36 @@ constexpr int BWD_WARP_WORDS = 2 * ItemShape<BWD_HV>::TILE_WORDS + 2 * ItemShape
                                2 * ItemShape<BWD_HV>::STASH_WORDS;
 constexpr size_t BWD_SMEM = (size_t)(AG_WORDS + BWD_WARPS * BWD_WARP_WORDS) * 4 + 16;
 
+// Slot pairs (lo = slots 0 / 2, hi = slots 1 / 3): rotation entries and gradient accumulators as packed pairs, so
+// the per-vertex arithmetic is 54 FFMA2-class instructions instead of 111 scalar ones.
+struct SlotPair {
+  f2 R[9];                   // R[r * 3 + c]
+  f2 D[AELEMS];              // dL/dA accumulators, D[r * 4 + c]
+};
 struct BwdState {
-  float a0[9], a1[9], a2[9], a3[9];                      // rotation parts of the 4 cached transforms
-  float d0[AELEMS], d1[AELEMS], d2[AELEMS], d3[AELEMS];  // their gradient accumulators
-  uint32_t prev;                                         // plan word of the previous vertex (joint ids of the slots)
+  SlotPair A, B;
+  uint32_t prev;             // plan word of the previous vertex (joint ids of the slots)
   float sx, sy, sz;
 };
+// close one slot: its accumulator halves -> fp32 RED into the group's dA rows [joint * 12 + e][32]; clear them
+template <bool HI>
+__device__ __forceinline__ void flush_half(SlotPair& P, float* dA_g, int joint, int lane) {
+  float* p = dA_g + (size_t)joint * AELEMS * 32 + lane;
+#pragma unroll
+  for (int e = 0; e < AELEMS; ++e) {
+    red_add(p + e * 32, get_half<HI>(P.D[e]));
+    P.D[e] = set_half<HI>(P.D[e], 0.f);
+  }
+}
+template <bool HI>
+__device__ __forceinline__ void load_rot_half(SlotPair& P, const float* A_s, int joint, int lane) {
+  const float4* p = reinterpret_cast<const float4*>(A_s) + joint * 96 + lane;
+  const float4 q0 = p[0], q1 = p[32], q2 = p[64];
+  P.R[0] = set_half<HI>(P.R[0], q0.x); P.R[3] = set_half<HI>(P.R[3], q0.y);
+  P.R[1] = set_half<HI>(P.R[1], q0.z); P.R[4] = set_half<HI>(P.R[4], q0.w);
+  P.R[2] = set_half<HI>(P.R[2], q1.x); P.R[5] = set_half<HI>(P.R[5], q1.y);
+  P.R[6] = set_half<HI>(P.R[6], q2.x); P.R[7] = set_half<HI>(P.R[7], q2.y); P.R[8] = set_half<HI>(P.R[8], q2.z);
+}
 
 // 4 vertices: v_posed from the dense buffer, staged dV of the lane's row -> dv_posed written back in place
 // (fp32), accumulators updated
@@ -378,10 +419,7 @@ __device__ __forceinline__ void skin_bwd4(BwdState& s, const float* A_s, float* 
                                           const float4* vp_s, float* row_io) {
   const uint4 m4 = *reinterpret_cast<const uint4*>(meta_s);
   const uint32_t mts[4] = {m4.x | force, m4.y, m4.z, m4.w};
-  float4 ws[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) ws[i] = wts_s[i];
-  float P[12], G[12], q[12];
+  float P[12], G[12];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const float4 v = vp_s[i * 32];
@@ -389,50 +427,57 @@ __device__ __forceinline__ void skin_bwd4(BwdState& s, const float* A_s, float* 
     const float4 h = *reinterpret_cast<const float4*>(row_io + i * 4);
     G[i * 4] = h.x; G[i * 4 + 1] = h.y; G[i * 4 + 2] = h.z; G[i * 4 + 3] = h.w;
   }
+  float4 w = wts_s[0];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t mt = mts[i];
-    const float4 w = ws[i];
+    const float4 wn = wts_s[i < 3 ? i + 1 : 3];            // next vertex's weights, one vertex ahead
     if (mt & (0xFu << 20)) {
       const uint32_t pv = s.prev;
-      if (mt & (1u << 20)) { flush_slot_g(s.d0, dA_g, pv & 31, lane); load_rot(s.a0, A_s, mt & 31, lane); }
-      if (mt & (1u << 21)) { flush_slot_g(s.d1, dA_g, (pv >> 5) & 31, lane); load_rot(s.a1, A_s, (mt >> 5) & 31, lane); }
-      if (mt & (1u << 22)) { flush_slot_g(s.d2, dA_g, (pv >> 10) & 31, lane); load_rot(s.a2, A_s, (mt >> 10) & 31, lane); }
-      if (mt & (1u << 23)) { flush_slot_g(s.d3, dA_g, (pv >> 15) & 31, lane); load_rot(s.a3, A_s, (mt >> 15) & 31, lane); }
+      if (mt & (1u << 20)) { flush_half<false>(s.A, dA_g, pv & 31, lane); load_rot_half<false>(s.A, A_s, mt & 31, lane); }
+      if (mt & (1u << 21)) { flush_half<true>(s.A, dA_g, (pv >> 5) & 31, lane); load_rot_half<true>(s.A, A_s, (mt >> 5) & 31, lane); }
+      if (mt & (1u << 22)) { flush_half<false>(s.B, dA_g, (pv >> 10) & 31, lane); load_rot_half<false>(s.B, A_s, (mt >> 10) & 31, lane); }
+      if (mt & (1u << 23)) { flush_half<true>(s.B, dA_g, (pv >> 15) & 31, lane); load_rot_half<true>(s.B, A_s, (mt >> 15) & 31, lane); }
     }
     s.prev = mt;
-    const float px = P[i * 3], py = P[i * 3 + 1], pz = P[i * 3 + 2];
+    const f2 px = bc2(P[i * 3]), py = bc2(P[i * 3 + 1]), pz = bc2(P[i * 3 + 2]);
     const float gx = G[i * 3], gy = G[i * 3 + 1], gz = G[i * 3 + 2];
     s.sx += gx; s.sy += gy; s.sz += gz;
-    float qx = 0.f, qy = 0.f, qz = 0.f;
-#define B200_SKIN_BWD(a, d, wk)                                                   \
-  {                                                                               \
-    const float hx = wk * gx, hy = wk * gy, hz = wk * gz;                         \
-    qx = fmaf(a[0], hx, fmaf(a[3], hy, fmaf(a[6], hz, qx)));                      \
-    qy = fmaf(a[1], hx, fmaf(a[4], hy, fmaf(a[7], hz, qy)));                      \
-    qz = fmaf(a[2], hx, fmaf(a[5], hy, fmaf(a[8], hz, qz)));                      \
-    d[0] = fmaf(hx, px, d[0]); d[1] = fmaf(hx, py, d[1]); d[2] = fmaf(hx, pz, d[2]); d[3] += hx;    \
-    d[4] = fmaf(hy, px, d[4]); d[5] = fmaf(hy, py, d[5]); d[6] = fmaf(hy, pz, d[6]); d[7] += hy;    \
-    d[8] = fmaf(hz, px, d[8]); d[9] = fmaf(hz, py, d[9]); d[10] = fmaf(hz, pz, d[10]); d[11] += hz; \
-  }
-    B200_SKIN_BWD(s.a0, s.d0, w.x)
-    B200_SKIN_BWD(s.a1, s.d1, w.y)
-    B200_SKIN_BWD(s.a2, s.d2, w.z)
-    B200_SKIN_BWD(s.a3, s.d3, w.w)
-#undef B200_SKIN_BWD
-    q[i * 3] = qx; q[i * 3 + 1] = qy; q[i * 3 + 2] = qz;
+    const f2 wA = mk2(w.x, w.y), wB = mk2(w.z, w.w);
+    const f2 hxA = mul2(wA, bc2(gx)), hyA = mul2(wA, bc2(gy)), hzA = mul2(wA, bc2(gz));
+    const f2 hxB = mul2(wB, bc2(gx)), hyB = mul2(wB, bc2(gy)), hzB = mul2(wB, bc2(gz));
+    // dv_posed = sum_slots R^T h   (pair lanes = slots, summed at the end); written over the consumed dV
+    f2 qx = fma2(s.A.R[0], hxA, fma2(s.A.R[3], hyA, mul2(s.A.R[6], hzA)));
+    f2 qy = fma2(s.A.R[1], hxA, fma2(s.A.R[4], hyA, mul2(s.A.R[7], hzA)));
+    f2 qz = fma2(s.A.R[2], hxA, fma2(s.A.R[5], hyA, mul2(s.A.R[8], hzA)));
+    qx = fma2(s.B.R[0], hxB, fma2(s.B.R[3], hyB, fma2(s.B.R[6], hzB, qx)));
+    qy = fma2(s.B.R[1], hxB, fma2(s.B.R[4], hyB, fma2(s.B.R[7], hzB, qy)));
+    qz = fma2(s.B.R[2], hxB, fma2(s.B.R[5], hyB, fma2(s.B.R[8], hzB, qz)));
+    G[i * 3] = lo2(qx) + hi2(qx); G[i * 3 + 1] = lo2(qy) + hi2(qy); G[i * 3 + 2] = lo2(qz) + hi2(qz);
+    // dA += h (x) [p ; 1]
+#define B200_ACC(P_, hx_, hy_, hz_)                                                                  \
+  P_.D[0] = fma2(hx_, px, P_.D[0]); P_.D[1] = fma2(hx_, py, P_.D[1]); P_.D[2] = fma2(hx_, pz, P_.D[2]);   \
+  P_.D[3] = add2(P_.D[3], hx_);                                                                      \
+  P_.D[4] = fma2(hy_, px, P_.D[4]); P_.D[5] = fma2(hy_, py, P_.D[5]); P_.D[6] = fma2(hy_, pz, P_.D[6]);   \
+  P_.D[7] = add2(P_.D[7], hy_);                                                                      \
+  P_.D[8] = fma2(hz_, px, P_.D[8]); P_.D[9] = fma2(hz_, py, P_.D[9]); P_.D[10] = fma2(hz_, pz, P_.D[10]); \
+  P_.D[11] = add2(P_.D[11], hz_);
+    B200_ACC(s.A, hxA, hyA, hzA)
+    B200_ACC(s.B, hxB, hyB, hzB)
+#undef B200_ACC
+    w = wn;
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i)
-    *reinterpret_cast<float4*>(row_io + i * 4) = make_float4(q[i * 4], q[i * 4 + 1], q[i * 4 + 2], q[i * 4 + 3]);
+    *reinterpret_cast<float4*>(row_io + i * 4) = make_float4(G[i * 4], G[i * 4 + 1], G[i * 4 + 2], G[i * 4 + 3]);
 }
 
 // close the accumulators of the current group: 4 slots -> dA, translation sums -> dtransl
 __device__ __forceinline__ void bwd_close_group(BwdState& s, float* dA_g, float* dtr_g, int lane) {
-  flush_slot_g(s.d0, dA_g, s.prev & 31, lane);
-  flush_slot_g(s.d1, dA_g, (s.prev >> 5) & 31, lane);
-  flush_slot_g(s.d2, dA_g, (s.prev >> 10) & 31, lane);
-  flush_slot_g(s.d3, dA_g, (s.prev >> 15) & 31, lane);
+  flush_half<false>(s.A, dA_g, s.prev & 31, lane);
+  flush_half<true>(s.A, dA_g, (s.prev >> 5) & 31, lane);
+  flush_half<false>(s.B, dA_g, (s.prev >> 10) & 31, lane);
+  flush_half<true>(s.B, dA_g, (s.prev >> 15) & 31, lane);
   red_add(dtr_g + lane, s.sx);
   red_add(dtr_g + 32 + lane, s.sy);
   red_add(dtr_g + 64 + lane, s.sz);
@@ -478,13 +523,15 @@ lbs_bwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
       const float4* vp_g = vpB + (size_t)g * nc4 * 32 + lane;
       const float* dv_g = grad_verts + (size_t)(b0 + g * 32) * V * 3;
       const int nrows = max(0, min(32, nb - g * 32));
-      plan_store<HV>(stash, plan_load<HV>(vmeta, vwts, it0 * HV, lane), lane);
+      issue_plan<HV>(stash, vmeta, vwts, it0 * HV, lane);
       issue_vp_dense<HV>(vbufs, vp_g + (size_t)(it0 * SH::NCH4) * 32, lane);
       if (vec_ok) issue_rows<HV>(tiles, dv_g + (size_t)it0 * HV * 3, row_stride, nrows, max(0, min(HV, V - it0 * HV)) * 3, lane);
       cp_async_commit();
       BwdState st;
 #pragma unroll
-      for (int e = 0; e < AELEMS; ++e) st.d0[e] = st.d1[e] = st.d2[e] = st.d3[e] = 0.f;
+      for (int e = 0; e < AELEMS; ++e) st.A.D[e] = st.B.D[e] = mk2(0.f, 0.f);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) st.A.R[e] = st.B.R[e] = mk2(0.f, 0.f);
       st.prev = 0u;
       st.sx = st.sy = st.sz = 0.f;
       int buf = 0;
@@ -494,9 +541,8 @@ lbs_bwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
         float* tile = tiles + buf * SH::TILE_WORDS;
         float* my_row = tile + lane * SH::HROW;
         const float4* vp_s = vbufs + buf * (SH::NCH4 * 32) + lane;
-        PlanRegs nplan;
         if (more) {
-          nplan = plan_load<HV>(vmeta, vwts, (t + 1) * HV, lane);
+          issue_plan<HV>(stash + (buf ^ 1) * SH::STASH_WORDS, vmeta, vwts, (t + 1) * HV, lane);
           issue_vp_dense<HV>(vbufs + (buf ^ 1) * (SH::NCH4 * 32), vp_g + (size_t)((t + 1) * SH::NCH4) * 32, lane);
           if (vec_ok)
             issue_rows<HV>(tiles + (buf ^ 1) * SH::TILE_WORDS, dv_g + (size_t)(t + 1) * HV * 3, row_stride, nrows,
@@ -514,7 +560,6 @@ lbs_bwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
         for (int u = 0; u < HV / 4; ++u)
           skin_bwd4(st, A_s, dA_g, lane, meta_s + u * 4, wts_s + u * 4, (u == 0 && t == it0) ? (0xFu << 20) : 0u,
                     vp_s + u * 96, my_row + u * 12);
-        if (more) plan_store<HV>(stash + (buf ^ 1) * SH::STASH_WORDS, nplan, lane);
         // ---- the lane's gradient rows -> bf16 hi/lo chunks of dvp (512 contiguous bytes per warp store) ----
         {
           // dvp [S/128][n_pad/8][128][8]: chunk stride 1024 elements, this body at ((g & 3) * 32 + lane) * 8

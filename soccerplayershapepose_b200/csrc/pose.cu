@@ -236,12 +236,15 @@ pose_fwd_kernel(DevModel m, const float* __restrict__ betas, const float* __rest
     __syncwarp();
   }
   __syncthreads();
-  // group-blocked output A_blk[group][joint][row][lane][4] (one contiguous 36 KB block per 32 bodies;
-  // a float4 = one row of [R | t] of one body)
+  // group-blocked output A_blk[group][joint][3][lane] float4 (one contiguous 36 KB block per 32 bodies), the
+  // three float4 of a joint holding (r00 r10 r01 r11) (r02 r12 t0 t1) (r20 r21 r22 t2): x/y rows interleaved
+  // as the operand pairs of the packed-fp32 skinning arithmetic (skin_common.cuh)
   (void)S;
   for (int idx = threadIdx.x; idx < NJ * AELEMS * 32; idx += POSE_THREADS) {
-    const int c = idx & 3, bl = (idx >> 2) & 31, jr = idx >> 7;          // jr = joint * 3 + row
-    A_T[(size_t)blockIdx.x * NJ * AELEMS * 32 + idx] = sOut[(jr * 4 + c) * OUT_PITCH + bl];
+    const int c = idx & 3, bl = (idx >> 2) & 31, jf = idx >> 7;          // jf = joint * 3 + float4 index
+    const int joint = jf / 3, f = jf - joint * 3;
+    const int e = f == 2 ? 8 + c : (f * 2 + (c >> 1)) + 4 * (c & 1);      // row-major [R | t] element
+    A_T[(size_t)blockIdx.x * NJ * AELEMS * 32 + idx] = sOut[(joint * AELEMS + e) * OUT_PITCH + bl];
   }
   // the 24 posed chain joints (+ transl) go straight into joints[:, 0:24] as 288 B row segments
   if (joints != nullptr) {

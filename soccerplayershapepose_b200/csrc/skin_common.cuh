@@ -89,40 +89,60 @@ __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-// ---- transforms: [joint][row r][lane] float4 = row r of [R | t] of that lane's body --------------------
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per instruction) -------------------
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 mk2(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float lo2(f2 v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo;
+}
+__device__ __forceinline__ float hi2(f2 v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return hi;
+}
+__device__ __forceinline__ f2 bc2(float x) { return mk2(x, x); }   // ptxas folds this into the scalar-broadcast operand form
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+template <bool HI>
+__device__ __forceinline__ f2 set_half(f2 v, float x) { return HI ? mk2(lo2(v), x) : mk2(x, hi2(v)); }
+template <bool HI>
+__device__ __forceinline__ float get_half(f2 v) { return HI ? hi2(v) : lo2(v); }
+
+// ---- transforms: [joint][3][lane] float4 = (r00 r10 r01 r11) (r02 r12 t0 t1) (r20 r21 r22 t2) of that lane's body
 // (the same indexing serves the shared-memory copy of one group and the global A_blk + group offset)
-__device__ __forceinline__ void load_slot(float (&a)[AELEMS], const float* A, int joint, int lane) {
-  const float4* p = reinterpret_cast<const float4*>(A) + joint * 96 + lane;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const float4 v = p[r * 32];
-    a[r * 4 + 0] = v.x; a[r * 4 + 1] = v.y; a[r * 4 + 2] = v.z; a[r * 4 + 3] = v.w;
-  }
+__device__ __forceinline__ void unpack_transform(float (&a)[AELEMS], const float4& q0, const float4& q1, const float4& q2) {
+  a[0] = q0.x; a[4] = q0.y; a[1] = q0.z; a[5] = q0.w;
+  a[2] = q1.x; a[6] = q1.y; a[3] = q1.z; a[7] = q1.w;
+  a[8] = q2.x; a[9] = q2.y; a[10] = q2.z; a[11] = q2.w;
 }
-__device__ __forceinline__ void load_rot(float (&a)[9], const float* A, int joint, int lane) {
-  const float4* p = reinterpret_cast<const float4*>(A) + joint * 96 + lane;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const float4 v = p[r * 32];
-    a[r * 3 + 0] = v.x; a[r * 3 + 1] = v.y; a[r * 3 + 2] = v.z;
-  }
-}
-// same, through the read-only path of global memory (L1-allocating: the warps of a CTA share a group)
 __device__ __forceinline__ void load_slot_g(float (&a)[AELEMS], const float4* A_g, int joint, int lane) {
   const float4* p = A_g + joint * 96 + lane;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const float4 v = __ldg(p + r * 32);
-    a[r * 4 + 0] = v.x; a[r * 4 + 1] = v.y; a[r * 4 + 2] = v.z; a[r * 4 + 3] = v.w;
-  }
+  unpack_transform(a, __ldg(p), __ldg(p + 32), __ldg(p + 64));
 }
 __device__ __forceinline__ void load_rot_g(float (&a)[9], const float4* A_g, int joint, int lane) {
   const float4* p = A_g + joint * 96 + lane;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const float4 v = __ldg(p + r * 32);
-    a[r * 3 + 0] = v.x; a[r * 3 + 1] = v.y; a[r * 3 + 2] = v.z;
-  }
+  const float4 q0 = __ldg(p), q1 = __ldg(p + 32), q2 = __ldg(p + 64);
+  a[0] = q0.x; a[3] = q0.y; a[1] = q0.z; a[4] = q0.w; a[2] = q1.x; a[5] = q1.y;
+  a[6] = q2.x; a[7] = q2.y; a[8] = q2.z;
 }
 // add a slot's gradient accumulators into the group's dA rows [joint * 12 + e][32] and clear them
 __device__ __forceinline__ void flush_slot_g(float (&d)[AELEMS], float* dA_g, int joint, int lane) {
