@@ -191,6 +191,7 @@ int b200smpl_model_create(const b200smpl_model_desc* desc, int device, b200smpl_
   UP(W32, h.W32);
   UP(vmeta, h.vmeta);
   UP(vwts, h.vwts);
+  UP(vplan, h.vplan);
   UP(Jt, h.Jt);
   UP(Jsd, h.Jsd);
   UP(term_ptr, h.term_ptr);

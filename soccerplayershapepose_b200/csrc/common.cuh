@@ -95,6 +95,7 @@ struct DevModel {
   const float* W32;            // [1 + nf][n_pad]           fp32 rows: template, shapedirs, posedirs
   const uint32_t* vmeta;       // [ntiles*32]
   const float4* vwts;          // [ntiles*32]
+  const uint32_t* vplan;       // [ntiles*4][40]: per 8 vertices, 8 float4 weights then 8 plan words (one 160 B TMA record)
   const float* Jt;             // [24][3]   J_regressor . v_template
   const float* Jsd;            // [24][3][nb]  J_regressor . shapedirs
   const int32_t* term_ptr;     // [njout-24+1]
@@ -112,6 +113,7 @@ struct HostArrays {
   std::vector<float> W32, Jt, Jsd, term_c;
   std::vector<uint32_t> vmeta;
   std::vector<float> vwts;     // 4 per vertex
+  std::vector<uint32_t> vplan; // 40 words per 8 vertices
   std::vector<int32_t> term_ptr, term_qrow, vt_j0, vt_nj;
   std::vector<uint32_t> qmeta;
   std::vector<float> qcoef;

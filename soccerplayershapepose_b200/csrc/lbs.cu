@@ -8,8 +8,9 @@
 // (re)loaded -- three coalesced 512-byte float4 loads from A_blk, L1/L2 resident -- only where the packed
 // plan says a slot's joint changes (8 times per 32 vertices on the SMPL mesh order).
 //
-// Data movement: v_posed comes from the blend GEMM group-blocked, [S/32][n/4][32][4]: a warp's run is one
-// contiguous stream (512 bytes per float4 and chunk).  The tensors whose layout the
+// Data movement: v_posed comes from the blend GEMM group-blocked, [S/32][n/4][32][4], so the v_posed of an
+// item is one contiguous block that a single TMA bulk copy (cp.async.bulk, completion on a per-warp
+// mbarrier) brings into shared memory together with the item's 160-byte plan records, one item ahead.  The tensors whose layout the
 // caller fixes -- (B, 6890, 3) vertices / vertex gradients -- are transposed through a per-warp
 // shared-memory tile [32 bodies][100]: the lane = body side uses 128-bit accesses on its own row, the
 // global side moves each 384-byte row segment as 8-byte accesses (two rows per three warp
@@ -20,10 +21,6 @@
 
 namespace b200smpl {
 
-// Pipeline: every warp keeps TWO staging buffers and fills the one of item k+1 with cp.async (v_posed: 16
-// bytes per lane and chunk into the lane's own row; vertex gradients: 8-byte pieces of the (B, V, 3) rows,
-// zero-filled outside the batch / mesh) while it works on item k, so a whole item per warp (3-6 KB) is in
-// flight at any time without holding registers.
 template <int HV>
 struct ItemShape {
   static constexpr int ROWS = HV * 3;             // blend rows (floats per body) of one item
@@ -32,20 +29,11 @@ struct ItemShape {
   static constexpr int NCH4 = ROWS / 4;           // float4 chunks of v_posed per body
   static constexpr int NCH8 = ROWS / 8;           // 8-row chunks of dvp per body
   static constexpr int PAIRS = ROWS / 2;          // 8-byte pieces per body row
-  static constexpr int STASH_WORDS = HV * 5;      // plan words of one item: HV metas + HV float4 weights
-  static_assert((HROW / 4) % 2 == 1 && ROWS % 8 == 0, "item shape");
+  static constexpr int VP_WORDS = NCH4 * 128;     // dense v_posed block [NCH4][32] float4
+  static constexpr int PLAN_WORDS = (HV / 8) * 40;  // plan records of one item
+  static constexpr uint32_t TX_BYTES = (VP_WORDS + PLAN_WORDS) * 4;
+  static_assert((HROW / 4) % 2 == 1 && ROWS % 8 == 0 && HV % 8 == 0, "item shape");
 };
-
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8_zfill(void* dst_smem, const void* src, int src_bytes) {
-  asm volatile("cp.async.ca.shared.global.L2::256B [%0], [%1], 8, %2;" ::"r"(smem_addr(dst_smem)), "l"(src), "r"(src_bytes)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // contiguous range of the flat (group, item) list owned by this CTA; it is walked one group at a time
 struct CtaRange {
@@ -59,78 +47,27 @@ __device__ __forceinline__ CtaRange make_cta_range(int ngroups, int nitems) {
   return r;
 }
 
-// plan words of one item (HV metas + HV float4 weights, warp-uniform data): lanes 0..HV-1 copy them into the
-// warp's stash with cp.async, in the same group as the item's data
-__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
-}
+// one lane: v_posed block + plan records of item t -> the warp's buffers, completion counted on `bar`
 template <int HV>
-__device__ __forceinline__ void issue_plan(uint32_t* stash, const uint32_t* __restrict__ vmeta,
-                                           const float4* __restrict__ vwts, int vbase, int lane) {
-  if (lane < HV) {
-    cp_async4(stash + lane, vmeta + vbase + lane);
-    cp_async16(reinterpret_cast<float4*>(stash + HV) + lane, vwts + vbase + lane);
-  }
+__device__ __forceinline__ void issue_item(float4* vbuf, uint32_t* stash, uint64_t* bar, const float4* __restrict__ vp_group,
+                                           const uint32_t* __restrict__ vplan, int t) {
+  using SH = ItemShape<HV>;
+  mbar_expect_tx(bar, SH::TX_BYTES);
+  bulk_g2s(vbuf, vp_group + (size_t)t * (SH::NCH4 * 32), SH::VP_WORDS * 4, bar);
+  bulk_g2s(stash, vplan + (size_t)t * SH::PLAN_WORDS, SH::PLAN_WORDS * 4, bar);
+}
+// plan words of vertices [4u, 4u+4) of the item inside the stash (records of 8 vertices: 8 float4 + 8 words)
+__device__ __forceinline__ const float4* plan_wts(const uint32_t* stash, int u) {
+  return reinterpret_cast<const float4*>(stash + (u >> 1) * 40 + (u & 1) * 16);
+}
+__device__ __forceinline__ const uint32_t* plan_meta(const uint32_t* stash, int u) {
+  return stash + (u >> 1) * 40 + 32 + (u & 1) * 4;
 }
 
-// v_posed of one item: NCH4 float4 per body, straight into the lane's own row (no cross-lane traffic)
-template <int HV>
-__device__ __forceinline__ void issue_vp_rows(float* my_row, const float4* __restrict__ vp_item_lane) {
-#pragma unroll
-  for (int c = 0; c < ItemShape<HV>::NCH4; ++c) cp_async16(my_row + c * 4, vp_item_lane + c * 32);
-}
-// ... or into a dense [chunk][lane] float4 array
-template <int HV>
-__device__ __forceinline__ void issue_vp_dense(float4* vbuf, const float4* __restrict__ vp_item_lane, int lane) {
-#pragma unroll
-  for (int c = 0; c < ItemShape<HV>::NCH4; ++c) cp_async16(vbuf + c * 32 + lane, vp_item_lane + c * 32);
-}
-// 32 row segments of a (B, V, 3) tensor <-> staging tile in 8-byte pieces.  The 32 * PAIRS pieces are taken
-// 32 per warp instruction: piece = k * 32 + lane -> row = piece / PAIRS, column pair = piece % PAIRS.  Since
-// 96 = RPP * PAIRS the (row offset, column) of a lane repeats every 3 instructions, RPP rows further down, so
-// a lane keeps 3 global pointers and adds a constant stride.
-template <int HV>
-__device__ __forceinline__ void issue_rows_full(float* tile, const float* __restrict__ src0, size_t row_stride, int lane) {
-  using SH = ItemShape<HV>;
-  constexpr int RPP = 96 / SH::PAIRS, J = 32 / RPP;
-  const float* gp[3];
-  float* sp[3];
-#pragma unroll
-  for (int kk = 0; kk < 3; ++kk) {
-    const int piece = kk * 32 + lane, rr = piece / SH::PAIRS, c = (piece - rr * SH::PAIRS) * 2;
-    gp[kk] = src0 + (size_t)rr * row_stride + c;
-    sp[kk] = tile + rr * SH::HROW + c;
-  }
-  const size_t step = (size_t)RPP * row_stride;
-#pragma unroll
-  for (int j = 0; j < J; ++j)
-#pragma unroll
-    for (int kk = 0; kk < 3; ++kk) {
-      cp_async8_zfill(sp[kk] + j * RPP * SH::HROW, gp[kk], 8);
-      gp[kk] += step;
-    }
-}
-// general version: zero-filled outside [nrows) x [ncols)
-template <int HV>
-__device__ __forceinline__ void issue_rows(float* tile, const float* __restrict__ src0, size_t row_stride, int nrows,
-                                           int ncols, int lane) {
-  using SH = ItemShape<HV>;
-  if (nrows == 32 && ncols == SH::ROWS) {
-    issue_rows_full<HV>(tile, src0, row_stride, lane);
-    return;
-  }
-#pragma unroll 1
-  for (int k = 0; k < SH::PAIRS; ++k) {
-    const int piece = k * 32 + lane;
-    const int r = piece / SH::PAIRS;
-    const int c = (piece - r * SH::PAIRS) * 2;
-    const bool ok = r < nrows && c < ncols;
-    const int bytes = ok ? (c + 1 < ncols ? 8 : 4) : 0;
-    cp_async8_zfill(tile + r * SH::HROW + c, ok ? src0 + (size_t)r * row_stride + c : src0, bytes);
-  }
-}
-
-// rows of the staging tile -> row segments of a (B, V, 3) tensor (8-byte stores)
+// ---- rows of the staging tile <-> row segments of a (B, V, 3) tensor, in 8-byte pieces.  The 32 * PAIRS pieces
+// are taken 32 per warp instruction: piece = k * 32 + lane -> row = piece / PAIRS, column pair = piece % PAIRS.
+// Since 96 = RPP * PAIRS the (row offset, column) of a lane repeats every 3 instructions, RPP rows further down,
+// so a lane keeps 3 global pointers and adds a constant stride.
 template <int HV>
 __device__ __forceinline__ void tile_to_global_full(const float* tile, float* dst0, size_t row_stride, int lane) {
   using SH = ItemShape<HV>;
@@ -173,6 +110,58 @@ __device__ __forceinline__ void tile_to_global(const float* tile, float* dst0, s
     }
   }
 }
+// gradient rows: global -> registers (issued one item ahead) -> staging tile
+template <int HV>
+struct RowRegs {
+  float2 v[ItemShape<HV>::PAIRS];
+};
+template <int HV>
+__device__ __forceinline__ void rows_load(RowRegs<HV>& R, const float* __restrict__ src0, size_t row_stride, int nrows,
+                                          int ncols, int lane) {
+  using SH = ItemShape<HV>;
+  constexpr int RPP = 96 / SH::PAIRS, J = 32 / RPP;
+  if (nrows == 32 && ncols == SH::ROWS) {
+    const float* gp[3];
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+      const int piece = kk * 32 + lane, rr = piece / SH::PAIRS, c = (piece - rr * SH::PAIRS) * 2;
+      gp[kk] = src0 + (size_t)rr * row_stride + c;
+    }
+    const size_t step = (size_t)RPP * row_stride;
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk) {
+        R.v[j * 3 + kk] = ld_stream2(gp[kk]);
+        gp[kk] += step;
+      }
+  } else {
+#pragma unroll
+    for (int k = 0; k < SH::PAIRS; ++k) {        // same piece order: k = j * 3 + kk
+      const int piece = (k % 3) * 32 + lane, rr = piece / SH::PAIRS, c = (piece - rr * SH::PAIRS) * 2;
+      const int r = (k / 3) * RPP + rr;
+      float2 x = make_float2(0.f, 0.f);
+      if (r < nrows) {
+        const float* src = src0 + (size_t)r * row_stride + c;
+        if (c + 1 < ncols) x = ld_stream2(src);
+        else if (c < ncols) x.x = ld_stream(src);
+      }
+      R.v[k] = x;
+    }
+  }
+}
+template <int HV>
+__device__ __forceinline__ void rows_store(float* tile, const RowRegs<HV>& R, int lane) {
+  using SH = ItemShape<HV>;
+  constexpr int RPP = 96 / SH::PAIRS, J = 32 / RPP;
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk) {
+    const int piece = kk * 32 + lane, rr = piece / SH::PAIRS, c = (piece - rr * SH::PAIRS) * 2;
+    float* sp = tile + rr * SH::HROW + c;
+#pragma unroll
+    for (int j = 0; j < J; ++j) *reinterpret_cast<float2*>(sp + j * RPP * SH::HROW) = R.v[j * 3 + kk];
+  }
+}
 // element-wise fallbacks (odd V or a base pointer that is not 8-byte aligned)
 template <int HV>
 __device__ __forceinline__ void tile_to_global_scalar(const float* tile, float* dst0, size_t row_stride, int nrows,
@@ -195,16 +184,17 @@ __device__ __forceinline__ void global_to_tile_scalar(float* tile, const float* 
 #define B200_FWD_HV 16
 #endif
 #ifndef B200_FWD_WARPS
-#define B200_FWD_WARPS 12
+#define B200_FWD_WARPS 8
 #endif
 #ifndef B200_FWD_RUN
-#define B200_FWD_RUN 2
+#define B200_FWD_RUN 1
 #endif
 constexpr int FWD_RUN = B200_FWD_RUN;       // consecutive items per warp and round (slots persist inside a run)
 constexpr int FWD_HV = B200_FWD_HV;
 constexpr int FWD_WARPS = B200_FWD_WARPS;
 constexpr int FWD_THREADS = FWD_WARPS * 32;
-constexpr int FWD_WARP_WORDS = 2 * ItemShape<FWD_HV>::TILE_WORDS + 2 * ItemShape<FWD_HV>::STASH_WORDS;
+// per warp: output tile | 2 x (v_posed block, plan records) | 2 mbarriers
+constexpr int FWD_WARP_WORDS = ItemShape<FWD_HV>::TILE_WORDS + 2 * (ItemShape<FWD_HV>::VP_WORDS + ItemShape<FWD_HV>::PLAN_WORDS) + 4;
 constexpr size_t FWD_SMEM = (size_t)(AG_WORDS + FWD_WARPS * FWD_WARP_WORDS) * 4 + 16;
 
 // The four cached transforms ("slots") as packed pairs: x/y rows of a slot are (r0c, r1c) pairs, the z rows of
@@ -229,10 +219,10 @@ __device__ __forceinline__ void load_slot2(SlotXY& s, SlotZ2& z, const float* A_
   z.r22 = set_half<HI>(z.r22, q2.z); z.t2 = set_half<HI>(z.t2, q2.w);
 }
 
-// 4 vertices, in place on the lane's own row: v_posed -> skinned coordinates
+// 4 vertices: v_posed from the dense block -> skinned coordinates into the lane's row of the output tile
 __device__ __forceinline__ void skin_fwd4(Slots& s, const float* A_s, int lane, const uint32_t* meta_s,
                                           const float4* wts_s, uint32_t force, float tx, float ty, float tz,
-                                          float* row_io) {
+                                          const float4* vp_s, float* row_out) {
   const uint4 m4 = *reinterpret_cast<const uint4*>(meta_s);
   const uint32_t mts[4] = {m4.x | force, m4.y, m4.z, m4.w};
   float4 ws[4];
@@ -241,7 +231,7 @@ __device__ __forceinline__ void skin_fwd4(Slots& s, const float* A_s, int lane, 
   float P[12], o[12];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const float4 v = *reinterpret_cast<const float4*>(row_io + i * 4);
+    const float4 v = vp_s[i * 32];
     P[i * 4] = v.x; P[i * 4 + 1] = v.y; P[i * 4 + 2] = v.z; P[i * 4 + 3] = v.w;
   }
   const f2 txy = mk2(tx, ty), tz0 = mk2(tz, 0.f);
@@ -269,28 +259,32 @@ __device__ __forceinline__ void skin_fwd4(Slots& s, const float* A_s, int lane, 
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i)
-    *reinterpret_cast<float4*>(row_io + i * 4) = make_float4(o[i * 4], o[i * 4 + 1], o[i * 4 + 2], o[i * 4 + 3]);
+    *reinterpret_cast<float4*>(row_out + i * 4) = make_float4(o[i * 4], o[i * 4 + 1], o[i * 4 + 2], o[i * 4 + 3]);
 }
 
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 lbs_fwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict__ A_blk, int b0, int nb, int ngroups,
                const float* __restrict__ transl, float* __restrict__ verts, int V, int nitems, int vec_ok,
-               const uint32_t* __restrict__ vmeta, const float4* __restrict__ vwts) {
+               const uint32_t* __restrict__ vplan) {
   constexpr int HV = FWD_HV;
   using SH = ItemShape<HV>;
   extern __shared__ __align__(128) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* A_s = smem;                                               // [24][3][32] float4: the group's transforms
   float* wbase = smem + AG_WORDS + warp * FWD_WARP_WORDS;
-  float* tiles = wbase;                                            // [2][32][HROW]
-  uint32_t* stash = reinterpret_cast<uint32_t*>(wbase + 2 * SH::TILE_WORDS);   // [2][STASH_WORDS]
+  float* tile = wbase;                                             // [32][HROW] output staging
+  float4* vbufs = reinterpret_cast<float4*>(wbase + SH::TILE_WORDS);                       // [2][NCH4][32]
+  uint32_t* stash = reinterpret_cast<uint32_t*>(wbase + SH::TILE_WORDS + 2 * SH::VP_WORDS);  // [2][PLAN_WORDS]
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(wbase + SH::TILE_WORDS + 2 * (SH::VP_WORDS + SH::PLAN_WORDS));  // [2]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + AG_WORDS + FWD_WARPS * FWD_WARP_WORDS);
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
+  if (lane == 0) {
+    mbar_init(&wbar[0], 1);
+    mbar_init(&wbar[1], 1);
+    if (warp == 0) mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  uint32_t a_phase = 0;
+  uint32_t a_phase = 0, n_used = 0;                                // n_used: items this warp has pulled so far
   const CtaRange cta = make_cta_range(ngroups, nitems);
   for (int seg0 = cta.begin; seg0 < cta.end;) {
     // ---- one body group at a time per CTA: its 36 KB of transforms come in with one TMA bulk copy ----
@@ -306,8 +300,7 @@ lbs_fwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
     const int sb = seg0 - g * nitems;
     auto off_at = [&](int n) { const int r = n / FWD_RUN; return (r * FWD_WARPS + warp) * FWD_RUN + (n - r * FWD_RUN); };
     if (off_at(0) < len) {
-      const int it0 = sb + off_at(0);
-      const float4* vp_g = vpB + (size_t)g * nc4 * 32 + lane;
+      const float4* vp_g = vpB + (size_t)g * nc4 * 32;
       float tx = 0.f, ty = 0.f, tz = 0.f;
       if (transl != nullptr && g * 32 + lane < nb) {
         const float* tp = transl + (size_t)(b0 + g * 32 + lane) * 3;
@@ -315,34 +308,28 @@ lbs_fwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
       }
       const int nrows = min(32, nb - g * 32);
       float* v_g = verts + (size_t)(b0 + g * 32) * V * 3;
-      issue_plan<HV>(stash, vmeta, vwts, it0 * HV, lane);
-      issue_vp_rows<HV>(tiles + lane * SH::HROW, vp_g + (size_t)(it0 * SH::NCH4) * 32);
-      cp_async_commit();
+      float* my_row = tile + lane * SH::HROW;
+      if (lane == 0) {
+        const uint32_t b = n_used & 1;
+        issue_item<HV>(vbufs + b * (SH::NCH4 * 32), stash + b * SH::PLAN_WORDS, &wbar[b], vp_g, vplan, sb + off_at(0));
+      }
       Slots sl;
       sl.zA.r20 = sl.zA.r21 = sl.zA.r22 = sl.zA.t2 = sl.zB.r20 = sl.zB.r21 = sl.zB.r22 = sl.zB.t2 = mk2(0.f, 0.f);
-      int buf = 0;
-      __syncwarp();
       mbar_wait(bar, a_phase);
       for (int n = 0;; ++n) {
         const int t = sb + off_at(n);
         if (t >= sb + len) break;
         const int tn = sb + off_at(n + 1);
-        const bool more = tn < sb + len;
-        float* tile = tiles + buf * SH::TILE_WORDS;
-        float* my_row = tile + lane * SH::HROW;
-        if (more) {                                                // next item: plan + v_posed into the other buffers
-          issue_plan<HV>(stash + (buf ^ 1) * SH::STASH_WORDS, vmeta, vwts, tn * HV, lane);
-          issue_vp_rows<HV>(tiles + (buf ^ 1) * SH::TILE_WORDS + lane * SH::HROW, vp_g + (size_t)(tn * SH::NCH4) * 32);
-        }
-        cp_async_commit();
-        cp_async_wait<1>();                                        // this item's rows and plan words have landed
-        __syncwarp();                                              // (the plan words were copied by lanes 0..HV-1)
-        const uint32_t* meta_s = stash + buf * SH::STASH_WORDS;
-        const float4* wts_s = reinterpret_cast<const float4*>(meta_s + HV);
+        const uint32_t b = n_used & 1;
+        if (tn < sb + len && lane == 0)                            // next item into the other buffers
+          issue_item<HV>(vbufs + (b ^ 1) * (SH::NCH4 * 32), stash + (b ^ 1) * SH::PLAN_WORDS, &wbar[b ^ 1], vp_g, vplan, tn);
+        mbar_wait(&wbar[b], (n_used >> 1) & 1);                    // this item's v_posed and plan have landed
+        const float4* vp_s = vbufs + b * (SH::NCH4 * 32) + lane;
+        const uint32_t* st = stash + b * SH::PLAN_WORDS;
 #pragma unroll 1
         for (int u = 0; u < HV / 4; ++u)
-          skin_fwd4(sl, A_s, lane, meta_s + u * 4, wts_s + u * 4, (u == 0 && n % FWD_RUN == 0) ? (0xFu << 20) : 0u, tx, ty, tz,
-                    my_row + u * 12);
+          skin_fwd4(sl, A_s, lane, plan_meta(st, u), plan_wts(st, u), (u == 0 && n % FWD_RUN == 0) ? (0xFu << 20) : 0u,
+                    tx, ty, tz, vp_s + u * 96, my_row + u * 12);
         __syncwarp();
         // flush: each body row of the item is ROWS contiguous floats of the (B, V, 3) output
         {
@@ -352,8 +339,8 @@ lbs_fwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
           if (!vec_ok) tile_to_global_scalar<HV>(tile, dst0, (size_t)V * 3, nrows, ncols, lane);
           else tile_to_global<HV>(tile, dst0, (size_t)V * 3, nrows, ncols, lane);
         }
-        __syncwarp();                                              // rows are re-filled two items later
-        buf ^= 1;
+        __syncwarp();                                              // tile and buffer b are free again
+        ++n_used;
       }
     }
     seg0 = seg1;
@@ -367,18 +354,19 @@ lbs_fwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
 //   dv_posed = sum_s w_s R_s^T dV            -> bf16 hi (+lo) chunks of dvp (GEMM operand)
 //   dA_j    += w_s [dV (x) p | dV]           -> per-slot register accumulators -> fp32 RED into dA_acc
 //   dtransl += dV                            -> fp32 RED into dtr_acc
+// The gradient rows are 8-byte aligned only (no TMA): they are loaded into registers one item ahead and
+// dropped into the staging tile when the previous item has been packed.
 // ---------------------------------------------------------------------------------------------
 #ifndef B200_BWD_HV
 #define B200_BWD_HV 8
 #endif
 #ifndef B200_BWD_WARPS
-#define B200_BWD_WARPS 12
+#define B200_BWD_WARPS 8
 #endif
 constexpr int BWD_HV = B200_BWD_HV;
 constexpr int BWD_WARPS = B200_BWD_WARPS;
 constexpr int BWD_THREADS = BWD_WARPS * 32;
-constexpr int BWD_WARP_WORDS = 2 * ItemShape<BWD_HV>::TILE_WORDS + 2 * ItemShape<BWD_HV>::NCH4 * 128 +
-                               2 * ItemShape<BWD_HV>::STASH_WORDS;
+constexpr int BWD_WARP_WORDS = ItemShape<BWD_HV>::TILE_WORDS + 2 * (ItemShape<BWD_HV>::VP_WORDS + ItemShape<BWD_HV>::PLAN_WORDS) + 4;
 constexpr size_t BWD_SMEM = (size_t)(AG_WORDS + BWD_WARPS * BWD_WARP_WORDS) * 4 + 16;
 
 // Slot pairs (lo = slots 0 / 2, hi = slots 1 / 3): rotation entries and gradient accumulators as packed pairs, so
@@ -487,7 +475,7 @@ __device__ __forceinline__ void bwd_close_group(BwdState& s, float* dA_g, float*
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 lbs_bwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict__ A_blk, int b0, int nb, int ngroups,
                const float* __restrict__ grad_verts, int V, int nitems, int vec_ok,
-               const uint32_t* __restrict__ vmeta, const float4* __restrict__ vwts,
+               const uint32_t* __restrict__ vplan,
                __nv_bfloat16* __restrict__ dvp_hi, __nv_bfloat16* __restrict__ dvp_lo,
                float* __restrict__ dA_acc, float* __restrict__ dtr_acc) {
   constexpr int HV = BWD_HV;
@@ -496,16 +484,19 @@ lbs_bwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* A_s = smem;                                                           // the group's transforms
   float* wbase = smem + AG_WORDS + warp * BWD_WARP_WORDS;
-  float* tiles = wbase;                                                        // [2][32][HROW]   dV in / dv_posed out
-  float4* vbufs = reinterpret_cast<float4*>(wbase + 2 * SH::TILE_WORDS);       // [2][NCH4][32]   v_posed
-  uint32_t* stash = reinterpret_cast<uint32_t*>(wbase + 2 * SH::TILE_WORDS + 2 * SH::NCH4 * 128);
+  float* tile = wbase;                                                         // [32][HROW]   dV in / dv_posed out
+  float4* vbufs = reinterpret_cast<float4*>(wbase + SH::TILE_WORDS);           // [2][NCH4][32]   v_posed
+  uint32_t* stash = reinterpret_cast<uint32_t*>(wbase + SH::TILE_WORDS + 2 * SH::VP_WORDS);
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(wbase + SH::TILE_WORDS + 2 * (SH::VP_WORDS + SH::PLAN_WORDS));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + AG_WORDS + BWD_WARPS * BWD_WARP_WORDS);
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
+  if (lane == 0) {
+    mbar_init(&wbar[0], 1);
+    mbar_init(&wbar[1], 1);
+    if (warp == 0) mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  uint32_t a_phase = 0;
+  uint32_t a_phase = 0, n_used = 0;
   const size_t row_stride = (size_t)V * 3;
   const CtaRange cta = make_cta_range(ngroups, nitems);
   for (int seg0 = cta.begin; seg0 < cta.end;) {
@@ -516,17 +507,25 @@ lbs_bwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
     }
     const int seg1 = min(cta.end, (g + 1) * nitems);
     const int len = seg1 - seg0;
-    const int it0 = seg0 - g * nitems + len * warp / BWD_WARPS;
+    const int it0 = seg0 - g * nitems + len * warp / BWD_WARPS;               // this warp's contiguous items
     const int it1 = seg0 - g * nitems + len * (warp + 1) / BWD_WARPS;
     if (it0 < it1) {
       float* dA_g = dA_acc + (size_t)g * AG_WORDS;
-      const float4* vp_g = vpB + (size_t)g * nc4 * 32 + lane;
+      const float4* vp_g = vpB + (size_t)g * nc4 * 32;
       const float* dv_g = grad_verts + (size_t)(b0 + g * 32) * V * 3;
       const int nrows = max(0, min(32, nb - g * 32));
-      issue_plan<HV>(stash, vmeta, vwts, it0 * HV, lane);
-      issue_vp_dense<HV>(vbufs, vp_g + (size_t)(it0 * SH::NCH4) * 32, lane);
-      if (vec_ok) issue_rows<HV>(tiles, dv_g + (size_t)it0 * HV * 3, row_stride, nrows, max(0, min(HV, V - it0 * HV)) * 3, lane);
-      cp_async_commit();
+      float* my_row = tile + lane * SH::HROW;
+      if (lane == 0) {
+        const uint32_t b = n_used & 1;
+        issue_item<HV>(vbufs + b * (SH::NCH4 * 32), stash + b * SH::PLAN_WORDS, &wbar[b], vp_g, vplan, it0);
+      }
+      RowRegs<HV> R;
+      if (vec_ok) {
+        rows_load<HV>(R, dv_g + (size_t)it0 * HV * 3, row_stride, nrows, max(0, min(HV, V - it0 * HV)) * 3, lane);
+        rows_store<HV>(tile, R, lane);
+      } else {
+        global_to_tile_scalar<HV>(tile, dv_g + (size_t)it0 * HV * 3, row_stride, nrows, max(0, min(HV, V - it0 * HV)) * 3, lane);
+      }
       BwdState st;
 #pragma unroll
       for (int e = 0; e < AELEMS; ++e) st.A.D[e] = st.B.D[e] = mk2(0.f, 0.f);
@@ -534,31 +533,24 @@ lbs_bwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
       for (int e = 0; e < 9; ++e) st.A.R[e] = st.B.R[e] = mk2(0.f, 0.f);
       st.prev = 0u;
       st.sx = st.sy = st.sz = 0.f;
-      int buf = 0;
+      __syncwarp();
       mbar_wait(bar, a_phase);
       for (int t = it0; t < it1; ++t) {
         const bool more = t + 1 < it1;
-        float* tile = tiles + buf * SH::TILE_WORDS;
-        float* my_row = tile + lane * SH::HROW;
-        const float4* vp_s = vbufs + buf * (SH::NCH4 * 32) + lane;
-        if (more) {
-          issue_plan<HV>(stash + (buf ^ 1) * SH::STASH_WORDS, vmeta, vwts, (t + 1) * HV, lane);
-          issue_vp_dense<HV>(vbufs + (buf ^ 1) * (SH::NCH4 * 32), vp_g + (size_t)((t + 1) * SH::NCH4) * 32, lane);
+        const uint32_t b = n_used & 1;
+        if (more) {                                               // next item: TMA for v_posed + plan, registers for dV
+          if (lane == 0)
+            issue_item<HV>(vbufs + (b ^ 1) * (SH::NCH4 * 32), stash + (b ^ 1) * SH::PLAN_WORDS, &wbar[b ^ 1], vp_g, vplan, t + 1);
           if (vec_ok)
-            issue_rows<HV>(tiles + (buf ^ 1) * SH::TILE_WORDS, dv_g + (size_t)(t + 1) * HV * 3, row_stride, nrows,
-                           max(0, min(HV, V - (t + 1) * HV)) * 3, lane);
+            rows_load<HV>(R, dv_g + (size_t)(t + 1) * HV * 3, row_stride, nrows, max(0, min(HV, V - (t + 1) * HV)) * 3, lane);
         }
-        cp_async_commit();
-        cp_async_wait<1>();
-        if (!vec_ok)
-          global_to_tile_scalar<HV>(tile, dv_g + (size_t)t * HV * 3, row_stride, nrows, max(0, min(HV, V - t * HV)) * 3, lane);
-        __syncwarp();                                              // the dV rows were written by other lanes
-        const uint32_t* meta_s = stash + buf * SH::STASH_WORDS;
-        const float4* wts_s = reinterpret_cast<const float4*>(meta_s + HV);
+        mbar_wait(&wbar[b], (n_used >> 1) & 1);
+        const float4* vp_s = vbufs + b * (SH::NCH4 * 32) + lane;
+        const uint32_t* ps = stash + b * SH::PLAN_WORDS;
         // the first vertex of the run (re)loads all four slots; the accumulators are zero there
 #pragma unroll 1
         for (int u = 0; u < HV / 4; ++u)
-          skin_bwd4(st, A_s, dA_g, lane, meta_s + u * 4, wts_s + u * 4, (u == 0 && t == it0) ? (0xFu << 20) : 0u,
+          skin_bwd4(st, A_s, dA_g, lane, plan_meta(ps, u), plan_wts(ps, u), (u == 0 && t == it0) ? (0xFu << 20) : 0u,
                     vp_s + u * 96, my_row + u * 12);
         // ---- the lane's gradient rows -> bf16 hi/lo chunks of dvp (512 contiguous bytes per warp store) ----
         {
@@ -572,8 +564,14 @@ lbs_bwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
             store_dvp_chunk(ch, dvp_hi + o0 + c * 1024, dvp_lo ? dvp_lo + o0 + c * 1024 : nullptr);
           }
         }
-        __syncwarp();                                              // buffers are re-filled two items later
-        buf ^= 1;
+        __syncwarp();                                              // every lane is done with its row of the tile
+        if (more) {
+          if (vec_ok) rows_store<HV>(tile, R, lane);
+          else global_to_tile_scalar<HV>(tile, dv_g + (size_t)(t + 1) * HV * 3, row_stride, nrows,
+                                         max(0, min(HV, V - (t + 1) * HV)) * 3, lane);
+        }
+        __syncwarp();                                              // the next item's rows were written by other lanes
+        ++n_used;
       }
       bwd_close_group(st, dA_g, dtr_acc + (size_t)g * 96, lane);
     }
@@ -599,7 +597,7 @@ int launch_lbs_fwd(const DevModel& m, const float* vpB, int S, const float* A_bl
   LaunchTimer _timer("lbs_fwd", st);
   lbs_fwd_kernel<<<run_grid(groups, nitems, FWD_WARPS, num_sms), FWD_THREADS, FWD_SMEM, st>>>(
       reinterpret_cast<const float4*>(vpB), m.n_pad / 4, reinterpret_cast<const float4*>(A_blk), b0, nb, groups, transl, verts,
-      m.V, nitems, vec_ok, m.vmeta, m.vwts);
+      m.V, nitems, vec_ok, m.vplan);
   B200_LAUNCH_CHECK("lbs_fwd");
   return 0;
 }
@@ -616,7 +614,7 @@ int launch_lbs_bwd(const DevModel& m, const float* vpB, int S, int Sw, const flo
   LaunchTimer _timer("lbs_bwd", st);
   lbs_bwd_kernel<<<run_grid(groups, nitems, BWD_WARPS, num_sms), BWD_THREADS, BWD_SMEM, st>>>(
       reinterpret_cast<const float4*>(vpB), m.n_pad / 4, reinterpret_cast<const float4*>(A_blk), b0, nb, groups, grad_verts, m.V,
-      nitems, vec_ok, m.vmeta, m.vwts, dvp_hi, dvp_lo, dA_acc, dtr_acc);
+      nitems, vec_ok, m.vplan, dvp_hi, dvp_lo, dA_acc, dtr_acc);
   B200_LAUNCH_CHECK("lbs_bwd");
   return 0;
 }

@@ -284,6 +284,15 @@ int pack_model(const b200smpl_model_desc* d, HostArrays& h, DevModel& dm, std::s
     }
   }
 
+  // the same plan as 160-byte records of 8 vertices (8 float4 weights, then 8 plan words): what the skinning
+  // kernels pull with one bulk copy per item
+  h.vplan.assign((size_t)ntiles * (TILE_V / 8) * 40, 0u);
+  for (int v = 0; v < ntiles * TILE_V; ++v) {
+    uint32_t* rec = h.vplan.data() + (size_t)(v / 8) * 40;
+    memcpy(rec + (v % 8) * 4, &h.vwts[(size_t)v * 4], 16);
+    rec[32 + v % 8] = h.vmeta[v];
+  }
+
   // ---- joint terms, flattened ----
   h.term_ptr.assign(nvj + nreg + 1, 0);
   h.term_joint.clear(); h.term_qrow.clear(); h.term_c.clear();
