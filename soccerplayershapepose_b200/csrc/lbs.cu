@@ -162,6 +162,48 @@ __device__ __forceinline__ void rows_store(float* tile, const RowRegs<HV>& R, in
     for (int j = 0; j < J; ++j) *reinterpret_cast<float2*>(sp + j * RPP * SH::HROW) = R.v[j * 3 + kk];
   }
 }
+// gradient rows: global -> staging tile with 8-byte cp.async (fully asynchronous, no registers held)
+__device__ __forceinline__ void cp_async8_zfill(void* dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global.L2::256B [%0], [%1], 8, %2;" ::"r"(smem_addr(dst_smem)), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <int HV>
+__device__ __forceinline__ void issue_rows(float* tile, const float* __restrict__ src0, size_t row_stride, int nrows,
+                                           int ncols, int lane) {
+  using SH = ItemShape<HV>;
+  constexpr int RPP = 96 / SH::PAIRS, J = 32 / RPP;
+  if (nrows == 32 && ncols == SH::ROWS) {
+    const float* gp[3];
+    float* sp[3];
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+      const int piece = kk * 32 + lane, rr = piece / SH::PAIRS, c = (piece - rr * SH::PAIRS) * 2;
+      gp[kk] = src0 + (size_t)rr * row_stride + c;
+      sp[kk] = tile + rr * SH::HROW + c;
+    }
+    const size_t step = (size_t)RPP * row_stride;
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk) {
+        cp_async8_zfill(sp[kk] + j * RPP * SH::HROW, gp[kk], 8);
+        gp[kk] += step;
+      }
+    return;
+  }
+#pragma unroll 1
+  for (int k = 0; k < SH::PAIRS; ++k) {
+    const int piece = k * 32 + lane;
+    const int r = piece / SH::PAIRS;
+    const int c = (piece - r * SH::PAIRS) * 2;
+    const bool ok = r < nrows && c < ncols;
+    const int bytes = ok ? (c + 1 < ncols ? 8 : 4) : 0;
+    cp_async8_zfill(tile + r * SH::HROW + c, ok ? src0 + (size_t)r * row_stride + c : src0, bytes);
+  }
+}
 // element-wise fallbacks (odd V or a base pointer that is not 8-byte aligned)
 template <int HV>
 __device__ __forceinline__ void tile_to_global_scalar(const float* tile, float* dst0, size_t row_stride, int nrows,
@@ -366,7 +408,11 @@ lbs_fwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
 constexpr int BWD_HV = B200_BWD_HV;
 constexpr int BWD_WARPS = B200_BWD_WARPS;
 constexpr int BWD_THREADS = BWD_WARPS * 32;
-constexpr int BWD_WARP_WORDS = ItemShape<BWD_HV>::TILE_WORDS + 2 * (ItemShape<BWD_HV>::VP_WORDS + ItemShape<BWD_HV>::PLAN_WORDS) + 4;
+#ifndef B200_BWD_ASYNC_ROWS
+#define B200_BWD_ASYNC_ROWS 1          // 1: dV rows via cp.async into a double-buffered tile; 0: via registers
+#endif
+constexpr int BWD_NTILE = B200_BWD_ASYNC_ROWS ? 2 : 1;
+constexpr int BWD_WARP_WORDS = BWD_NTILE * ItemShape<BWD_HV>::TILE_WORDS + 2 * (ItemShape<BWD_HV>::VP_WORDS + ItemShape<BWD_HV>::PLAN_WORDS) + 4;
 constexpr size_t BWD_SMEM = (size_t)(AG_WORDS + BWD_WARPS * BWD_WARP_WORDS) * 4 + 16;
 
 // Slot pairs (lo = slots 0 / 2, hi = slots 1 / 3): rotation entries and gradient accumulators as packed pairs, so
@@ -484,10 +530,10 @@ lbs_bwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* A_s = smem;                                                           // the group's transforms
   float* wbase = smem + AG_WORDS + warp * BWD_WARP_WORDS;
-  float* tile = wbase;                                                         // [32][HROW]   dV in / dv_posed out
-  float4* vbufs = reinterpret_cast<float4*>(wbase + SH::TILE_WORDS);           // [2][NCH4][32]   v_posed
-  uint32_t* stash = reinterpret_cast<uint32_t*>(wbase + SH::TILE_WORDS + 2 * SH::VP_WORDS);
-  uint64_t* wbar = reinterpret_cast<uint64_t*>(wbase + SH::TILE_WORDS + 2 * (SH::VP_WORDS + SH::PLAN_WORDS));
+  float* tiles = wbase;                                                        // [BWD_NTILE][32][HROW]   dV in / dv_posed out
+  float4* vbufs = reinterpret_cast<float4*>(wbase + BWD_NTILE * SH::TILE_WORDS);  // [2][NCH4][32]   v_posed
+  uint32_t* stash = reinterpret_cast<uint32_t*>(wbase + BWD_NTILE * SH::TILE_WORDS + 2 * SH::VP_WORDS);
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(wbase + BWD_NTILE * SH::TILE_WORDS + 2 * (SH::VP_WORDS + SH::PLAN_WORDS));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + AG_WORDS + BWD_WARPS * BWD_WARP_WORDS);
   if (lane == 0) {
     mbar_init(&wbar[0], 1);
@@ -514,18 +560,25 @@ lbs_bwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
       const float4* vp_g = vpB + (size_t)g * nc4 * 32;
       const float* dv_g = grad_verts + (size_t)(b0 + g * 32) * V * 3;
       const int nrows = max(0, min(32, nb - g * 32));
-      float* my_row = tile + lane * SH::HROW;
       if (lane == 0) {
         const uint32_t b = n_used & 1;
         issue_item<HV>(vbufs + b * (SH::NCH4 * 32), stash + b * SH::PLAN_WORDS, &wbar[b], vp_g, vplan, it0);
       }
+      // first item's gradient rows
+#if B200_BWD_ASYNC_ROWS
+      int tb = 0;
+      if (vec_ok) issue_rows<HV>(tiles, dv_g + (size_t)it0 * HV * 3, row_stride, nrows, max(0, min(HV, V - it0 * HV)) * 3, lane);
+      cp_async_commit();
+#else
+      constexpr int tb = 0;
       RowRegs<HV> R;
       if (vec_ok) {
         rows_load<HV>(R, dv_g + (size_t)it0 * HV * 3, row_stride, nrows, max(0, min(HV, V - it0 * HV)) * 3, lane);
-        rows_store<HV>(tile, R, lane);
-      } else {
-        global_to_tile_scalar<HV>(tile, dv_g + (size_t)it0 * HV * 3, row_stride, nrows, max(0, min(HV, V - it0 * HV)) * 3, lane);
+        rows_store<HV>(tiles, R, lane);
       }
+#endif
+      if (!vec_ok)
+        global_to_tile_scalar<HV>(tiles, dv_g + (size_t)it0 * HV * 3, row_stride, nrows, max(0, min(HV, V - it0 * HV)) * 3, lane);
       BwdState st;
 #pragma unroll
       for (int e = 0; e < AELEMS; ++e) st.A.D[e] = st.B.D[e] = mk2(0.f, 0.f);
@@ -538,12 +591,25 @@ lbs_bwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
       for (int t = it0; t < it1; ++t) {
         const bool more = t + 1 < it1;
         const uint32_t b = n_used & 1;
-        if (more) {                                               // next item: TMA for v_posed + plan, registers for dV
+        float* tile = tiles + tb * SH::TILE_WORDS;
+        float* my_row = tile + lane * SH::HROW;
+        if (more) {                                               // next item: TMA for v_posed + plan, dV rows
           if (lane == 0)
             issue_item<HV>(vbufs + (b ^ 1) * (SH::NCH4 * 32), stash + (b ^ 1) * SH::PLAN_WORDS, &wbar[b ^ 1], vp_g, vplan, t + 1);
+#if B200_BWD_ASYNC_ROWS
+          if (vec_ok)
+            issue_rows<HV>(tiles + (tb ^ 1) * SH::TILE_WORDS, dv_g + (size_t)(t + 1) * HV * 3, row_stride, nrows,
+                           max(0, min(HV, V - (t + 1) * HV)) * 3, lane);
+#else
           if (vec_ok)
             rows_load<HV>(R, dv_g + (size_t)(t + 1) * HV * 3, row_stride, nrows, max(0, min(HV, V - (t + 1) * HV)) * 3, lane);
+#endif
         }
+#if B200_BWD_ASYNC_ROWS
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();                                              // this item's dV rows were copied by other lanes
+#endif
         mbar_wait(&wbar[b], (n_used >> 1) & 1);
         const float4* vp_s = vbufs + b * (SH::NCH4 * 32) + lane;
         const uint32_t* ps = stash + b * SH::PLAN_WORDS;
@@ -565,11 +631,18 @@ lbs_bwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
           }
         }
         __syncwarp();                                              // every lane is done with its row of the tile
+#if B200_BWD_ASYNC_ROWS
+        if (more && !vec_ok)
+          global_to_tile_scalar<HV>(tiles + (tb ^ 1) * SH::TILE_WORDS, dv_g + (size_t)(t + 1) * HV * 3, row_stride, nrows,
+                                    max(0, min(HV, V - (t + 1) * HV)) * 3, lane);
+        tb ^= 1;
+#else
         if (more) {
           if (vec_ok) rows_store<HV>(tile, R, lane);
           else global_to_tile_scalar<HV>(tile, dv_g + (size_t)(t + 1) * HV * 3, row_stride, nrows,
                                          max(0, min(HV, V - (t + 1) * HV)) * 3, lane);
         }
+#endif
         __syncwarp();                                              // the next item's rows were written by other lanes
         ++n_used;
       }
