@@ -34,23 +34,21 @@ struct ChainTables {
   int32_t maxdepth;
 };
 
-// Feature (K) layout of the packed blend operand, in elements.  One body's feature row is
-//   [1,1,1 | b_hi b_lo b_hi | pf_hi | (pad to k_bf16) | pf_lo | pf_hi | pad]
-// and the matching model rows hold
-//   [t_hi t_lo t_lo2 | S_hi S_hi S_lo | P_hi | 0 | P_hi | P_lo | 0]
-// so the first k_bf16x2 columns are the "bf16 mode" product (template + shape terms error-
-// compensated; pose-corrective term = (pf_hi + pf_lo) * P_hi, i.e. bf16 model operand, 16-bit
-// features) and all k_fp32 columns give the bf16x3 split product (~2^-16 relative, fp32 accumulate).
+// K layout of the two forward blend operands (elements; 64-element slabs = one 128-byte swizzle row each).
+//   feature row of a body:  [1 1 1 | b_hi b_lo b_hi | 0.. ]  [pf_hi (207) | 0..]  [pf_lo (207) | 0..]
+//   model row n:            [t_hi t_lo t_lo2 | S_hi S_hi S_lo | 0..]  [P_hi (207) | 0..]  [P_lo (207) | 0..]
+// Slab 0 pairs position by position (template exact 3-way split, shape terms error-compensated).  The pose
+// segments are multiplied crosswise by the kernel: pf_hi x P_hi + pf_lo x P_hi ("bf16 mode": bf16 model operand,
+// 16-bit features) + pf_hi x P_lo ("fp32 mode": bf16x3 split, ~2^-16 relative, fp32 accumulate) -- each operand
+// segment is stored and streamed once and used by two of the three products.
 struct FeatLayout {
   int nb;       // betas
-  int off_s0, off_s1, off_s2;   // 3, 3+nb, 3+2nb
-  int off_p0;   // 3+3nb
-  int k_bf16;   // roundup16(off_p0 + 207)
-  int k_bf16x2; // roundup16(off_p1 + 207): K extent of the bf16 mode (adds the pf_lo * P_hi segment)
-  int off_p1;   // k_bf16
-  int off_p2;   // k_bf16 + 207
-  int k_fp32;   // roundup16(off_p2 + 207)
-  int pitch;    // = k_fp32 (elements; *2 bytes is a multiple of 16)
+  int off_s0, off_s1, off_s2;   // 3, 3+nb, 3+2nb  (inside slab 0)
+  int k_cs;     // used extent of slab 0 = 3 + 3 nb
+  int pseg;     // elements per pose segment = roundup64(207)
+  int off_p0;   // 64: first pose segment  (features: pf_hi, model: P_hi)
+  int off_p1;   // 64 + pseg: second       (features: pf_lo, model: P_lo)
+  int pitch;    // 64 + 2 pseg (elements; *2 bytes is a multiple of 128)
   int nf;       // nb + 207 gradient features
   int nf_pad;   // roundup16(nf)
 };
@@ -63,13 +61,11 @@ inline FeatLayout make_feat_layout(int nb) {
   L.off_s0 = 3;
   L.off_s1 = 3 + nb;
   L.off_s2 = 3 + 2 * nb;
-  L.off_p0 = 3 + 3 * nb;
-  L.k_bf16 = round_up(L.off_p0 + NPOSE, 16);
-  L.off_p1 = L.k_bf16;
-  L.off_p2 = L.k_bf16 + NPOSE;
-  L.k_bf16x2 = round_up(L.off_p1 + NPOSE, 16);
-  L.k_fp32 = round_up(L.off_p2 + NPOSE, 16);
-  L.pitch = L.k_fp32;
+  L.k_cs = 3 + 3 * nb;          // <= 51 for nb <= 16
+  L.pseg = round_up(NPOSE, 64);
+  L.off_p0 = 64;
+  L.off_p1 = 64 + L.pseg;
+  L.pitch = 64 + 2 * L.pseg;
   L.nf = nb + NPOSE;
   L.nf_pad = round_up(L.nf, 16);
   return L;

@@ -209,9 +209,9 @@ int pack_model(const b200smpl_model_desc* d, HostArrays& h, DevModel& dm, std::s
       const __nv_bfloat16 hi = h_bf16(x), lo = h_bf16(x - h_f32(hi));
       if (f < nb) {   // features: [b_hi | b_lo | b_hi]  x  rows: [S_hi | S_hi | S_lo]
         wr[fl.off_s0 + f] = hi; wr[fl.off_s1 + f] = hi; wr[fl.off_s2 + f] = lo;
-      } else {        // features: [pf_hi | pf_lo | pf_hi]  x  rows: [P_hi | P_hi | P_lo]
+      } else {        // pose segments [P_hi | P_lo]; the kernel forms pf_hi.P_hi + pf_lo.P_hi + pf_hi.P_lo
         const int p = f - nb;
-        wr[fl.off_p0 + p] = hi; wr[fl.off_p1 + p] = hi; wr[fl.off_p2 + p] = lo;
+        wr[fl.off_p0 + p] = hi; wr[fl.off_p1 + p] = lo;
       }
       h.Wb_hi[(size_t)f * n_pad + n] = hi;
       h.Wb_lo[(size_t)f * n_pad + n] = lo;

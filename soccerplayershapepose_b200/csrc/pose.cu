@@ -222,7 +222,6 @@ pose_fwd_kernel(DevModel m, const float* __restrict__ betas, const float* __rest
           const __nv_bfloat16 h = bf_hi(pf), l = bf_lo(pf, h);
           sF[fl.off_p0 + idx] = h;
           sF[fl.off_p1 + idx] = l;
-          sF[fl.off_p2 + idx] = h;
           if (featf != nullptr) featf[(size_t)sc * fl.nf_pad + fl.nb + idx] = pf;
         }
       }

@@ -179,7 +179,7 @@ def test_bf16_split_operand(host_engine):
     Wf = _bf16_to_f32(eng.debug_array("Wf", np.uint16)).reshape(n_pad, pitch).astype(np.float64)
     Wb_hi = _bf16_to_f32(eng.debug_array("Wb_hi", np.uint16)).reshape(-1, n_pad)
     Wb_lo = _bf16_to_f32(eng.debug_array("Wb_lo", np.uint16)).reshape(-1, n_pad)
-    assert pitch == 656 and Wb_hi.shape[0] == 224
+    assert pitch == 576 and Wb_hi.shape[0] == 224
     # template: exact 3-way split
     np.testing.assert_array_equal((Wf[:, 0] + Wf[:, 1] + Wf[:, 2]).astype(np.float32), W32[0])
     rng = np.random.default_rng(0)
@@ -188,16 +188,19 @@ def test_bf16_split_operand(host_engine):
     x = np.concatenate([beta, pf])
     hi = _bf16_to_f32(_f32_to_bf16_rn(x))
     lo = _bf16_to_f32(_f32_to_bf16_rn(x - hi))
+    # feature row as pose.cu writes it: slab 0 = [1 1 1 | b_hi b_lo b_hi], then the pf_hi and pf_lo segments
     feat = np.zeros(pitch)
     feat[0:3] = 1.0
     feat[3:13], feat[13:23], feat[23:33] = hi[:10], lo[:10], hi[:10]
-    feat[33:240], feat[240:447], feat[447:654] = hi[10:], lo[10:], hi[10:]
+    feat[64:271], feat[320:527] = hi[10:], lo[10:]
     exact = W32[0].astype(np.float64) + x.astype(np.float64) @ W32[1:].astype(np.float64)
-    split = Wf @ feat
-    assert np.abs(split - exact).max() < 1e-6           # "fp32 mode": bf16x3 along K (~2^-16 rel)
-    bf16_mode = Wf[:, :240] @ feat[:240]
+    # the kernel's K schedule: slab 0 position by position; pf_hi.P_hi + pf_lo.P_hi (+ pf_hi.P_lo in fp32 mode)
+    P_hi, P_lo = Wf[:, 64:320], Wf[:, 320:576]
+    bf16_mode = Wf[:, :64] @ feat[:64] + P_hi @ feat[64:320] + P_hi @ feat[320:576]
+    split = bf16_mode + P_lo @ feat[64:320]
+    assert np.abs(split - exact).max() < 1e-6           # "fp32 mode": bf16x3 split (~2^-16 rel)
     err = np.abs(bf16_mode - exact).max()
-    assert 1e-7 < err < 1e-4                            # "bf16 mode": single-bf16 pose term
+    assert 1e-7 < err < 1e-4                            # "bf16 mode": single-bf16 pose-corrective model operand
     # backward operands: hi + lo reproduces the fp32 rows to 2^-16 relative
     rec = (Wb_hi[:nf].astype(np.float64) + Wb_lo[:nf]).astype(np.float64)
     scale = np.abs(W32[1:]).max()
