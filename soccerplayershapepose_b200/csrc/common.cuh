@@ -83,6 +83,7 @@ struct DevModel {
   int njout;      // 24 + nvj + nreg
   int nterms;
   int ntv;        // virtual (joint) tiles of 32 q-groups appended after the vertex tiles
+  int vt_maxcols; // max over virtual tiles of 3 * (output joints of the tile)
   FeatLayout fl;
   ChainTables chain;
   const __nv_bfloat16* Wf;     // [n_pad][fl.pitch]         forward operand, K-major

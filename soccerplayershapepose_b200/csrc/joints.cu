@@ -6,9 +6,9 @@
 //   sum_i  A_i . [ q_ji ; c_ji ],   q_ji = sum_v Jr[j][v] w_vi p_v  (linear in the blend features),
 // so the q_ji are extra "virtual" rows of the blend GEMM, grouped 32 q-groups (96 rows) per virtual
 // tile, and a joint costs a handful of 3x4 transforms.  These kernels are the skinning kernels of
-// lbs.cu specialised to virtual tiles: lane = body, every warp owns a contiguous run of the flat
-// (body group, virtual tile) list, transforms come straight from A_blk (L1/L2), q rows are read as
-// float4 from the blend output, results are transposed through a per-warp shared tile and written as
+// lbs.cu specialised to virtual tiles: lane = body, one CTA per body group with the group's transforms in
+// shared memory (one TMA bulk copy), warps stride over the virtual tiles, q rows are read as float4 from the
+// blend output, the warp-uniform plan words are held one per lane and broadcast with shuffles, results are transposed through a per-warp shared tile and written as
 // contiguous row segments of joints (B, 90, 3); the backward emits dq as 16-byte dvp chunks and adds
 // dA / dtransl with fp32 REDs.  The 24 chain joints are written by the pose kernel; reprojection is
 // the orthographic kernel.
@@ -16,10 +16,8 @@
 
 namespace b200smpl {
 
-constexpr int JW = 8;                       // warps per CTA
+constexpr int JW = 8;                       // warps per CTA; one CTA per body group, warps stride over the virtual tiles
 constexpr int JT = JW * 32;
-constexpr int JROW = 97;                    // staging tile [32 bodies][97]: scalar accesses only, odd pitch
-constexpr size_t J_SMEM = (size_t)JW * 32 * JROW * 4;
 
 __device__ __forceinline__ void load_q96(float (&q)[96], const float4* __restrict__ p) {
 #pragma unroll
@@ -28,38 +26,47 @@ __device__ __forceinline__ void load_q96(float (&q)[96], const float4* __restric
     q[i * 4] = v.x; q[i * 4 + 1] = v.y; q[i * 4 + 2] = v.z; q[i * 4 + 3] = v.w;
   }
 }
+// transforms from the shared-memory copy of the group (paired layout, skin_common.cuh)
+__device__ __forceinline__ void load_slot_s(float (&a)[AELEMS], const float* A_s, int joint, int lane) {
+  const float4* p = reinterpret_cast<const float4*>(A_s) + joint * 96 + lane;
+  unpack_transform(a, p[0], p[32], p[64]);
+}
 
-__global__ void __launch_bounds__(JT, 1)
+// dynamic shared memory: A_s [24][3][32] float4 | JW staging tiles [32][pitch] | mbarrier
+__global__ void __launch_bounds__(JT, 2)
 joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const float4* __restrict__ A_blk, int b0, int nb,
-                  int ngroups, const float* __restrict__ transl, float* __restrict__ joints) {
+                  int pitch, const float* __restrict__ transl, float* __restrict__ joints) {
   extern __shared__ __align__(128) float smem[];
+  float* A_s = smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* tile = smem + warp * 32 * JROW;
-  float* my_row = tile + lane * JROW;
-  const long long total = (long long)ngroups * m.ntv;
-  const int gw = blockIdx.x * JW + warp, nw = gridDim.x * JW;
-  const int item0 = (int)(total * gw / nw), item1 = (int)(total * (gw + 1) / nw);
+  float* tile = smem + AG_WORDS + warp * 32 * pitch;
+  float* my_row = tile + lane * pitch;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + AG_WORDS + JW * 32 * pitch + ((JW * 32 * pitch) & 1));
+  const int g = blockIdx.x;
+  if (threadIdx.x == 0) fetch_group_transforms(A_s, reinterpret_cast<const float*>(A_blk), g, bar);
+  float tx = 0.f, ty = 0.f, tz = 0.f;
+  if (transl != nullptr && g * 32 + lane < nb) {
+    const float* t = transl + (size_t)(b0 + g * 32 + lane) * 3;
+    tx = t[0]; ty = t[1]; tz = t[2];
+  }
+  __syncthreads();                                           // barrier init visible to every waiter
   const size_t ncol_all = (size_t)m.njout * 3;
-  for (int item = item0; item < item1; ++item) {
-    const int g = item / m.ntv, tv = item - g * m.ntv;
+  const int nrows = min(32, nb - g * 32);
+  bool waited = false;
+  for (int tv = blockIdx.y * JW + warp; tv < m.ntv; tv += JW * gridDim.y) {
     float q[96];
     load_q96(q, vpB + ((size_t)g * nc4 + (m.ntiles + tv) * 24) * 32 + lane);
-    const float4* A_g = A_blk + (size_t)g * (AG_WORDS / 4);
-    float tx = 0.f, ty = 0.f, tz = 0.f;
-    if (transl != nullptr && g * 32 + lane < nb) {
-      const float* t = transl + (size_t)(b0 + g * 32 + lane) * 3;
-      tx = t[0]; ty = t[1]; tz = t[2];
-    }
-    const uint32_t* meta = m.qmeta + tv * 32;
-    const float* coef = m.qcoef + tv * 32;
+    const uint32_t mt_l = __ldg(m.qmeta + tv * 32 + lane);   // lane i holds the plan of q-group i
+    const float c_l = __ldg(m.qcoef + tv * 32 + lane);
+    if (!waited) { mbar_wait(bar, 0); waited = true; }
     float a[AELEMS];
     float x = tx, y = ty, z = tz;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const uint32_t mt = __ldg(meta + i);
+      const uint32_t mt = __shfl_sync(0xffffffffu, mt_l, i);
       if (!(mt & (1u << 14))) continue;
-      if ((mt & (1u << 5)) || i == 0) load_slot_g(a, A_g, mt & 31, lane);
-      const float c = __ldg(coef + i);
+      if ((mt & (1u << 5)) || i == 0) load_slot_s(a, A_s, mt & 31, lane);
+      const float c = __shfl_sync(0xffffffffu, c_l, i);
       const float qx = q[i * 3], qy = q[i * 3 + 1], qz = q[i * 3 + 2];
       x += fmaf(a[0], qx, fmaf(a[1], qy, fmaf(a[2], qz, a[3] * c)));
       y += fmaf(a[4], qx, fmaf(a[5], qy, fmaf(a[6], qz, a[7] * c)));
@@ -72,12 +79,11 @@ joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
     }
     __syncwarp();
     // flush the tile's joints: 3 nj contiguous floats per body row
-    const int nrows = min(32, nb - g * 32);
     const int ncols = m.vt_nj[tv] * 3;
     float* dst0 = joints + (size_t)(b0 + g * 32) * ncol_all + (size_t)(NJ + m.vt_j0[tv]) * 3;
     for (int idx = lane; idx < nrows * ncols; idx += 32) {
       const int r = idx / ncols, c = idx - r * ncols;
-      dst0[(size_t)r * ncol_all + c] = tile[r * JROW + c];
+      dst0[(size_t)r * ncol_all + c] = tile[r * pitch + c];
     }
     __syncwarp();
   }
@@ -85,39 +91,41 @@ joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
 
 // backward over virtual tiles.  dJ: total joint gradient (B, NJout, 3).
 //   dq -> virtual rows of dvp ; dA, dtransl -> fp32 REDs into the slab accumulators
-__global__ void __launch_bounds__(JT, 1)
+__global__ void __launch_bounds__(JT, 2)
 joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const float4* __restrict__ A_blk, int b0, int nb,
-                  int ngroups, const float* __restrict__ dJ, __nv_bfloat16* __restrict__ dvp_hi,
+                  int pitch, const float* __restrict__ dJ, __nv_bfloat16* __restrict__ dvp_hi,
                   __nv_bfloat16* __restrict__ dvp_lo, float* __restrict__ dA_acc, float* __restrict__ dtr_acc) {
   extern __shared__ __align__(128) float smem[];
+  float* A_s = smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* tile = smem + warp * 32 * JROW;
-  const float* my_row = tile + lane * JROW;
-  const long long total = (long long)ngroups * m.ntv;
-  const int gw = blockIdx.x * JW + warp, nw = gridDim.x * JW;
-  const int item0 = (int)(total * gw / nw), item1 = (int)(total * (gw + 1) / nw);
+  float* tile = smem + AG_WORDS + warp * 32 * pitch;
+  const float* my_row = tile + lane * pitch;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + AG_WORDS + JW * 32 * pitch + ((JW * 32 * pitch) & 1));
+  const int g = blockIdx.x;
+  if (threadIdx.x == 0) fetch_group_transforms(A_s, reinterpret_cast<const float*>(A_blk), g, bar);
+  __syncthreads();
   const size_t ncol_all = (size_t)m.njout * 3;
-  for (int item = item0; item < item1; ++item) {
-    const int g = item / m.ntv, tv = item - g * m.ntv;
+  float* dA_g = dA_acc + (size_t)g * AG_WORDS;
+  const int nrows = max(0, min(32, nb - g * 32));
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  bool waited = false;
+  for (int tv = blockIdx.y * JW + warp; tv < m.ntv; tv += JW * gridDim.y) {
     float q[96];
     load_q96(q, vpB + ((size_t)g * nc4 + (m.ntiles + tv) * 24) * 32 + lane);
-    const float4* A_g = A_blk + (size_t)g * (AG_WORDS / 4);
-    float* dA_g = dA_acc + (size_t)g * AG_WORDS;
-    const int nrows = max(0, min(32, nb - g * 32));
+    const uint32_t mt_l = __ldg(m.qmeta + tv * 32 + lane);
+    const float c_l = __ldg(m.qcoef + tv * 32 + lane);
     const int ncols = m.vt_nj[tv] * 3;
     // stage the gradients of this tile's joints (3 nj floats of each body row)
     {
       const float* src0 = dJ + (size_t)(b0 + g * 32) * ncol_all + (size_t)(NJ + m.vt_j0[tv]) * 3;
       for (int idx = lane; idx < 32 * ncols; idx += 32) {
         const int r = idx / ncols, c = idx - r * ncols;
-        tile[r * JROW + c] = (r < nrows) ? ld_stream(src0 + (size_t)r * ncol_all + c) : 0.f;
+        tile[r * pitch + c] = (r < nrows) ? ld_stream(src0 + (size_t)r * ncol_all + c) : 0.f;
       }
     }
+    if (!waited) { mbar_wait(bar, 0); waited = true; }
     __syncwarp();
-    const uint32_t* meta = m.qmeta + tv * 32;
-    const float* coef = m.qcoef + tv * 32;
-    float a[9];
-    float sx = 0.f, sy = 0.f, sz = 0.f;
+    float a[AELEMS];
     const size_t chunk0 = (size_t)(g >> 2) * (nc4 >> 1) + (size_t)((m.ntiles + tv) * 12);
     __nv_bfloat16* hi_p = dvp_hi + (chunk0 * 128 + (g & 3) * 32 + lane) * 8;
     __nv_bfloat16* lo_p = dvp_lo ? dvp_lo + (chunk0 * 128 + (g & 3) * 32 + lane) * 8 : nullptr;
@@ -127,20 +135,20 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
 #pragma unroll
       for (int ii = 0; ii < 8; ++ii) {
         const int i = blk * 8 + ii;
-        const uint32_t mt = __ldg(meta + i);
+        const uint32_t mt = __shfl_sync(0xffffffffu, mt_l, i);
         if (!(mt & (1u << 14))) {                          // dummy slot: its dvp rows must be 0
           dq[ii * 3] = dq[ii * 3 + 1] = dq[ii * 3 + 2] = 0.f;
           continue;
         }
         const int joint = mt & 31;
-        if ((mt & (1u << 5)) || i == 0) load_rot_g(a, A_g, joint, lane);
-        const float c = __ldg(coef + i);
+        if ((mt & (1u << 5)) || i == 0) load_slot_s(a, A_s, joint, lane);
+        const float c = __shfl_sync(0xffffffffu, c_l, i);
         const float* gj = my_row + ((mt >> 8) & 31) * 3;
         const float gx = gj[0], gy = gj[1], gz = gj[2];
         const float qx = q[i * 3], qy = q[i * 3 + 1], qz = q[i * 3 + 2];
-        dq[ii * 3] = fmaf(a[0], gx, fmaf(a[3], gy, a[6] * gz));
-        dq[ii * 3 + 1] = fmaf(a[1], gx, fmaf(a[4], gy, a[7] * gz));
-        dq[ii * 3 + 2] = fmaf(a[2], gx, fmaf(a[5], gy, a[8] * gz));
+        dq[ii * 3] = fmaf(a[0], gx, fmaf(a[4], gy, a[8] * gz));
+        dq[ii * 3 + 1] = fmaf(a[1], gx, fmaf(a[5], gy, a[9] * gz));
+        dq[ii * 3 + 2] = fmaf(a[2], gx, fmaf(a[6], gy, a[10] * gz));
         float* dp = dA_g + (size_t)joint * AELEMS * 32 + lane;
         red_add(dp, gx * qx); red_add(dp + 32, gx * qy); red_add(dp + 64, gx * qz); red_add(dp + 96, gx * c);
         red_add(dp + 128, gy * qx); red_add(dp + 160, gy * qy); red_add(dp + 192, gy * qz); red_add(dp + 224, gy * c);
@@ -155,12 +163,12 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
         store_dvp_chunk(ch, hi_p + off, lo_p ? lo_p + off : nullptr);
       }
     }
-    float* dtr_g = dtr_acc + (size_t)g * 96;
-    red_add(dtr_g + lane, sx);
-    red_add(dtr_g + 32 + lane, sy);
-    red_add(dtr_g + 64 + lane, sz);
     __syncwarp();
   }
+  float* dtr_g = dtr_acc + (size_t)g * 96;
+  red_add(dtr_g + lane, sx);
+  red_add(dtr_g + 32 + lane, sy);
+  red_add(dtr_g + 64 + lane, sz);
 }
 
 // total joint gradient when a 2D reprojection gradient is present:
@@ -194,20 +202,20 @@ joint_grad_total_kernel(const float* __restrict__ joints, const float* __restric
   if (gcam != nullptr && threadIdx.x < 3) gcam[b * 3 + threadIdx.x] = sh[threadIdx.x][0] + sh[threadIdx.x][1] + sh[threadIdx.x][2] + sh[threadIdx.x][3];
 }
 
-static int joints_grid(int ngroups, int ntv) {
-  const long long total = (long long)ngroups * ntv;
-  return (int)std::max<long long>(1, std::min<long long>(148 * 2, (total + JW - 1) / JW));
-}
+// CTAs per body group: one virtual tile per warp
+static int joints_split(int ntv) { return std::max(1, (ntv + JW - 1) / JW); }
+static size_t joints_smem(int pitch) { return (size_t)(AG_WORDS + JW * 32 * pitch + 1) * 4 + 16; }
 
 int launch_joints_fwd(const DevModel& m, const float* vpB, int S, const float* A_blk, int b0, int nb,
                       const float* transl, float* joints, cudaStream_t st) {
   if (nb <= 0 || m.ntv == 0) return 0;
   const int groups = (nb + 31) / 32;
-  B200_CUDA_TRY(cudaFuncSetAttribute(joints_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)J_SMEM));
+  const int pitch = m.vt_maxcols | 1;
+  const size_t smem = joints_smem(pitch);
+  B200_CUDA_TRY(cudaFuncSetAttribute(joints_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LaunchTimer _timer("joints_fwd", st);
-  joints_fwd_kernel<<<joints_grid(groups, m.ntv), JT, J_SMEM, st>>>(m, reinterpret_cast<const float4*>(vpB), m.n_pad / 4,
-                                                                   reinterpret_cast<const float4*>(A_blk), b0, nb,
-                                                                   groups, transl, joints);
+  joints_fwd_kernel<<<dim3(groups, joints_split(m.ntv)), JT, smem, st>>>(m, reinterpret_cast<const float4*>(vpB), m.n_pad / 4,
+                                             reinterpret_cast<const float4*>(A_blk), b0, nb, pitch, transl, joints);
   B200_LAUNCH_CHECK("joints_fwd");
   return 0;
 }
@@ -218,11 +226,13 @@ int launch_joints_bwd(const DevModel& m, const float* vpB, int S, int Sw, const 
                       cudaStream_t st) {
   if (m.ntv == 0) return 0;
   const int groups = Sw / 32;
-  B200_CUDA_TRY(cudaFuncSetAttribute(joints_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)J_SMEM));
+  const int pitch = m.vt_maxcols | 1;
+  const size_t smem = joints_smem(pitch);
+  B200_CUDA_TRY(cudaFuncSetAttribute(joints_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LaunchTimer _timer("joints_bwd", st);
-  joints_bwd_kernel<<<joints_grid(groups, m.ntv), JT, J_SMEM, st>>>(m, reinterpret_cast<const float4*>(vpB), m.n_pad / 4,
-                                                                   reinterpret_cast<const float4*>(A_blk), b0, nb,
-                                                                   groups, dJ, dvp_hi, dvp_lo, dA_acc, dtr_acc);
+  joints_bwd_kernel<<<dim3(groups, joints_split(m.ntv)), JT, smem, st>>>(m, reinterpret_cast<const float4*>(vpB), m.n_pad / 4,
+                                             reinterpret_cast<const float4*>(A_blk), b0, nb, pitch, dJ, dvp_hi, dvp_lo,
+                                             dA_acc, dtr_acc);
   B200_LAUNCH_CHECK("joints_bwd");
   return 0;
 }

@@ -312,6 +312,8 @@ int pack_model(const b200smpl_model_desc* d, HostArrays& h, DevModel& dm, std::s
   memset(&dm, 0, sizeof(dm));
   h.qmeta = qmeta; h.qcoef = qcoef; h.vt_j0 = vt_j0; h.vt_nj = vt_nj;
   dm.ntv = ntv;
+  dm.vt_maxcols = 3;
+  for (int x : vt_nj) dm.vt_maxcols = std::max(dm.vt_maxcols, 3 * x);
   dm.V = V; dm.ntiles = ntiles; dm.n_real = 3 * V; dm.nq = nq; dm.n_virt0 = n_virt0; dm.n_rows = n_rows;
   dm.n_pad = n_pad; dm.njout = NJ + nvj + nreg; dm.nterms = h.term_ptr.back();
   dm.fl = fl; dm.chain = ch;

@@ -11,9 +11,9 @@
 
 namespace b200smpl {
 
-constexpr int POSE_WARPS = 8;
+constexpr int POSE_WARPS = 16;
 constexpr int POSE_THREADS = POSE_WARPS * 32;
-constexpr int BODIES_PER_WARP = 4;          // 32 bodies per CTA
+constexpr int BODIES_PER_WARP = 2;          // 32 bodies per CTA
 constexpr int OUT_ROWS = NJ * AELEMS + NJ * 3;  // 288 A rows + 72 posed-joint rows
 constexpr int OUT_PITCH = 33;
 
