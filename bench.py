@@ -37,6 +37,32 @@ UNIT = "meshes/s"
 LBS_FWD_BYTES = 82680 + 1152 + 82680                 # v_posed in, A in, vertices out
 LBS_BWD_BYTES = 82680 + 82680 + 1152 + 82680 + 1152  # dV in, v_posed in, A in, dv_posed out, dA out
 KERNEL_BYTES = {"lbs_fwd": LBS_FWD_BYTES, "lbs_bwd": LBS_BWD_BYTES}
+# tensor-pipe kernels: bf16 MMA FLOPs executed per mesh (fp32 mode = bf16x3 split: 3 products per fp32 product;
+# K steps of 16: 3 for the constants+shape slab, 13 per pose product) and the fp32-equivalent algorithmic FLOPs
+# of SURVEY.md section 8(d) (2 * 217 * 20670 per mesh, forward and backward-data alike)
+ALGO_GEMM_FLOPS = 2 * 217 * 20670
+
+
+def gemm_flops_per_mesh(kernel, mode, n_pad):
+    if kernel == "blend_fwd_umma":
+        ksteps = 3 + 13 * (3 if mode == "fp32" else 2)
+        return 2.0 * 16 * ksteps * n_pad
+    if kernel == "blend_bwd_umma":
+        return 2.0 * 224 * n_pad * (3 if mode == "fp32" else 1)
+    return None
+
+
+def measured_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops"]), "measured burst (MEASURED_PEAKS.json)"
+    return 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
 
 
 def measured_peaks():
@@ -258,19 +284,39 @@ def main():
     lib.b200smpl_timing_enable(0)
     kt = timing_report(lib)
     peak, peak_src = measured_peaks()
+    tpeak, tpeak_src = measured_tensor_peak()
     step_ms_timed = sum(ms for _, ms in kt.values()) / args.steps
-    dom = max((k for k in kt if k in KERNEL_BYTES), key=lambda k: kt[k][1], default=None)
-    roofline = None
-    if dom is not None:
-        n_launch, ms = kt[dom]
+    traffic = ncu_traffic()
+    n_pad = int(eng.info.num_blend_rows_padded)
+
+    def kernel_roofline(k):
+        n_launch, ms = kt[k]
         per_launch_ms = ms / n_launch
         bodies_per_launch = B * args.steps / n_launch
-        achieved = KERNEL_BYTES[dom] * bodies_per_launch / (per_launch_ms / 1e3) / 1e9
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "bytes_per_mesh": KERNEL_BYTES[dom], "avg_launch_ms": per_launch_ms,
-                    "share_of_step": ms / args.steps / step_ms_timed,
-                    "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(kt.items())}}
+        tr = traffic.get(k) if (traffic.get("batch") == bodies_per_launch and args.mode == "fp32") else None
+        common = {"kernel": k, "avg_launch_ms": per_launch_ms, "share_of_step": ms / args.steps / step_ms_timed,
+                  "traffic": tr}
+        if k in KERNEL_BYTES:
+            achieved = KERNEL_BYTES[k] * bodies_per_launch / (per_launch_ms / 1e3) / 1e9
+            return dict(common, bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                        peak_source=peak_src, bytes_per_mesh=KERNEL_BYTES[k])
+        fl = gemm_flops_per_mesh(k, args.mode, n_pad)
+        if fl is not None:
+            achieved = fl * bodies_per_launch / (per_launch_ms / 1e3) / 1e12
+            algo = ALGO_GEMM_FLOPS * bodies_per_launch / (per_launch_ms / 1e3) / 1e12
+            return dict(common, bound="tensor", achieved=achieved, peak=tpeak, unit="TFLOP/s", frac=achieved / tpeak,
+                        peak_source=tpeak_src, flops_per_mesh=fl,
+                        note="achieved = bf16 MMA FLOPs executed (bf16x3 split in fp32 mode); fp32-equivalent "
+                             "algorithmic rate %.1f TFLOP/s" % algo)
+        return None
+
+    dom = max(kt, key=lambda k: kt[k][1], default=None)
+    roofline = kernel_roofline(dom) if dom is not None else None
+    if roofline is not None:
+        roofline["kernels_ms_per_step"] = {k: v[1] / args.steps for k, v in sorted(kt.items())}
+        roofline["others"] = {k: {kk: vv for kk, vv in r.items() if kk in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+                              for k in ("lbs_fwd", "lbs_bwd", "blend_fwd_umma", "blend_bwd_umma") if k in kt and k != dom
+                              for r in [kernel_roofline(k)] if r is not None}
 
     # ---- end to end through the public module API, host buffers in, gradients out ----
     hb, hr, ht = (x.cpu().pin_memory() for x in (betas, rot, trans))
