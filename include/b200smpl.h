@@ -200,6 +200,35 @@ B200SMPL_API int b200smpl_joints2d_loss(const float* joints, const float* cam, c
                            const uint8_t* vis, int batch, int num_joints, int nmap, float proj_wh, float norm_wh,
                            float log_var, float* loss, float* grad_joints, float* grad_cam, void* stream);
 
+/*
+ * Batched per-player fitting loop -- replaces the body of the reference's single_view_optimization
+ * (player_recon.py:1172-1294: Adam over global_orient / body pose without hands and feet / cam / betas on the
+ * joints2D loss, best iterate kept) for a batch of independent players.  One iteration is
+ *   b200smpl_forward (joints only) -> b200smpl_fit_loss -> b200smpl_backward -> b200smpl_fit_mark_best ->
+ *   b200smpl_fit_adam_step per parameter tensor
+ * and is CUDA-graph capturable: the step counter and the "improved" flags live in device memory.
+ *
+ * fit_loss: loss_per_body[b] = mean over the player's visible (joint, xy) pairs of the squared normalised
+ *   reprojection error (cam_utils.py:5-26 -> joints2d_utils.py:5-10 -> multi_task_loss.py:97-113 for ONE player)
+ *   * exp(-log_var) + log_var + shape_weight * mean(betas^2)   (multi_task_loss.py:120-124 against zeros);
+ *   grad_joints [B][NJ][3], grad_cam [B][3], grad_betas [B][nb] (shape term only; may be NULL) are written.
+ * fit_mark_best: improved[b] = loss < best_loss (best_loss, best_iter updated); step[1] = step[0] + 1.
+ * fit_adam_step: params [B][cols]; rows flagged improved are first copied to best_params (the parameters that
+ *   produced this iteration's loss, player_recon.py:1258-1262), then torch.optim.Adam's update with the gradient
+ *   grad (+ grad_extra) is applied to every column not marked in frozen_cols [cols] (may be NULL).  step is the
+ *   2-int device counter shared with fit_mark_best; the call of an iteration's last tensor passes commit_step=1.
+ */
+B200SMPL_API int b200smpl_fit_loss(const float* joints, const float* cam, const int32_t* joint_map, const float* label,
+                      const uint8_t* vis, const float* betas, int batch, int num_joints, int nmap, int num_betas,
+                      float proj_wh, float norm_wh, float log_var, float shape_weight, float* loss_per_body,
+                      float* grad_joints, float* grad_cam, float* grad_betas, void* stream);
+B200SMPL_API int b200smpl_fit_mark_best(const float* loss_per_body, float* best_loss, int32_t* best_iter, uint8_t* improved,
+                           int32_t* step, int batch, void* stream);
+B200SMPL_API int b200smpl_fit_adam_step(float* params, const float* grad, const float* grad_extra, float* exp_avg,
+                           float* exp_avg_sq, float* best_params, const uint8_t* improved, const uint8_t* frozen_cols,
+                           int32_t* step, int commit_step, int batch, int cols, float lr, float beta1, float beta2,
+                           float eps, void* stream);
+
 B200SMPL_API const char* b200smpl_last_error(void);
 B200SMPL_API int b200smpl_abi_version(void);
 

@@ -81,6 +81,11 @@ SYMBOLS = {
                                                       c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
     "b200smpl_joints2d_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200smpl_fit_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                  c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200smpl_fit_mark_best": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "b200smpl_fit_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_void_p]),
     "b200smpl_last_error": (c_char_p, []),
     "b200smpl_abi_version": (c_int, []),
     "b200smpl_launch_count": (c_int64, []),

@@ -1,0 +1,117 @@
+"""GPU tests of the batched fitting loop against a restatement of the reference's
+single_view_optimization (player_recon.py:1172-1294) on the CPU oracle with torch.optim.Adam, float64."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import smpl_oracle as O
+from soccerplayershapepose_b200 import config
+from soccerplayershapepose_b200.fitting import BatchedFitter, FROZEN_FULL_JOINTS
+from soccerplayershapepose_b200.smpl import SMPL
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(B, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    betas_t = torch.randn(B, 10, generator=g) * 0.8
+    pose_t = torch.randn(B, 72, generator=g) * 0.25
+    cam_t = torch.stack([0.6 + 0.6 * torch.rand(B, generator=g), 0.4 * torch.rand(B, generator=g) - 0.2,
+                         0.4 * torch.rand(B, generator=g) - 0.2], 1)
+    rot_t = O.batch_rodrigues(pose_t.reshape(-1, 3)).reshape(B, 24, 3, 3)
+    # initial guess: perturbed truth
+    betas0 = betas_t + 0.5 * torch.randn(B, 10, generator=g)
+    pose0 = pose_t + 0.15 * torch.randn(B, 72, generator=g)
+    cam0 = cam_t + 0.05 * torch.randn(B, 3, generator=g)
+    rot0 = O.batch_rodrigues(pose0.reshape(-1, 3)).reshape(B, 24, 3, 3)
+    return betas_t, rot_t, cam_t, betas0, rot0, cam0
+
+
+def _ref_fit(model, rot0, betas0, cam0, label, iters, lr, shape_w):
+    """The reference loop restated (float64, CPU): Adam over raw rotation matrices / betas / cam, hands and feet
+    frozen, per-player joints2D loss (+ shape term), best iterate by loss."""
+    orc = O.SMPLOracle(model, dtype=torch.float64)
+    rot = rot0.double().clone().requires_grad_(True)
+    betas = betas0.double().clone().requires_grad_(True)
+    cam = cam0.double().clone().requires_grad_(True)
+    opt = torch.optim.Adam([rot, betas, cam], lr=lr)
+    B = rot.shape[0]
+    best_loss = torch.full((B,), float("inf"), dtype=torch.float64)
+    best = [rot.detach().clone(), betas.detach().clone(), cam.detach().clone()]
+    best_iter = torch.zeros(B, dtype=torch.int64)
+    losses = []
+    for it in range(1, iters + 1):
+        out = orc.forward_flat(betas, rot, None, pose2rot=False)
+        j2d = O.orthographic_project(out.joints, cam)[:, config.SMPL_TO_KPRCNN_MAP, :]
+        px = O.undo_keypoint_normalisation(j2d, 512)
+        d = (2.0 * px / config.REGRESSOR_IMG_WH - 1.0) - (2.0 * label.double() / config.REGRESSOR_IMG_WH - 1.0)
+        loss_b = (d * d).mean(dim=(1, 2)) + shape_w * (betas * betas).mean(1)
+        losses.append(loss_b.detach().clone())
+        imp = loss_b.detach() < best_loss
+        best_loss = torch.where(imp, loss_b.detach(), best_loss)
+        best_iter[imp] = it
+        for cur, bst in zip((rot, betas, cam), best):
+            bst[imp] = cur.detach()[imp]
+        opt.zero_grad()
+        loss_b.sum().backward()
+        rot.grad[:, list(FROZEN_FULL_JOINTS)] = 0.0
+        opt.step()
+    return dict(rot=rot.detach(), betas=betas.detach(), cam=cam.detach(), best_loss=best_loss, best_iter=best_iter,
+                best=best, losses=torch.stack(losses))
+
+
+@pytest.fixture(scope="module")
+def setup(synthetic_model):
+    dev = torch.device("cuda", 0)
+    smpl = SMPL(model_data=synthetic_model, mode="fp32").to(dev)
+    return synthetic_model, smpl, dev
+
+
+def _labels(model, rot_t, betas_t, cam_t):
+    orc = O.SMPLOracle(model, dtype=torch.float64)
+    out = orc.forward_flat(betas_t.double(), rot_t.double(), None, pose2rot=False)
+    j2d = O.orthographic_project(out.joints, cam_t.double())[:, config.SMPL_TO_KPRCNN_MAP, :]
+    return O.undo_keypoint_normalisation(j2d, 512).float()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_fit_matches_reference_loop(setup, graph):
+    model, smpl, dev = setup
+    B, iters, lr, sw = 6, 10, 2e-3, 0.05
+    betas_t, rot_t, cam_t, betas0, rot0, cam0 = _problem(B)
+    label = _labels(model, rot_t, betas_t, cam_t)
+    ref = _ref_fit(model, rot0, betas0, cam0, label, iters, lr, sw)
+    fitter = BatchedFitter(smpl, lr=lr, shape_weight=sw, use_cuda_graph=graph)
+    res = fitter.fit(rot0.to(dev), betas0.to(dev), cam0.to(dev), label.to(dev), iterations=iters)
+    torch.cuda.synchronize()
+    # loss of the first and of the last iteration, per player
+    np.testing.assert_allclose(res["initial_loss"].cpu().double().numpy(), ref["losses"][0].numpy(), rtol=2e-4)
+    np.testing.assert_allclose(res["last_loss"].cpu().double().numpy(), ref["losses"][-1].numpy(), rtol=2e-3)
+    np.testing.assert_allclose(res["best_loss"].cpu().double().numpy(), ref["best_loss"].numpy(), rtol=2e-3)
+    assert torch.equal(res["best_iter"].cpu().long(), ref["best_iter"])
+    # parameters after `iters` Adam steps (Adam normalises the gradient: entries with a vanishing gradient are
+    # sensitive to rounding, hence the robust statistic next to the max)
+    for got, want in ((res["final_rotmats"], ref["rot"]), (res["final_betas"], ref["betas"]), (res["final_cam"], ref["cam"])):
+        diff = (got.cpu().double() - want).abs()
+        assert diff.median().item() < 1e-5 and diff.max().item() < 2 * lr * iters
+        assert torch.quantile(diff.flatten(), 0.99).item() < 2e-3
+    # frozen joints never move
+    assert torch.equal(res["final_rotmats"][:, list(FROZEN_FULL_JOINTS)].cpu(), rot0[:, list(FROZEN_FULL_JOINTS)])
+    # the loss goes down
+    assert (res["best_loss"] < res["initial_loss"]).all()
+
+
+def test_fit_result_keys_and_translation(setup):
+    model, smpl, dev = setup
+    B = 3
+    betas_t, rot_t, cam_t, betas0, rot0, cam0 = _problem(B, seed=3)
+    label = _labels(model, rot_t, betas_t, cam_t)
+    vis = torch.ones(B, 17, dtype=torch.bool)
+    vis[0, 3] = False
+    res = BatchedFitter(smpl, lr=1e-3).fit(rot0.to(dev), betas0.to(dev), cam0.to(dev), label.to(dev), vis=vis.to(dev),
+                                           iterations=5)
+    # the reference's .npz keys (player_recon.py:1293-1294)
+    assert res["body_pose"].shape == (B, 23, 3, 3) and res["global_orient"].shape == (B, 1, 3, 3)
+    assert res["betas"].shape == (B, 10) and res["translation"].shape == (B, 3)
+    t = O.weak_perspective_to_translation(res["cam"].cpu().double(), config.FOCAL_LENGTH, 512)
+    np.testing.assert_allclose(res["translation"].cpu().double().numpy(), t.numpy(), rtol=1e-5)
