@@ -270,11 +270,9 @@ def main():
     launches = lib.b200smpl_launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = B * world * args.steps / (ms_total / 1e3)
+    from soccerplayershapepose_b200 import sharding
+    ms_total = sharding.max_over_ranks(ms_total, dev)           # the slowest rank decides
+    value = sharding.aggregate_throughput(B, world, args.steps, ms_total)
 
     # ---- per-kernel device times over the same K steps (events on the launching stream) ----
     lib.b200smpl_timing_enable(1)
@@ -342,10 +340,7 @@ def main():
     for _ in range(args.steps):
         e2e_step()
     sync_all()
-    dt = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_val = B * world * args.steps / float(dt.item())
+    e2e_val = B * world * args.steps / sharding.max_over_ranks(time.perf_counter() - t0, dev)
     io_bytes = B * (10 + 216 + 3) * 4
 
     cpu_baseline = None
