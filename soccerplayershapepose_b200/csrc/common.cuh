@@ -31,6 +31,7 @@ struct ChainTables {
   int8_t depth[NJ];
   int8_t nchild[NJ];
   int8_t child[NJ][MAX_CHILD];
+  int8_t maxchild_at[NJ];   // [d]: max number of children a joint of depth d-1 has (bounds the gather of round d)
   int32_t maxdepth;
 };
 
@@ -99,7 +100,7 @@ struct DevModel {
   const uint8_t* term_joint;   // [nterms] skinning joint of the term
   const int32_t* term_qrow;    // [nterms] first of the 3 blend rows holding q
   const float* term_c;         // [nterms]
-  const uint32_t* qmeta;       // [ntv*32] virtual-tile plan: joint | reload<<5 | jl<<8 | last<<13 | valid<<14
+  const uint32_t* qmeta;       // [ntv*32] virtual-tile plan (groups sorted by skinning joint): joint | reload<<5 | jl<<8 | valid<<14
   const float* qcoef;          // [ntv*32] homogeneous coefficient c of the q-group
   const int32_t* vt_j0;        // [ntv] first output joint (index into joints 24..) of the tile
   const int32_t* vt_nj;        // [ntv] output joints covered by the tile

@@ -59,27 +59,24 @@ joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
     const uint32_t mt_l = __ldg(m.qmeta + tv * 32 + lane);   // lane i holds the plan of q-group i
     const float c_l = __ldg(m.qcoef + tv * 32 + lane);
     if (!waited) { mbar_wait(bar, 0); waited = true; }
+    // every output joint of the tile starts at the translation and accumulates its terms in the lane's row
+    const int ncols = m.vt_nj[tv] * 3;
+    for (int c = 0; c < ncols; c += 3) { my_row[c] = tx; my_row[c + 1] = ty; my_row[c + 2] = tz; }
     float a[AELEMS];
-    float x = tx, y = ty, z = tz;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const uint32_t mt = __shfl_sync(0xffffffffu, mt_l, i);
       if (!(mt & (1u << 14))) continue;
-      if ((mt & (1u << 5)) || i == 0) load_slot_s(a, A_s, mt & 31, lane);
+      if (mt & (1u << 5)) load_slot_s(a, A_s, mt & 31, lane);       // groups are sorted by skinning joint
       const float c = __shfl_sync(0xffffffffu, c_l, i);
       const float qx = q[i * 3], qy = q[i * 3 + 1], qz = q[i * 3 + 2];
-      x += fmaf(a[0], qx, fmaf(a[1], qy, fmaf(a[2], qz, a[3] * c)));
-      y += fmaf(a[4], qx, fmaf(a[5], qy, fmaf(a[6], qz, a[7] * c)));
-      z += fmaf(a[8], qx, fmaf(a[9], qy, fmaf(a[10], qz, a[11] * c)));
-      if (mt & (1u << 13)) {                               // last term of this joint
-        float* o = my_row + ((mt >> 8) & 31) * 3;
-        o[0] = x; o[1] = y; o[2] = z;
-        x = tx; y = ty; z = tz;
-      }
+      float* o = my_row + ((mt >> 8) & 31) * 3;
+      o[0] += fmaf(a[0], qx, fmaf(a[1], qy, fmaf(a[2], qz, a[3] * c)));
+      o[1] += fmaf(a[4], qx, fmaf(a[5], qy, fmaf(a[6], qz, a[7] * c)));
+      o[2] += fmaf(a[8], qx, fmaf(a[9], qy, fmaf(a[10], qz, a[11] * c)));
     }
     __syncwarp();
     // flush the tile's joints: 3 nj contiguous floats per body row
-    const int ncols = m.vt_nj[tv] * 3;
     float* dst0 = joints + (size_t)(b0 + g * 32) * ncol_all + (size_t)(NJ + m.vt_j0[tv]) * 3;
     for (int idx = lane; idx < nrows * ncols; idx += 32) {
       const int r = idx / ncols, c = idx - r * ncols;
@@ -125,7 +122,12 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
     }
     if (!waited) { mbar_wait(bar, 0); waited = true; }
     __syncwarp();
-    float a[AELEMS];
+    // dL/dtransl: every output joint of the tile once
+    for (int c = 0; c < ncols; c += 3) { sx += my_row[c]; sy += my_row[c + 1]; sz += my_row[c + 2]; }
+    float a[AELEMS], d[AELEMS];
+#pragma unroll
+    for (int e = 0; e < AELEMS; ++e) d[e] = 0.f;
+    int jcur = 0;
     const size_t chunk0 = (size_t)(g >> 2) * (nc4 >> 1) + (size_t)((m.ntiles + tv) * 12);
     __nv_bfloat16* hi_p = dvp_hi + (chunk0 * 128 + (g & 3) * 32 + lane) * 8;
     __nv_bfloat16* lo_p = dvp_lo ? dvp_lo + (chunk0 * 128 + (g & 3) * 32 + lane) * 8 : nullptr;
@@ -140,8 +142,11 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
           dq[ii * 3] = dq[ii * 3 + 1] = dq[ii * 3 + 2] = 0.f;
           continue;
         }
-        const int joint = mt & 31;
-        if ((mt & (1u << 5)) || i == 0) load_slot_s(a, A_s, joint, lane);
+        if (mt & (1u << 5)) {                              // next skinning joint: close the accumulators of the last
+          flush_slot_g(d, dA_g, jcur, lane);               // (zeros the first time)
+          jcur = mt & 31;
+          load_slot_s(a, A_s, jcur, lane);
+        }
         const float c = __shfl_sync(0xffffffffu, c_l, i);
         const float* gj = my_row + ((mt >> 8) & 31) * 3;
         const float gx = gj[0], gy = gj[1], gz = gj[2];
@@ -149,11 +154,9 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
         dq[ii * 3] = fmaf(a[0], gx, fmaf(a[4], gy, a[8] * gz));
         dq[ii * 3 + 1] = fmaf(a[1], gx, fmaf(a[5], gy, a[9] * gz));
         dq[ii * 3 + 2] = fmaf(a[2], gx, fmaf(a[6], gy, a[10] * gz));
-        float* dp = dA_g + (size_t)joint * AELEMS * 32 + lane;
-        red_add(dp, gx * qx); red_add(dp + 32, gx * qy); red_add(dp + 64, gx * qz); red_add(dp + 96, gx * c);
-        red_add(dp + 128, gy * qx); red_add(dp + 160, gy * qy); red_add(dp + 192, gy * qz); red_add(dp + 224, gy * c);
-        red_add(dp + 256, gz * qx); red_add(dp + 288, gz * qy); red_add(dp + 320, gz * qz); red_add(dp + 352, gz * c);
-        if (mt & (1u << 13)) { sx += gx; sy += gy; sz += gz; }
+        d[0] = fmaf(gx, qx, d[0]); d[1] = fmaf(gx, qy, d[1]); d[2] = fmaf(gx, qz, d[2]); d[3] = fmaf(gx, c, d[3]);
+        d[4] = fmaf(gy, qx, d[4]); d[5] = fmaf(gy, qy, d[5]); d[6] = fmaf(gy, qz, d[6]); d[7] = fmaf(gy, c, d[7]);
+        d[8] = fmaf(gz, qx, d[8]); d[9] = fmaf(gz, qy, d[9]); d[10] = fmaf(gz, qz, d[10]); d[11] = fmaf(gz, c, d[11]);
       }
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) {
@@ -163,6 +166,7 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
         store_dvp_chunk(ch, hi_p + off, lo_p ? lo_p + off : nullptr);
       }
     }
+    flush_slot_g(d, dA_g, jcur, lane);
     __syncwarp();
   }
   float* dtr_g = dtr_acc + (size_t)g * 96;

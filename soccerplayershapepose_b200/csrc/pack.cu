@@ -53,6 +53,8 @@ int pack_model(const b200smpl_model_desc* d, HostArrays& h, DevModel& dm, std::s
     if (ch.nchild[p] >= MAX_CHILD) { err = "a joint has more than 4 children"; return B200SMPL_ERR_INVALID; }
     ch.child[p][ch.nchild[p]++] = (int8_t)j;
   }
+  for (int j = 0; j < NJ; ++j)
+    if (ch.depth[j] + 1 < NJ) ch.maxchild_at[ch.depth[j] + 1] = std::max(ch.maxchild_at[ch.depth[j] + 1], ch.nchild[j]);
 
   // ---- skinning influences per vertex (<= 4 non-zeros) ----
   struct Infl { int n; int j[4]; float w[4]; };
@@ -118,41 +120,49 @@ int pack_model(const b200smpl_model_desc* d, HostArrays& h, DevModel& dm, std::s
       group_src.emplace_back();
     }
   std::vector<int> group_slot(group_src.size(), -1);     // group -> slot (position) in the padded layout
-  std::vector<uint32_t> qmeta;                            // per slot: joint | reload<<5 | jl<<8 | last<<13 | valid<<14
+  std::vector<uint32_t> qmeta;                            // per slot: joint | reload<<5 | jl<<8 | valid<<14
   std::vector<float> qcoef;
   std::vector<int32_t> vt_j0, vt_nj;
   {
-    int prev_joint = -1;
+    // a tile = up to 32 q-groups covering whole, consecutive output joints; inside the tile the groups are
+    // ordered by SKINNING joint, so that the kernels keep one transform (and, backward, one gradient
+    // accumulator) in registers across all the output joints of the tile that share it
+    struct Entry { int joint, jl, group; float c; };
+    std::vector<Entry> cur;
+    int cur_j0 = -1, cur_nj = 0;
+    auto flush_tile = [&]() {
+      if (cur_j0 < 0) return;
+      std::stable_sort(cur.begin(), cur.end(), [](const Entry& a, const Entry& b) {
+        return a.joint != b.joint ? a.joint < b.joint : a.jl < b.jl;
+      });
+      int prev_joint = -1;
+      for (const Entry& e : cur) {
+        const uint32_t mword = (uint32_t)e.joint | ((e.joint != prev_joint ? 1u : 0u) << 5) | ((uint32_t)e.jl << 8) |
+                               (1u << 14);
+        prev_joint = e.joint;
+        group_slot[e.group] = (int)qmeta.size();
+        qmeta.push_back(mword);
+        qcoef.push_back(e.c);
+      }
+      while (qmeta.size() % 32) { qmeta.push_back(0u); qcoef.push_back(0.f); }
+      vt_j0.push_back(cur_j0);
+      vt_nj.push_back(cur_nj);
+      cur.clear();
+      cur_j0 = -1;
+      cur_nj = 0;
+    };
     for (int J = 0; J < nvj + nreg; ++J) {
       auto& tv = joint_terms[J];
-      std::stable_sort(tv.begin(), tv.end(), [](const Term& a, const Term& b) { return a.joint < b.joint; });
       const int k = (int)tv.size();
-      if (k == 0) continue;                               // joint with an all-zero regressor row: stays at transl
+      if (k == 0) continue;
       if (k > 32) { err = "a joint depends on more than 32 skinning joints"; return B200SMPL_ERR_INVALID; }
-      int pos = (int)qmeta.size();
-      if (pos % 32 + k > 32) {                            // pad to the next tile
-        while (qmeta.size() % 32) { qmeta.push_back(0u); qcoef.push_back(0.f); }
-        pos = (int)qmeta.size();
-      }
-      const int tile = pos / 32;
-      if (pos % 32 == 0) { vt_j0.push_back(J); vt_nj.push_back(0); prev_joint = -1; }
-      if (vt_j0[tile] + vt_nj[tile] != J) {               // joints of a tile must be consecutive
-        // a skipped (empty) joint in between: extend the range, its columns are written as transl
-        vt_nj[tile] = J - vt_j0[tile];
-      }
-      const int jl = J - vt_j0[tile];
-      if (jl >= 32) { err = "virtual tile joint range overflow"; return B200SMPL_ERR_INVALID; }
-      for (int t = 0; t < k; ++t) {
-        uint32_t mword = (uint32_t)tv[t].joint | ((tv[t].joint != prev_joint ? 1u : 0u) << 5) | ((uint32_t)jl << 8) |
-                         ((t == k - 1 ? 1u : 0u) << 13) | (1u << 14);
-        prev_joint = tv[t].joint;
-        group_slot[tv[t].group] = (int)qmeta.size();
-        qmeta.push_back(mword);
-        qcoef.push_back(tv[t].c);
-      }
-      vt_nj[tile] = jl + 1;
+      if (cur_j0 >= 0 && ((int)cur.size() + k > 32 || J - cur_j0 >= 32)) flush_tile();
+      if (cur_j0 < 0) cur_j0 = J;
+      const int jl = J - cur_j0;                          // joints of a tile are consecutive (gaps stay at transl)
+      for (int t = 0; t < k; ++t) cur.push_back({tv[t].joint, jl, tv[t].group, tv[t].c});
+      cur_nj = jl + 1;
     }
-    while (qmeta.size() % 32) { qmeta.push_back(0u); qcoef.push_back(0.f); }
+    flush_tile();
   }
   const int ntv = (int)qmeta.size() / 32;
   // re-index groups by slot: slot s owns blend rows n_virt0 + 3 s + k

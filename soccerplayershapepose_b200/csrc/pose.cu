@@ -344,8 +344,9 @@ pose_bwd_kernel(DevModel m, const float* __restrict__ betas, const float* __rest
         for (int c = 0; c < 3; ++c) drel[c] = cdrel[c];
       }
       // parent-side gather
-#pragma unroll
-      for (int k = 0; k < MAX_CHILD; ++k) {
+      const int kmax = m.chain.maxchild_at[d];          // warp-uniform: most levels of the SMPL tree have 1
+#pragma unroll 1
+      for (int k = 0; k < kmax; ++k) {
         const int ch = (k < nchild) ? m.chain.child[j][k] : -1;
         const int src = ch < 0 ? 0 : ch;
         const int chd = __shfl_sync(0xffffffffu, depth, src);

@@ -151,22 +151,22 @@ def test_packed_model_emulation_matches_oracle(host_engine, synthetic_model):
         joints2 = np.full((info.num_joints_out, 3), np.nan)
         joints2[:24] = joints[:24]
         for tv in range(len(vt_j0)):
-            acc = trans[b].numpy().copy()
+            # groups of a tile are ordered by skinning joint; every output joint of the tile accumulates its terms
+            accs = np.tile(trans[b].numpy(), (int(vt_nj[tv]), 1)).astype(np.float64)
             cur = -1
             for i in range(32):
                 mw = int(qmeta[tv * 32 + i])
                 if not (mw >> 14) & 1:
                     continue
                 if (mw >> 5) & 1:
+                    assert (mw & 31) > cur or cur == -1      # sorted by skinning joint: each one loaded once
                     cur = mw & 31
                 assert cur == (mw & 31)
+                jl = (mw >> 8) & 31
+                assert jl < vt_nj[tv]
                 row = n_virt0 + 3 * (tv * 32 + i)
-                acc = acc + A[cur] @ np.append(vp[row:row + 3], qcoef[tv * 32 + i])
-                if (mw >> 13) & 1:
-                    jl = (mw >> 8) & 31
-                    assert jl < vt_nj[tv]
-                    joints2[24 + vt_j0[tv] + jl] = acc
-                    acc = trans[b].numpy().copy()
+                accs[jl] = accs[jl] + A[cur] @ np.append(vp[row:row + 3], qcoef[tv * 32 + i])
+            joints2[24 + vt_j0[tv]:24 + vt_j0[tv] + vt_nj[tv]] = accs
         np.testing.assert_allclose(joints2, ref.joints[b].numpy(), atol=2e-7)
 
 
