@@ -1,0 +1,145 @@
+"""Regressor head + multi-task loss around the SMPL layer (BASELINE.json configs[4]).
+
+Mirrors the reference's training step (PlayerReconstruction/PyTorch3DTest.py:1046-1106):
+
+    features -> IEFModule (models/ief_module.py:8-64) -> (cam, pose 6D, shape)
+             -> rot6d_to_rotmat (utils/rigid_transform_utils.py:27-41)           [C-ABI kernel]
+             -> SMPL(body_pose, global_orient, betas, pose2rot=False)            [C-ABI kernels]
+             -> orthographic projection of the joints, COCO map, pixels          [fused C-ABI kernel]
+             -> HomoscedasticUncertaintyWeightedMultiTaskLoss (losses/multi_task_loss.py:92-130)
+             -> backward -> (data-parallel: NCCL all-reduce of the head's gradients) -> Adam
+
+The CNN encoder in front is the caller's (BASELINE.json: "CNN features -> SMPL head"); the head's three linear
+layers are plain library GEMMs (torch.nn.Linear).  The SMPL layer has no parameters, so under
+DistributedDataParallel only the head (and the loss's log-variances) are all-reduced: ~1.9 M floats for the
+reference sizes (fc 1024/1024, 512 input features, 157 outputs).  The SMPL layer and the fused loss need a CUDA
+device; the head and `MultiTaskLoss` themselves are device-agnostic (the CPU tests run them with the oracle).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import config
+
+NUM_OUTPUT_PARAMS = 3 + 24 * 6 + 10
+
+
+def default_mean_params() -> torch.Tensor:
+    """models/ief_module.py:36-48 with the SMPL mean parameters file absent: camera [0.9, 0, 0], identity
+    rotations in the 6D representation (columns (1,0,0),(0,1,0) -> x.view(3,2) = [[1,0],[0,1],[0,0]]), zero shape."""
+    p = np.zeros(NUM_OUTPUT_PARAMS, np.float32)
+    p[0] = 0.9
+    p[3:3 + 24 * 6] = np.tile(np.array([1, 0, 0, 1, 0, 0], np.float32), 24)
+    return torch.from_numpy(p)
+
+
+class IEFModule(nn.Module):
+    """Iterative error feedback head (models/ief_module.py:8-64): same layers, same zero-bias init, same loop."""
+
+    def __init__(self, fc_layers_neurons: Sequence[int] = (1024, 1024), in_features: int = 512,
+                 num_output_params: int = NUM_OUTPUT_PARAMS, iterations: int = 3,
+                 mean_params: Optional[torch.Tensor] = None):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features + num_output_params, fc_layers_neurons[0])
+        self.fc2 = nn.Linear(fc_layers_neurons[0], fc_layers_neurons[1])
+        self.fc3 = nn.Linear(fc_layers_neurons[1], num_output_params)
+        self.relu = nn.ReLU(inplace=True)
+        for fc in (self.fc1, self.fc2, self.fc3):
+            torch.nn.init.zeros_(fc.bias)
+        self.ief_layers = nn.Sequential(self.fc1, self.relu, self.fc2, self.relu, self.fc3)
+        self.iterations = iterations
+        self.register_buffer("initial_params_estimate",
+                             default_mean_params() if mean_params is None else mean_params.float().clone())
+
+    def forward(self, img_features: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        params = self.initial_params_estimate.repeat([img_features.size(0), 1])
+        state = torch.cat([img_features, params], dim=1)
+        for _ in range(self.iterations):
+            params = params + self.ief_layers(state)
+            state = torch.cat([img_features, params], dim=1)
+        return params[:, :3], params[:, 3:3 + 24 * 6], params[:, 3 + 24 * 6:]
+
+
+class MultiTaskLoss(nn.Module):
+    """HomoscedasticUncertaintyWeightedMultiTaskLoss (losses/multi_task_loss.py:16-152) without the silhouette
+    term: MSE(mean) per task * exp(-log_var) + log_var, log_var0 = -log(w + 1e-6), log-variances trainable."""
+
+    TASKS = ("verts", "joints2D", "joints3D", "shape_params", "pose_params")
+
+    def __init__(self, losses_on: Sequence[str], init_loss_weights: Optional[Dict[str, float]] = None, eps: float = 1e-6):
+        super().__init__()
+        self.losses_on = tuple(losses_on)
+        for t in self.losses_on:
+            if t not in self.TASKS:
+                raise ValueError("unsupported loss term: " + t)
+            w = None if init_loss_weights is None else init_loss_weights.get(t)
+            lv = 0.0 if w is None else float(-np.log(w + eps))
+            setattr(self, t + "_log_var", nn.Parameter(torch.tensor(lv).float()))
+
+    def forward(self, labels: Dict[str, torch.Tensor], outputs: Dict[str, torch.Tensor]):
+        total, parts = 0.0, {}
+
+        def add(name, value):
+            nonlocal total
+            lv = getattr(self, name + "_log_var")
+            total = total + value * torch.exp(-lv) + lv
+            parts[name] = value * torch.exp(-lv)
+
+        if "verts" in self.losses_on:
+            add("verts", torch.mean((outputs["verts"] - labels["verts"]) ** 2))
+        if "joints2D" in self.losses_on:
+            lab, pred = labels["joints2D"], outputs["joints2D"]
+            if "vis" in labels:
+                lab, pred = lab[labels["vis"], :], pred[labels["vis"], :]
+            lab = (2.0 * lab) / config.REGRESSOR_IMG_WH - 1.0
+            pred = (2.0 * pred) / config.REGRESSOR_IMG_WH - 1.0
+            add("joints2D", torch.mean((pred - lab) ** 2))
+        if "joints3D" in self.losses_on:
+            add("joints3D", torch.mean((outputs["joints3D"] - labels["joints3D"]) ** 2))
+        if "shape_params" in self.losses_on:
+            add("shape_params", torch.mean((outputs["shape_params"] - labels["shape_params"]) ** 2))
+        if "pose_params" in self.losses_on:
+            add("pose_params", torch.mean((outputs["pose_params_rot_matrices"] - labels["pose_params_rot_matrices"]) ** 2))
+        return total, parts
+
+
+def predict(head: nn.Module, smpl: Callable, features: torch.Tensor, rot6d_to_rotmat: Callable,
+            project_pixels: Callable, need_verts: bool = True) -> Dict[str, torch.Tensor]:
+    """PyTorch3DTest.py:1046-1071: head -> rotation matrices -> SMPL -> COCO joints in 3D and in pixels.
+    `smpl`, `rot6d_to_rotmat` and `project_pixels(joints, cam) -> (B,90,2) pixels` are injected so that the same
+    code runs on the C-ABI kernels (GPU) and on the oracle (CPU tests)."""
+    cam, pose6d, shape = head(features)
+    rotmats = rot6d_to_rotmat(pose6d.contiguous()).view(-1, 24, 3, 3)
+    out = smpl(body_pose=rotmats[:, 1:], global_orient=rotmats[:, 0].unsqueeze(1), betas=shape, pose2rot=False,
+               return_verts=need_verts)
+    joints2d = project_pixels(out.joints, cam)[:, config.SMPL_TO_KPRCNN_MAP, :]
+    return {"joints2D": joints2d, "verts": out.vertices if need_verts else None, "shape_params": shape,
+            "pose_params_rot_matrices": rotmats, "joints3D": out.joints[:, config.ALL_JOINTS_TO_COCO_MAP, :],
+            "cam": cam}
+
+
+def train_step(head: nn.Module, criterion: MultiTaskLoss, optimiser: torch.optim.Optimizer, smpl: Callable,
+               features: torch.Tensor, labels: Dict[str, torch.Tensor], rot6d_to_rotmat: Callable,
+               project_pixels: Callable) -> torch.Tensor:
+    """One optimisation step (PyTorch3DTest.py:1097-1102).  When `head` / `criterion` are wrapped in
+    DistributedDataParallel the backward all-reduces their gradients (NCCL on the GPUs)."""
+    optimiser.zero_grad(set_to_none=True)
+    outputs = predict(head, smpl, features, rot6d_to_rotmat, project_pixels, need_verts="verts" in _tasks(criterion))
+    loss, _ = criterion(labels, outputs)
+    loss.backward()
+    optimiser.step()
+    return loss.detach()
+
+
+def _tasks(criterion) -> Sequence[str]:
+    return getattr(criterion, "module", criterion).losses_on
+
+
+def gpu_ops():
+    """The C-ABI-backed implementations to inject on a CUDA device."""
+    from . import ops
+    return ops.rot6d_to_rotmat, (lambda joints, cam: ops.orthographic_project(joints, cam, 512.0))
