@@ -302,6 +302,172 @@ umma_gemm_kernel(const __grid_constant__ GemmOps ops, int nseg, int nc8, int sla
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same GEMM on a CTA PAIR (tcgen05 cta_group::2, cluster of 2 along the body tiles): M = 256 bodies (128
+// per CTA, each CTA streams its own dvp tile and accumulates into its own TMEM), the B operand (Wb slab,
+// BN x 64) is split -- each CTA loads and holds BN/2 rows, the pair's tensor cores read both halves -- which
+// halves the per-SM shared-memory write and read traffic of B, the bound of the single-CTA kernel.
+// Only the leader (rank 0) issues MMAs; it waits for its own stage and, through a relayed remote arrive, for
+// the peer's; its commits are multicast to the barriers of both CTAs.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void remote_arrive(uint64_t* local_bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_bar)), "r"(cta));
+  // relaxed: the payload was written by the TMA (async proxy) and is consumed by the tensor core (async proxy);
+  // a cluster-scope release here costs a full membar per stage and serialises the pipeline
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+umma_gemm2_kernel(const __grid_constant__ GemmOps ops, int nseg, int nc8, int slab_begin, int slab_end,
+                  int slabs_per_split, float* __restrict__ D, int ldd, long long split_stride) {
+  constexpr int BNH = BN / 2;
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 256;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* peer_full_bar = full_bar + STAGES;
+  uint64_t* empty_bar = peer_full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int m0 = blockIdx.x * BM;
+  const int s_begin = slab_begin + blockIdx.z * slabs_per_split;
+  const int s_end = min(slab_end, s_begin + slabs_per_split);
+  const int slabs = max(0, s_end - s_begin);
+  const int total_iters = slabs * nseg;
+
+  if (warp == 0 && lane == 0)
+    for (int s = 0; s < nseg; ++s) prefetch_tmap(&ops.b[s]);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&peer_full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer (both CTAs): own dvp tile + own half of the Wb slab =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < total_iters; ++it) {
+      const int seg = it / slabs, slab = s_begin + (it - seg * slabs);
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      unsigned char* sa = smem + stage * STAGE_BYTES;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+        bulk_g2s(sa, ops.a[seg] + (((size_t)blockIdx.x * nc8 + (size_t)slab * 8) * 128) * 8, A_BYTES, &full_bar[stage]);
+        tma_load_2d(sa + A_BYTES, &ops.b[seg], &full_bar[stage], slab * BK, (int)rank * BNH);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    if (rank == 0) {
+      // ===== leader: MMA issuer for the pair =====
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN);
+      for (int it = 0; it < total_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&peer_full_bar[stage], phase);                   // remote arrive (release.cluster) of the peer's relay
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t da = make_nosw_desc(sa, 2048, 128), db = make_sw128_desc(sa + A_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_2cta(tmem_base, da + (uint64_t)(k * (4096 >> 4)), db + 2 * k, idesc, (it | k) != 0);
+          umma_commit_2cta(&empty_bar[stage]);
+          if (it == total_iters - 1) umma_commit_2cta(tmem_full_bar);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    } else {
+      // ===== peer: tell the leader when this CTA's stage has landed =====
+      for (int it = 0; it < total_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        if (elect_one()) remote_arrive(&peer_full_bar[stage], 0);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) of this CTA's 128 bodies =====
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    float* drow = D + (long long)blockIdx.z * split_stride + (long long)row * ldd;
+    if (total_iters > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        float* o = drow + c0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(o + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 4) *reinterpret_cast<uint4*>(drow + c0) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Forward blend GEMM, W-stationary.  A CTA keeps its 128-row slice of the model operand (all K: 9 x 16 KB)
 // resident in shared memory and streams only the feature tiles of its share of the bodies through a
 // 5-stage ring (the stream is latency-bound: bytes in flight decide the rate), accumulating in two
@@ -568,11 +734,18 @@ int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat
 }
 
 // number of split-K partials the backward GEMM writes for slab width S
+// CTA-pair kernels are the default; B200_BWD_2CTA=0 selects the single-CTA kernel (kept for comparison)
+static bool bwd_use_2cta() {
+  static const bool v = getenv("B200_BWD_2CTA") == nullptr || atoi(getenv("B200_BWD_2CTA")) != 0;
+  return v;
+}
+
 int blend_bwd_umma_splits(const DevModel& m, int mode, int S, int num_sms) {
   (void)mode;
   const int mtiles = (S + BM - 1) / BM;
   const int slabs = (m.n_rows + BK - 1) / BK;
-  int want = (num_sms + mtiles - 1) / mtiles;
+  // CTA pairs are scheduled per TPC (2 SMs): never more pairs than TPCs, or a second, nearly empty wave runs
+  int want = bwd_use_2cta() ? std::max(1, num_sms / mtiles) : (num_sms + mtiles - 1) / mtiles;
   want = std::max(1, std::min(want, slabs / 8));
   return want;
 }
@@ -588,6 +761,40 @@ static int launch_bwd_bn(const GemmOps& ops, int nseg, int nc8, int slab_begin, 
   dim3 grid(Sw / BM, 1, nsplit);
   LaunchTimer _timer_316("blend_bwd_umma", st);
   kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(ops, nseg, nc8, slab_begin, slab_end, sps, dfeat_part, nf_pad, split_stride);
+  B200_LAUNCH_CHECK("blend_bwd_umma");
+  return 0;
+}
+
+template <int BN>
+static int launch_bwd_bn_2cta(GemmOps& ops, const DevModel& m, int nseg, int row_end, int slab_begin, int slab_end,
+                              int nsplit, int Sw, float* dfeat_part, int nf_pad, long long split_stride, cudaStream_t st) {
+  constexpr int STAGES2 = 6;
+  constexpr int smem = STAGES2 * (BM * BK * 2 + (BN / 2) * BK * 2) + 1024 + 256;
+  // every CTA loads BN/2 rows of the Wb slab: tensor maps with that box height
+  int rc;
+  const __nv_bfloat16* bsrc[MAX_SEG] = {m.Wb_hi, m.Wb_hi, m.Wb_lo};
+  for (int s = 0; s < nseg; ++s)
+    if ((rc = make_map(&ops.b[s], bsrc[s], row_end, nf_pad, m.n_pad, BN / 2))) return rc;
+  auto kern = umma_gemm2_kernel<BN, STAGES2>;
+  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int slabs = slab_end - slab_begin;
+  const int sps = (slabs + nsplit - 1) / nsplit;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(Sw / BM, 1, nsplit);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LaunchTimer _timer("blend_bwd_umma", st);
+  B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ops, nseg, m.n_pad / 8, slab_begin, slab_end, sps, dfeat_part, nf_pad,
+                                   split_stride));
   B200_LAUNCH_CHECK("blend_bwd_umma");
   return 0;
 }
@@ -614,6 +821,8 @@ int launch_blend_bwd_umma(const DevModel& m, int mode, const __nv_bfloat16* dvp_
   }
   const int slab_begin = row_begin / BK, slab_end = (row_end + BK - 1) / BK;
   const long long split_stride = (long long)S * nf_pad;
+  if (bwd_use_2cta() && nf_pad == 224 && (Sw / BM) % 2 == 0)
+    return launch_bwd_bn_2cta<224>(ops, m, nseg, row_end, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
   switch (nf_pad) {
     case 224: return launch_bwd_bn<224>(ops, nseg, m.n_pad / 8, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
     case 208: return launch_bwd_bn<208>(ops, nseg, m.n_pad / 8, slab_begin, slab_end, nsplit, Sw, dfeat_part, nf_pad, split_stride, st);
