@@ -345,19 +345,25 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
-template <int BN, int STAGES>
+// One stage = one 64-row K slab with everything the split needs, each loaded ONCE: dvp_hi (and dvp_lo) tiles of
+// this CTA's 128 bodies, this CTA's half of the Wb_hi (and Wb_lo) slab; the three products hi.hi, lo.hi, hi.lo
+// are issued back to back on the resident tiles (fp32 mode: 60 KB per stage, 3 stages; bf16 mode: 30 KB, 6).
+template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-umma_gemm2_kernel(const __grid_constant__ GemmOps ops, int nseg, int nc8, int slab_begin, int slab_end,
+umma_gemm2_kernel(const __grid_constant__ GemmOps ops, int split3, int nc8, int slab_begin, int slab_end,
                   int slabs_per_split, float* __restrict__ D, int ldd, long long split_stride) {
   constexpr int BNH = BN / 2;
-  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2;
+  constexpr int MAX_STAGES = 6;
   constexpr uint32_t TMEM_COLS = 256;
+  const int stage_bytes = (split3 ? 2 : 1) * (A_BYTES + B_BYTES);
+  const int nstages = split3 ? 3 : 6;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* peer_full_bar = full_bar + STAGES;
-  uint64_t* empty_bar = peer_full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + MAX_STAGES * (A_BYTES + B_BYTES));
+  uint64_t* peer_full_bar = full_bar + MAX_STAGES;
+  uint64_t* empty_bar = peer_full_bar + MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -365,13 +371,14 @@ umma_gemm2_kernel(const __grid_constant__ GemmOps ops, int nseg, int nc8, int sl
   const int m0 = blockIdx.x * BM;
   const int s_begin = slab_begin + blockIdx.z * slabs_per_split;
   const int s_end = min(slab_end, s_begin + slabs_per_split);
-  const int slabs = max(0, s_end - s_begin);
-  const int total_iters = slabs * nseg;
+  const int total_iters = max(0, s_end - s_begin);
 
-  if (warp == 0 && lane == 0)
-    for (int s = 0; s < nseg; ++s) prefetch_tmap(&ops.b[s]);
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&ops.b[0]);
+    if (split3) prefetch_tmap(&ops.b[2]);
+  }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < MAX_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&peer_full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -389,22 +396,29 @@ umma_gemm2_kernel(const __grid_constant__ GemmOps ops, int nseg, int nc8, int sl
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // stage layout: [A_hi | B_hi | A_lo | B_lo]
+  const int off_bhi = A_BYTES, off_alo = A_BYTES + B_BYTES, off_blo = 2 * A_BYTES + B_BYTES;
 
   if (warp == 0) {
-    // ===== producer (both CTAs): own dvp tile + own half of the Wb slab =====
+    // ===== producer (both CTAs): own dvp tiles + own halves of the Wb slabs =====
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < total_iters; ++it) {
-      const int seg = it / slabs, slab = s_begin + (it - seg * slabs);
+      const int slab = s_begin + it;
       mbar_wait(&empty_bar[stage], phase ^ 1);
-      unsigned char* sa = smem + stage * STAGE_BYTES;
+      unsigned char* sa = smem + stage * stage_bytes;
       if (elect_one()) {
-        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-        bulk_g2s(sa, ops.a[seg] + (((size_t)blockIdx.x * nc8 + (size_t)slab * 8) * 128) * 8, A_BYTES, &full_bar[stage]);
-        tma_load_2d(sa + A_BYTES, &ops.b[seg], &full_bar[stage], slab * BK, (int)rank * BNH);
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+        const size_t aoff = (((size_t)blockIdx.x * nc8 + (size_t)slab * 8) * 128) * 8;
+        bulk_g2s(sa, ops.a[0] + aoff, A_BYTES, &full_bar[stage]);
+        tma_load_2d(sa + off_bhi, &ops.b[0], &full_bar[stage], slab * BK, (int)rank * BNH);
+        if (split3) {
+          bulk_g2s(sa + off_alo, ops.a[1] + aoff, A_BYTES, &full_bar[stage]);
+          tma_load_2d(sa + off_blo, &ops.b[2], &full_bar[stage], slab * BK, (int)rank * BNH);
+        }
       }
       __syncwarp();
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == nstages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     int stage = 0;
@@ -414,19 +428,29 @@ umma_gemm2_kernel(const __grid_constant__ GemmOps ops, int nseg, int nc8, int sl
       constexpr uint32_t idesc = make_idesc(2 * BM, BN);
       for (int it = 0; it < total_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
-        mbar_wait(&peer_full_bar[stage], phase);                   // remote arrive (release.cluster) of the peer's relay
+        mbar_wait(&peer_full_bar[stage], phase);                   // relaxed remote arrive of the peer's relay
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint64_t da = make_nosw_desc(sa, 2048, 128), db = make_sw128_desc(sa + A_BYTES);
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint64_t da_hi = make_nosw_desc(sa, 2048, 128), db_hi = make_sw128_desc(sa + off_bhi);
+        const uint64_t da_lo = make_nosw_desc(sa + off_alo, 2048, 128), db_lo = make_sw128_desc(sa + off_blo);
         if (elect_one()) {
+          // A: two 16-byte chunks per UMMA_K -> +4096 B; B: +32 bytes inside the swizzle row (16-byte units)
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16_2cta(tmem_base, da + (uint64_t)(k * (4096 >> 4)), db + 2 * k, idesc, (it | k) != 0);
+            umma_bf16_2cta(tmem_base, da_hi + (uint64_t)(k * (4096 >> 4)), db_hi + 2 * k, idesc, (it | k) != 0);
+          if (split3) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16_2cta(tmem_base, da_lo + (uint64_t)(k * (4096 >> 4)), db_hi + 2 * k, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16_2cta(tmem_base, da_hi + (uint64_t)(k * (4096 >> 4)), db_lo + 2 * k, idesc, 1u);
+          }
           umma_commit_2cta(&empty_bar[stage]);
           if (it == total_iters - 1) umma_commit_2cta(tmem_full_bar);
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
     } else {
       // ===== peer: tell the leader when this CTA's stage has landed =====
@@ -434,7 +458,7 @@ umma_gemm2_kernel(const __grid_constant__ GemmOps ops, int nseg, int nc8, int sl
         mbar_wait(&full_bar[stage], phase);
         if (elect_one()) remote_arrive(&peer_full_bar[stage], 0);
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -1015,14 +1039,13 @@ static int launch_bwd_bn(const GemmOps& ops, int nseg, int nc8, int slab_begin, 
 template <int BN>
 static int launch_bwd_bn_2cta(GemmOps& ops, const DevModel& m, int nseg, int row_end, int slab_begin, int slab_end,
                               int nsplit, int Sw, float* dfeat_part, int nf_pad, long long split_stride, cudaStream_t st) {
-  constexpr int STAGES2 = 6;
-  constexpr int smem = STAGES2 * (BM * BK * 2 + (BN / 2) * BK * 2) + 1024 + 256;
+  constexpr int smem = 6 * (BM * BK * 2 + (BN / 2) * BK * 2) + 1024 + 512;
   // every CTA loads BN/2 rows of the Wb slab: tensor maps with that box height
   int rc;
   const __nv_bfloat16* bsrc[MAX_SEG] = {m.Wb_hi, m.Wb_hi, m.Wb_lo};
   for (int s = 0; s < nseg; ++s)
     if ((rc = make_map(&ops.b[s], bsrc[s], row_end, nf_pad, m.n_pad, BN / 2))) return rc;
-  auto kern = umma_gemm2_kernel<BN, STAGES2>;
+  auto kern = umma_gemm2_kernel<BN>;
   B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int slabs = slab_end - slab_begin;
   const int sps = (slabs + nsplit - 1) / nsplit;
@@ -1040,8 +1063,8 @@ static int launch_bwd_bn_2cta(GemmOps& ops, const DevModel& m, int nseg, int row
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   LaunchTimer _timer("blend_bwd_umma", st);
-  B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ops, nseg, m.n_pad / 8, slab_begin, slab_end, sps, dfeat_part, nf_pad,
-                                   split_stride));
+  B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ops, nseg == 3 ? 1 : 0, m.n_pad / 8, slab_begin, slab_end, sps, dfeat_part,
+                                   nf_pad, split_stride));
   B200_LAUNCH_CHECK("blend_bwd_umma");
   return 0;
 }
