@@ -286,7 +286,8 @@ umma_gemm_kernel(const __grid_constant__ GemmOps ops, int nseg, int nc8, int sla
         float* o = drow + c0;
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<uint4*>(o + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          if (c0 + i < BN)                         // BN is a multiple of 16, not of 32: the last block may be half
+            *reinterpret_cast<uint4*>(o + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
     } else {
 #pragma unroll 1
@@ -476,7 +477,8 @@ umma_gemm2_kernel(const __grid_constant__ GemmOps ops, int split3, int nc8, int 
         float* o = drow + c0;
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<uint4*>(o + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          if (c0 + i < BN)                         // BN is a multiple of 16, not of 32: the last block may be half
+            *reinterpret_cast<uint4*>(o + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
     } else {
 #pragma unroll 1

@@ -262,3 +262,35 @@ def test_full_size_properties(engine, dev, mode):
     gb = engine.backward(betas[sl], pose_aa[sl], trans[sl], None, None, 2 * dV, 2 * dJ, None, axis_angle=True, mode=m)
     for a, b in zip(ga[:3], gb[:3]):
         assert _rel(b, 2 * a) < (1e-5 if mode == "fp32" else 2e-2)
+
+
+@pytest.mark.parametrize("nb,B", [(1, 37), (4, 130), (16, 256)])
+def test_other_beta_counts_and_tile_counts(synthetic_model, dev, nb, B):
+    """Models with another number of betas (other K layouts / gradient widths: nf_pad 208 takes the single-CTA
+    gradient GEMM, 224 the CTA-pair one) at batch sizes with an odd (37 -> 1), even (130 -> 2, 256 -> 2) number
+    of 128-body tiles: forward and backward against the oracle."""
+    model = dict(synthetic_model)
+    sd = synthetic_model["shapedirs"]
+    if nb <= sd.shape[2]:
+        model["shapedirs"] = np.ascontiguousarray(sd[:, :, :nb])
+    else:
+        rng = np.random.default_rng(7)
+        model["shapedirs"] = np.concatenate([sd, (rng.standard_normal((sd.shape[0], 3, nb - sd.shape[2])) * 0.002).astype(np.float32)], 2)
+    eng = SMPLEngine(model, dev)
+    orc = O.SMPLOracle(model, dtype=torch.float64)
+    g = torch.Generator().manual_seed(11 + nb)
+    betas = torch.randn(B, nb, generator=g)
+    pose = rotmats_of(torch.randn(B, 72, generator=g) * 0.3)
+    trans = torch.rand(B, 3, generator=g)
+    dV = torch.randn(B, 6890, 3, generator=g)
+    dJ = torch.randn(B, 90, 3, generator=g)
+    rb, rp, rt, _ = _oracle_grads(orc, betas, pose, trans, None, dV, dJ, None, False)
+    ref = orc.forward_flat(betas.double(), pose.double(), trans.double(), pose2rot=False)
+    d = lambda x: x.to(dev)  # noqa: E731
+    v, j, _ = eng.forward(d(betas), d(pose), d(trans), None, mode=_lib.MODES["fp32"])
+    assert (v.cpu().double() - ref.vertices).abs().max().item() < POS_TOL["fp32"]
+    assert (j.cpu().double() - ref.joints).abs().max().item() < POS_TOL["fp32"]
+    gb, gp, gt, _ = eng.backward(d(betas), d(pose), d(trans), None, None, d(dV), d(dJ), None, mode=_lib.MODES["fp32"])
+    assert _rel(gb.cpu().double(), rb) < GRAD_TOL["fp32"]
+    assert _rel(gp.cpu().double().reshape(rp.shape), rp) < GRAD_TOL["fp32"]
+    assert _rel(gt.cpu().double(), rt) < GRAD_TOL["fp32"]
