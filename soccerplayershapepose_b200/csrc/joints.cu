@@ -26,6 +26,14 @@ __device__ __forceinline__ void load_q96(float (&q)[96], const float4* __restric
     q[i * 4] = v.x; q[i * 4 + 1] = v.y; q[i * 4 + 2] = v.z; q[i * 4 + 3] = v.w;
   }
 }
+// 8 q-groups = 24 rows = 6 float4 of one body
+__device__ __forceinline__ void load_q24(float (&q)[24], const float4* __restrict__ p) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float4 v = ld_stream4(p + i * 32);
+    q[i * 4] = v.x; q[i * 4 + 1] = v.y; q[i * 4 + 2] = v.z; q[i * 4 + 3] = v.w;
+  }
+}
 // transforms from the shared-memory copy of the group (paired layout, skin_common.cuh)
 __device__ __forceinline__ void load_slot_s(float (&a)[AELEMS], const float* A_s, int joint, int lane) {
   const float4* p = reinterpret_cast<const float4*>(A_s) + joint * 96 + lane;
@@ -33,7 +41,7 @@ __device__ __forceinline__ void load_slot_s(float (&a)[AELEMS], const float* A_s
 }
 
 // dynamic shared memory: A_s [24][3][32] float4 | JW staging tiles [32][pitch] | mbarrier
-__global__ void __launch_bounds__(JT, 2)
+__global__ void __launch_bounds__(JT, 3)
 joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const float4* __restrict__ A_blk, int b0, int nb,
                   int pitch, const float* __restrict__ transl, float* __restrict__ joints) {
   extern __shared__ __align__(128) float smem[];
@@ -54,8 +62,9 @@ joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
   const int nrows = min(32, nb - g * 32);
   bool waited = false;
   for (int tv = blockIdx.y * JW + warp; tv < m.ntv; tv += JW * gridDim.y) {
-    float q[96];
-    load_q96(q, vpB + ((size_t)g * nc4 + (m.ntiles + tv) * 24) * 32 + lane);
+    const float4* qp = vpB + ((size_t)g * nc4 + (m.ntiles + tv) * 24) * 32 + lane;
+    float qa[24], qb[24];                                    // q rows, 8 groups at a time, one block ahead
+    load_q24(qa, qp);
     const uint32_t mt_l = __ldg(m.qmeta + tv * 32 + lane);   // lane i holds the plan of q-group i
     const float c_l = __ldg(m.qcoef + tv * 32 + lane);
     if (!waited) { mbar_wait(bar, 0); waited = true; }
@@ -64,16 +73,22 @@ joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
     for (int c = 0; c < ncols; c += 3) { my_row[c] = tx; my_row[c + 1] = ty; my_row[c + 2] = tz; }
     float a[AELEMS];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const uint32_t mt = __shfl_sync(0xffffffffu, mt_l, i);
-      if (!(mt & (1u << 14))) continue;
-      if (mt & (1u << 5)) load_slot_s(a, A_s, mt & 31, lane);       // groups are sorted by skinning joint
-      const float c = __shfl_sync(0xffffffffu, c_l, i);
-      const float qx = q[i * 3], qy = q[i * 3 + 1], qz = q[i * 3 + 2];
-      float* o = my_row + ((mt >> 8) & 31) * 3;
-      o[0] += fmaf(a[0], qx, fmaf(a[1], qy, fmaf(a[2], qz, a[3] * c)));
-      o[1] += fmaf(a[4], qx, fmaf(a[5], qy, fmaf(a[6], qz, a[7] * c)));
-      o[2] += fmaf(a[8], qx, fmaf(a[9], qy, fmaf(a[10], qz, a[11] * c)));
+    for (int blk = 0; blk < 4; ++blk) {
+      float (&q)[24] = (blk & 1) ? qb : qa;
+      if (blk < 3) load_q24((blk & 1) ? qa : qb, qp + (blk + 1) * 6 * 32);
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        const int i = blk * 8 + ii;
+        const uint32_t mt = __shfl_sync(0xffffffffu, mt_l, i);
+        if (!(mt & (1u << 14))) continue;
+        if (mt & (1u << 5)) load_slot_s(a, A_s, mt & 31, lane);       // groups are sorted by skinning joint
+        const float c = __shfl_sync(0xffffffffu, c_l, i);
+        const float qx = q[ii * 3], qy = q[ii * 3 + 1], qz = q[ii * 3 + 2];
+        float* o = my_row + ((mt >> 8) & 31) * 3;
+        o[0] += fmaf(a[0], qx, fmaf(a[1], qy, fmaf(a[2], qz, a[3] * c)));
+        o[1] += fmaf(a[4], qx, fmaf(a[5], qy, fmaf(a[6], qz, a[7] * c)));
+        o[2] += fmaf(a[8], qx, fmaf(a[9], qy, fmaf(a[10], qz, a[11] * c)));
+      }
     }
     __syncwarp();
     // flush the tile's joints: 3 nj contiguous floats per body row
@@ -88,7 +103,7 @@ joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
 
 // backward over virtual tiles.  dJ: total joint gradient (B, NJout, 3).
 //   dq -> virtual rows of dvp ; dA, dtransl -> fp32 REDs into the slab accumulators
-__global__ void __launch_bounds__(JT, 2)
+__global__ void __launch_bounds__(JT, 3)
 joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const float4* __restrict__ A_blk, int b0, int nb,
                   int pitch, const float* __restrict__ dJ, __nv_bfloat16* __restrict__ dvp_hi,
                   __nv_bfloat16* __restrict__ dvp_lo, float* __restrict__ dA_acc, float* __restrict__ dtr_acc) {
@@ -107,8 +122,9 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
   float sx = 0.f, sy = 0.f, sz = 0.f;
   bool waited = false;
   for (int tv = blockIdx.y * JW + warp; tv < m.ntv; tv += JW * gridDim.y) {
-    float q[96];
-    load_q96(q, vpB + ((size_t)g * nc4 + (m.ntiles + tv) * 24) * 32 + lane);
+    const float4* qp = vpB + ((size_t)g * nc4 + (m.ntiles + tv) * 24) * 32 + lane;
+    float qa[24], qb[24];                                    // q rows, 8 groups at a time, one block ahead
+    load_q24(qa, qp);
     const uint32_t mt_l = __ldg(m.qmeta + tv * 32 + lane);
     const float c_l = __ldg(m.qcoef + tv * 32 + lane);
     const int ncols = m.vt_nj[tv] * 3;
@@ -133,6 +149,8 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
     __nv_bfloat16* lo_p = dvp_lo ? dvp_lo + (chunk0 * 128 + (g & 3) * 32 + lane) * 8 : nullptr;
 #pragma unroll
     for (int blk = 0; blk < 4; ++blk) {                    // 8 q-groups = 24 rows = 3 chunks of dvp
+      float (&q)[24] = (blk & 1) ? qb : qa;
+      if (blk < 3) load_q24((blk & 1) ? qa : qb, qp + (blk + 1) * 6 * 32);
       float dq[24];
 #pragma unroll
       for (int ii = 0; ii < 8; ++ii) {
@@ -150,7 +168,7 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
         const float c = __shfl_sync(0xffffffffu, c_l, i);
         const float* gj = my_row + ((mt >> 8) & 31) * 3;
         const float gx = gj[0], gy = gj[1], gz = gj[2];
-        const float qx = q[i * 3], qy = q[i * 3 + 1], qz = q[i * 3 + 2];
+        const float qx = q[ii * 3], qy = q[ii * 3 + 1], qz = q[ii * 3 + 2];
         dq[ii * 3] = fmaf(a[0], gx, fmaf(a[4], gy, a[8] * gz));
         dq[ii * 3 + 1] = fmaf(a[1], gx, fmaf(a[5], gy, a[9] * gz));
         dq[ii * 3 + 2] = fmaf(a[2], gx, fmaf(a[6], gy, a[10] * gz));
