@@ -19,13 +19,6 @@ namespace b200smpl {
 constexpr int JW = 8;                       // warps per CTA; one CTA per body group, warps stride over the virtual tiles
 constexpr int JT = JW * 32;
 
-__device__ __forceinline__ void load_q96(float (&q)[96], const float4* __restrict__ p) {
-#pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    const float4 v = ld_stream4(p + i * 32);
-    q[i * 4] = v.x; q[i * 4 + 1] = v.y; q[i * 4 + 2] = v.z; q[i * 4 + 3] = v.w;
-  }
-}
 // 8 q-groups = 24 rows = 6 float4 of one body
 __device__ __forceinline__ void load_q24(float (&q)[24], const float4* __restrict__ p) {
 #pragma unroll

@@ -17,8 +17,6 @@
 namespace b200smpl {
 
 constexpr int AG_WORDS = NJ * AELEMS * 32;       // 9216 floats = 36 KB: one group's skinning transforms
-constexpr int TROW = 100;                        // staging tile [32 bodies][100]: 96 floats + 4 pad; rows stay 16-byte
-constexpr int TTILE_WORDS = 32 * TROW;           // aligned and (25 * lane + k) % 8 spreads a quarter-warp over all banks
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -146,16 +144,6 @@ __device__ __forceinline__ void unpack_transform(float (&a)[AELEMS], const float
   a[0] = q0.x; a[4] = q0.y; a[1] = q0.z; a[5] = q0.w;
   a[2] = q1.x; a[6] = q1.y; a[3] = q1.z; a[7] = q1.w;
   a[8] = q2.x; a[9] = q2.y; a[10] = q2.z; a[11] = q2.w;
-}
-__device__ __forceinline__ void load_slot_g(float (&a)[AELEMS], const float4* A_g, int joint, int lane) {
-  const float4* p = A_g + joint * 96 + lane;
-  unpack_transform(a, __ldg(p), __ldg(p + 32), __ldg(p + 64));
-}
-__device__ __forceinline__ void load_rot_g(float (&a)[9], const float4* A_g, int joint, int lane) {
-  const float4* p = A_g + joint * 96 + lane;
-  const float4 q0 = __ldg(p), q1 = __ldg(p + 32), q2 = __ldg(p + 64);
-  a[0] = q0.x; a[3] = q0.y; a[1] = q0.z; a[4] = q0.w; a[2] = q1.x; a[5] = q1.y;
-  a[6] = q2.x; a[7] = q2.y; a[8] = q2.z;
 }
 // add a slot's gradient accumulators into the group's dA rows [joint * 12 + e][32] and clear them
 __device__ __forceinline__ void flush_slot_g(float (&d)[AELEMS], float* dA_g, int joint, int lane) {

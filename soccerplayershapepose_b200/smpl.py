@@ -145,6 +145,19 @@ class SMPL(nn.Module):
         return out
 
 
+    def silhouette_inputs(self, vertices: torch.Tensor, cam_wp: torch.Tensor, proj_wh: float = 512.0) -> Dict:
+        """Hand-off to a differentiable rasteriser in the layout the reference feeds its neural renderer
+        (player_recon.py:288-289, 686-697): `vertices` (B,6890,3) fp32 contiguous as the skinning kernel wrote them,
+        `faces` (B,13776,3) float (the int32 topology cast to float and repeated per body), `t` (B,1,3) camera
+        translation from the weak-perspective camera (cam_utils.py:44-52).  No copy of the vertices is made."""
+        from . import config
+        from .cam_utils import convert_weak_perspective_to_camera_translation_torch
+        B = vertices.shape[0]
+        faces = torch.from_numpy(self.faces.astype(np.int32)).float().to(vertices.device)
+        t = convert_weak_perspective_to_camera_translation_torch(cam_wp, config.FOCAL_LENGTH, proj_wh)
+        return {"vertices": vertices.contiguous(), "faces": faces[None].expand(B, -1, -1), "t": t.unsqueeze(1)}
+
+
 class SMPLLayer(SMPL):
     """north_star surface: forward(betas, pose, trans) -> (vertices, joints).
     pose: (B,24,3,3) rotation matrices, or (B,72) axis-angle (detected from the shape)."""

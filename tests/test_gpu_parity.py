@@ -294,3 +294,17 @@ def test_other_beta_counts_and_tile_counts(synthetic_model, dev, nb, B):
     assert _rel(gb.cpu().double(), rb) < GRAD_TOL["fp32"]
     assert _rel(gp.cpu().double().reshape(rp.shape), rp) < GRAD_TOL["fp32"]
     assert _rel(gt.cpu().double(), rt) < GRAD_TOL["fp32"]
+
+
+def test_silhouette_handoff_layout(synthetic_model, dev):
+    """player_recon.py:288-289, 694-697: vertices (B,6890,3), faces (B,F,3) float, t (B,1,3)."""
+    smpl = SMPL(model_data=synthetic_model).to(dev)
+    betas, pose, trans, cam = make_inputs(3, 2)
+    rot = rotmats_of(pose).to(dev)
+    out = smpl(betas=betas.to(dev), body_pose=rot[:, 1:], global_orient=rot[:, :1], pose2rot=False)
+    h = smpl.silhouette_inputs(out.vertices, cam.to(dev))
+    assert h["vertices"].data_ptr() == out.vertices.data_ptr() and h["vertices"].shape == (3, 6890, 3)
+    assert h["faces"].shape == (3, smpl.faces.shape[0], 3) and h["faces"].dtype == torch.float32
+    assert np.array_equal(h["faces"][1].cpu().numpy().astype(np.int64), smpl.faces.astype(np.int64))
+    t = O.weak_perspective_to_translation(cam.double(), 5000.0, 512)
+    assert h["t"].shape == (3, 1, 3) and np.allclose(h["t"][:, 0].cpu().double().numpy(), t.numpy(), rtol=1e-5)
