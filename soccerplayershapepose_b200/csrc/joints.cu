@@ -124,9 +124,19 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
     // stage the gradients of this tile's joints (3 nj floats of each body row)
     {
       const float* src0 = dJ + (size_t)(b0 + g * 32) * ncol_all + (size_t)(NJ + m.vt_j0[tv]) * 3;
-      for (int idx = lane; idx < 32 * ncols; idx += 32) {
-        const int r = idx / ncols, c = idx - r * ncols;
-        tile[r * pitch + c] = (r < nrows) ? ld_stream(src0 + (size_t)r * ncol_all + c) : 0.f;
+      for (int k0 = 0; k0 < ncols; k0 += 4) {               // 32 * ncols elements, four loads in flight per lane
+        float v[4];
+        int so[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = (k0 + u) * 32 + lane;
+          const int r = idx / ncols, c = idx - r * ncols;
+          so[u] = (k0 + u < ncols) ? r * pitch + c : -1;
+          v[u] = (k0 + u < ncols && r < nrows) ? ld_stream(src0 + (size_t)r * ncol_all + c) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (so[u] >= 0) tile[so[u]] = v[u];
       }
     }
     if (!waited) { mbar_wait(bar, 0); waited = true; }
