@@ -317,28 +317,57 @@ def main():
                               for r in [kernel_roofline(k)] if r is not None}
 
     # ---- end to end through the public module API, host buffers in, gradients out ----
+    # Every step copies ITS inputs from pinned host memory and ITS gradients back to pinned host memory; as in any
+    # input pipeline the copies run on their own streams (double-buffered), so the H2D of step i+1 and the D2H of
+    # step i-1 overlap the kernels of step i.  The timed region ends when the last step's gradients are on the host.
     hb, hr, ht = (x.cpu().pin_memory() for x in (betas, rot, trans))
-    gb_h = torch.empty((B, 10)).pin_memory()
-    gr_h = torch.empty((B, 24, 3, 3)).pin_memory()
-    gt_h = torch.empty((B, 3)).pin_memory()
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    d_in = [[torch.empty_like(x, device=dev) for x in (hb, hr, ht)] for _ in range(2)]
+    h_out = [[torch.empty((B, 10)).pin_memory(), torch.empty((B, 24, 3, 3)).pin_memory(), torch.empty((B, 3)).pin_memory()]
+             for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_used = [torch.cuda.Event() for _ in range(2)]
+    ev_grad = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step():
-        b = hb.to(dev, non_blocking=True).requires_grad_(True)
-        r = hr.to(dev, non_blocking=True).requires_grad_(True)
-        tt = ht.to(dev, non_blocking=True).requires_grad_(True)
-        v, j = layer(b, r, tt)
-        torch.autograd.backward([v, j], [dV, dJ])
-        gb_h.copy_(b.grad, non_blocking=True)
-        gr_h.copy_(r.grad, non_blocking=True)
-        gt_h.copy_(tt.grad, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()       # the step's result is on the host
+    def prefetch(i):
+        k = i & 1
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_used[k])                    # the step that read this slot has finished with it
+            for dst, src in zip(d_in[k], (hb, hr, ht)):
+                dst.copy_(src, non_blocking=True)
+            ev_in[k].record(s_in)
 
-    for _ in range(3):
-        e2e_step()
+    def e2e_run(n):
+        for k in range(2):
+            ev_used[k].record(cur)
+            ev_out[k].record(s_out)
+        prefetch(0)
+        for i in range(n):
+            k = i & 1
+            if i + 1 < n:
+                prefetch(i + 1)
+            cur.wait_event(ev_in[k])
+            b, r, tt = (x.detach().requires_grad_(True) for x in d_in[k])
+            v, j = layer(b, r, tt)
+            torch.autograd.backward([v, j], [dV, dJ])
+            ev_used[k].record(cur)
+            ev_grad[k].record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_grad[k])
+                ev_out[k].synchronize()                    # the host buffers of this slot were consumed two steps ago
+                for dst, src in zip(h_out[k], (b.grad, r.grad, tt.grad)):
+                    dst.copy_(src, non_blocking=True)
+                    src.record_stream(s_out)
+                ev_out[k].record(s_out)
+        s_out.synchronize()                                # the last step's result is on the host
+        cur.synchronize()
+
+    e2e_run(4)
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     sync_all()
     e2e_val = B * world * args.steps / sharding.max_over_ranks(time.perf_counter() - t0, dev)
     io_bytes = B * (10 + 216 + 3) * 4
