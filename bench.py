@@ -188,6 +188,38 @@ def cpu_reference_run(steps, warmup, sample_B, min_seconds=0.0):
     return sample_B * n / dt, dt / n * 1e3, n, torch.get_num_threads()
 
 
+def eager_gpu_reference_run(dev, B=1024, iters=5, warmup=3):
+    """the same PyTorch-eager restatement run on the GPU (what the reference's own
+    torch path does on a CUDA device) -- reported inside `cpu_baseline` as a second comparison point."""
+    from oracle.smpl_oracle import SMPLOracle, batch_rodrigues
+    from soccerplayershapepose_b200.model_io import make_synthetic_smpl
+    orc = SMPLOracle(make_synthetic_smpl(1234), dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    kw = dict(generator=g, device=dev)
+    betas = torch.randn(B, 10, **kw)
+    rot = batch_rodrigues((torch.randn(B, 72, **kw) * 0.3).reshape(-1, 3)).reshape(B, 24, 3, 3)
+    trans = torch.rand(B, 3, **kw) * 2 - 1
+    dV, dJ = torch.randn(B, 6890, 3, **kw), torch.randn(B, 90, 3, **kw)
+
+    def step():
+        b, r, t = (x.clone().requires_grad_(True) for x in (betas, rot, trans))
+        out = orc.forward_flat(b, r, t, pose2rot=False)
+        torch.autograd.backward([out.vertices, out.joints], [dV, dJ])
+
+    for _ in range(warmup):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    return {"value": B / ms * 1e3, "unit": UNIT, "sample": "oracle port (PyTorch eager) on the GPU, fwd+bwd at batch %d, "
+            "%d iterations, %.2f ms each" % (B, iters, ms)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -378,6 +410,10 @@ def main():
         cpu_baseline = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": "oracle port (PyTorch eager CPU, fp32) fwd+bwd at batch %d, %d iterations, "
                                   "%.1f ms each" % (args.cpu_sample, n, ms)}
+        try:
+            cpu_baseline["torch_eager_gpu"] = eager_gpu_reference_run(dev)
+        except Exception as e:  # a comparison point only: never fail the bench line on it
+            cpu_baseline["torch_eager_gpu"] = {"unavailable": repr(e)[:200]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

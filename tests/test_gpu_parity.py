@@ -308,3 +308,69 @@ def test_silhouette_handoff_layout(synthetic_model, dev):
     assert np.array_equal(h["faces"][1].cpu().numpy().astype(np.int64), smpl.faces.astype(np.int64))
     t = O.weak_perspective_to_translation(cam.double(), 5000.0, 512)
     assert h["t"].shape == (3, 1, 3) and np.allclose(h["t"][:, 0].cpu().double().numpy(), t.numpy(), rtol=1e-5)
+
+
+def test_batch_past_int32_element_index(engine, dev):
+    """Maximum sizes: B * 6890 * 3 > 2^31 elements (B = 106 000, one 8.8 GB vertex tensor), BASELINE.json
+    config 4's per-box batch and beyond.  64 distinct bodies repeated down the batch: every copy must equal the
+    result of the 64-body batch bit for bit (forward), and the gradients of the copies at the far end -- past
+    the 32-bit element index -- must equal those of the small batch (backward; fp32 RED order only)."""
+    B, P = 106000, 64
+    assert B * 6890 * 3 > 2 ** 31
+    betas, pose_aa, trans, _ = make_inputs(P, 77)
+    betas, pose_aa, trans = betas.to(dev), pose_aa.to(dev), trans.to(dev)
+    rep = lambda x: x.repeat((B + P - 1) // P, 1)[:B].contiguous()  # noqa: E731
+    v0, j0, _ = engine.forward(betas, pose_aa, trans, None, axis_angle=True)
+    v0, j0 = v0.clone(), j0.clone()
+    v, j, _ = engine.forward(rep(betas), rep(pose_aa), rep(trans), None, axis_angle=True)
+    assert v.shape == (B, 6890, 3)
+    nfull = B // P
+    assert torch.equal(v[:nfull * P].view(nfull, P, 6890, 3), v0.expand(nfull, -1, -1, -1))
+    assert torch.equal(j[:nfull * P].view(nfull, P, 90, 3), j0.expand(nfull, -1, -1, -1))
+    assert torch.equal(v[nfull * P:], v0[:B - nfull * P])
+    del v, j
+    g = torch.Generator().manual_seed(5)
+    dV0 = torch.randn(P, 6890, 3, generator=g).to(dev)
+    dJ0 = torch.randn(P, 90, 3, generator=g).to(dev)
+    g0 = engine.backward(betas, pose_aa, trans, None, None, dV0, dJ0, None, axis_angle=True)
+    g0 = [x.clone() for x in g0[:3]]
+    dV = dV0.repeat((B + P - 1) // P, 1, 1)[:B].contiguous()
+    dJ = dJ0.repeat((B + P - 1) // P, 1, 1)[:B].contiguous()
+    gB = engine.backward(rep(betas), rep(pose_aa), rep(trans), None, None, dV, dJ, None, axis_angle=True)
+    # the 64-body batch and the 4096-body slabs split the K range of the gradient GEMM differently, so the two
+    # differ by fp32 accumulation rounding (measured <= 3e-5 on grad_betas, 5e-7 on the others)
+    for a, b in zip(g0, gB[:3]):
+        last = b[(nfull - 1) * P:nfull * P]
+        assert _rel(last, a) < 1e-4
+        assert _rel(b[:P], a) < 1e-4
+        assert torch.isfinite(b).all()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_backward_full_size_vs_oracle(engine, oracle64, dev, mode):
+    """BASELINE.json config 2 size (B = 4096, the CTA-pair GEMMs with their production split-K counts): the
+    gradients of a handful of bodies spread over the batch against the fp64 oracle run on just those bodies
+    (bodies are independent, so the oracle does not need the other 4090)."""
+    B = 4096
+    m = _lib.MODES[mode]
+    betas, pose_aa, trans, cam = make_inputs(B, 21)
+    pick = torch.tensor([0, 1, 127, 128, 2049, 4095])
+    g = torch.Generator().manual_seed(22)
+    dVs = torch.randn(len(pick), 6890, 3, generator=g)
+    dJs = torch.randn(len(pick), 90, 3, generator=g)
+    dV = torch.zeros(B, 6890, 3)
+    dJ = torch.zeros(B, 90, 3)
+    dV[pick], dJ[pick] = dVs, dJs
+    d = lambda x: x.to(dev)  # noqa: E731
+    gb, gp, gt, _ = engine.backward(d(betas), d(pose_aa), d(trans), None, None, d(dV), d(dJ), None,
+                                    axis_angle=True, mode=m)
+    rb, rp, rt, _ = _oracle_grads(oracle64, betas[pick], pose_aa[pick], trans[pick], None, dVs, dJs, None, True)
+    tol = GRAD_TOL[mode]
+    errs = (_rel(gb[pick.to(dev)].cpu().double(), rb), _rel(gp[pick.to(dev)].cpu().double(), rp),
+            _rel(gt[pick.to(dev)].cpu().double(), rt))
+    print("full-size gradient errors vs fp64 oracle (betas, pose, transl):", errs)
+    assert max(errs) < tol
+    # bodies whose upstream gradient is zero get exactly zero
+    others = torch.ones(B, dtype=torch.bool)
+    others[pick] = False
+    assert gb[others.to(dev)].abs().max().item() == 0.0 and gp[others.to(dev)].abs().max().item() == 0.0
