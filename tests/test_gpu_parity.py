@@ -374,3 +374,48 @@ def test_backward_full_size_vs_oracle(engine, oracle64, dev, mode):
     others = torch.ones(B, dtype=torch.bool)
     others[pick] = False
     assert gb[others.to(dev)].abs().max().item() == 0.0 and gp[others.to(dev)].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("B", [1, 37, 130, 300])
+def test_no_write_outside_caller_buffers(engine, dev, monkeypatch, B):
+    """Every buffer the host side hands to the C-ABI (outputs, gradients, workspace, saved-for-backward) is
+    allocated between two sentinel-filled guard bands; ragged batches (not multiples of the 32-body group or
+    the 128-body GEMM tile) must leave every band untouched in all three modes."""
+    GUARD = 4096                                   # bytes on each side; keeps the 512-byte alignment torch gives
+    real_empty = torch.empty
+    bands = []
+
+    def guarded_empty(*size, dtype=torch.float32, device=None, **kw):
+        shape = tuple(size[0]) if len(size) == 1 and isinstance(size[0], (tuple, list, torch.Size)) else tuple(size)
+        if device is None or torch.device(device).type != "cuda":
+            return real_empty(shape, dtype=dtype, device=device, **kw)
+        item = torch.empty((), dtype=dtype).element_size()
+        n = 1
+        for s in shape:
+            n *= int(s)
+        pad = (-(n * item)) % 512                  # round the payload up so the upper band starts 512-aligned
+        raw = real_empty(GUARD + n * item + pad + GUARD, dtype=torch.uint8, device=device)
+        raw.fill_(0xA5)
+        bands.append((raw, GUARD, GUARD + n * item))
+        return raw[GUARD:GUARD + n * item].view(dtype).view(shape)
+
+    monkeypatch.setattr(torch, "empty", guarded_empty)
+    engine._ws.clear()                             # force fresh (guarded) workspaces
+    betas, pose_aa, trans, cam = (x.to(dev) for x in make_inputs(B, 300 + B))
+    g = torch.Generator().manual_seed(B)
+    dV = torch.randn(B, 6890, 3, generator=g).to(dev)
+    dJ = torch.randn(B, 90, 3, generator=g).to(dev)
+    dJ2 = torch.randn(B, 90, 2, generator=g).to(dev)
+    for mode in MODES:
+        m = _lib.MODES[mode]
+        out = engine.forward(betas, pose_aa, trans, cam, axis_angle=True, mode=m, save=True)
+        engine.backward(betas, pose_aa, trans, cam, out[1], dV, dJ, dJ2, axis_angle=True, mode=m, saved=out[3])
+        engine.backward(betas, pose_aa, trans, cam, out[1], dV, dJ, dJ2, axis_angle=True, mode=m)
+        engine.forward(betas, pose_aa, None, None, axis_angle=True, mode=m, want_vertices=False)
+    torch.cuda.synchronize(dev)
+    monkeypatch.setattr(torch, "empty", real_empty)
+    engine._ws.clear()
+    assert len(bands) >= 10
+    for raw, lo, hi in bands:
+        assert bool((raw[:lo] == 0xA5).all()), "write below a caller buffer"
+        assert bool((raw[hi:] == 0xA5).all()), "write above a caller buffer"
