@@ -851,6 +851,199 @@ blend_fwd_ws2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Forward blend GEMM on a CTA pair, BODY-stationary: the pair owns one pair of body tiles (each CTA keeps the
+// feature slabs of ITS 128 bodies resident: 9 x 16 KB, loaded once) and walks a contiguous range of model-row
+// tile pairs, streaming ITS 128 rows of each model slab through the stage ring.  Same MMAs, same accumulator
+// layout and epilogue as blend_fwd_ws2_kernel; what changes is what is kept and what is streamed: with
+// 16 body-tile pairs x 4 row chunks the whole GEMM is ONE wave of 64 clusters with ~22 tiles each, so the
+// prologue (resident load, pipeline fill) and the drain (last tile's MMAs + epilogue) are paid once per cluster
+// instead of once per 4 tiles (measured with clock64 counters in the MMA warp: 8-9 k of 35 k cycles waiting for
+// the resident slice, another 12 k refilling the ring, ~10 k draining).
+// ---------------------------------------------------------------------------------------------
+template <int DUMMY>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+blend_fwd_bs2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_f, int pslabs,
+                     int ksteps_cs, int ksteps_p, int use_lo, int row0, int mtiles, int ntiles_n, int wpairs_per_chunk,
+                     float4* __restrict__ vpB, int nc4) {
+  constexpr int SLAB = BM * BK * 2;
+  constexpr int KS = BK / UMMA_K;
+  constexpr uint32_t TMEM_COLS = 512;
+  const int nslab_f = 1 + 2 * pslabs;                                  // resident: constants+shape, P_hi, P_lo features
+  const int nslab_w = 1 + (use_lo ? 2 : 1) * pslabs;                   // streamed per row-tile pair
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* f_s = smem;                                          // [nslab_f][16 KB] this CTA's 128 bodies
+  unsigned char* w_s = smem + WS_MAX_SLABS * SLAB;                    // [WS_STAGES][16 KB] this CTA's 128 model rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + WS_STAGES * SLAB);
+  uint64_t* f_full = bars;
+  uint64_t* peer_f_full = bars + 1;
+  uint64_t* full_bar = bars + 2;
+  uint64_t* peer_full_bar = full_bar + WS_STAGES;
+  uint64_t* empty_bar = peer_full_bar + WS_STAGES;
+  uint64_t* tfull_bar = empty_bar + WS_STAGES;      // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;             // [2] (leader's are the ones waited on: 8 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int btile = (int)blockIdx.x;                                  // this CTA's body tile (pair = blockIdx.x >> 1)
+  const int wtp_total = (mtiles + 1) / 2;
+  const int wtp_begin = blockIdx.y * wpairs_per_chunk;
+  const int wtp_end = min(wtp_total, wtp_begin + wpairs_per_chunk);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_w);
+    prefetch_tmap(&map_f);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(f_full, 1);
+    mbar_init(peer_f_full, 1);
+    for (int i = 0; i < WS_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&peer_full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);                 // four epilogue warps of each CTA of the pair
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own body tile once, then own half of every model-row tile pair =====
+    if (elect_one()) {
+      mbar_arrive_expect_tx(f_full, (uint32_t)nslab_f * SLAB);
+      // rows beyond the slab (odd number of body tiles) are zero-filled by the TMA unit
+      for (int s = 0; s < nslab_f; ++s) tma_load_2d(f_s + s * SLAB, &map_f, f_full, s * BK, btile * WS_BN);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int wtp = wtp_begin; wtp < wtp_end; ++wtp)
+      for (int s = 0; s < nslab_w; ++s) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[stage], SLAB);
+          // a row tile beyond the model (odd number of row tiles) is zero-filled by the TMA unit
+          tma_load_2d(w_s + stage * SLAB, &map_w, &full_bar[stage], s * BK, row0 + (wtp * 2 + (int)rank) * BM);
+        }
+        __syncwarp();
+        if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+      }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    if (rank == 0) {
+      // ===== leader: MMA issuer of the pair =====
+      constexpr uint32_t idesc = make_idesc(2 * BM, 2 * WS_BN);
+      mbar_wait(f_full, 0);
+      mbar_wait(peer_f_full, 0);
+      uint32_t tph0 = 0, tph1 = 0;
+      int acc = 0;
+      for (int wtp = wtp_begin; wtp < wtp_end; ++wtp, acc ^= 1) {
+        const uint32_t tph = acc ? tph1 : tph0;
+        mbar_wait(&tempty_bar[acc], tph ^ 1);           // both CTAs' epilogues have drained this accumulator
+        if (acc) tph1 ^= 1; else tph0 ^= 1;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * WS_BN);
+        for (int s = 0; s < nslab_w; ++s) {
+          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(&peer_full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t db = make_sw128_desc(smem_u32(w_s + stage * SLAB));
+          // model slab s meets: s = 0 the constants+shape features; 1..pslabs (W_hi[j]) the hi AND lo pose
+          // features; pslabs+1.. (W_lo[j], fp32 mode) the hi pose features
+          int ks = ksteps_cs, f0 = 0, f1 = -1;
+          if (s > 0) {
+            const int j = (s - 1) % pslabs;
+            ks = min(KS, ksteps_p - j * KS);
+            f0 = 1 + j;
+            if (s <= pslabs) f1 = 1 + pslabs + j;
+          }
+          const uint64_t da0 = make_sw128_desc(smem_u32(f_s + f0 * SLAB));
+          const uint64_t da1 = make_sw128_desc(smem_u32(f_s + max(f1, 0) * SLAB));
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < KS; ++k)
+              if (k < ks) umma_bf16_2cta(d_tmem, da0 + 2 * k, db + 2 * k, idesc, (s | k) != 0);
+            if (f1 >= 0) {
+#pragma unroll
+              for (int k = 0; k < KS; ++k)
+                if (k < ks) umma_bf16_2cta(d_tmem, da1 + 2 * k, db + 2 * k, idesc, 1u);
+            }
+            umma_commit_2cta(&empty_bar[stage]);
+            if (s == nslab_w - 1) umma_commit_2cta(&tfull_bar[acc]);
+          }
+          __syncwarp();
+          if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else {
+      // ===== peer: relay "body tile landed" and every "stage landed" to the leader =====
+      mbar_wait(f_full, 0);
+      if (elect_one()) remote_arrive(peer_f_full, 0);
+      __syncwarp();
+      for (int wtp = wtp_begin; wtp < wtp_end; ++wtp)
+        for (int s = 0; s < nslab_w; ++s) {
+          mbar_wait(&full_bar[stage], phase);
+          if (elect_one()) remote_arrive(&peer_full_bar[stage], 0);
+          __syncwarp();
+          if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+  } else {
+    // ===== epilogue (both CTAs): 128 bodies x 256 model rows of the tile pair per accumulator =====
+    const int q = warp & 3;
+    uint32_t tph0 = 0, tph1 = 0;
+    int acc = 0;
+    for (int wtp = wtp_begin; wtp < wtp_end; ++wtp, acc ^= 1) {
+      const uint32_t tph = acc ? tph1 : tph0;
+      mbar_wait(&tfull_bar[acc], tph);
+      if (acc) tph1 ^= 1; else tph0 ^= 1;
+      tc_fence_after();
+      if (btile < ntiles_n) {
+        const bool live_hi = wtp * 2 + 1 < mtiles;
+        float4* colbase = vpB + ((size_t)(btile * 4 + q) * nc4 + ((row0 + wtp * 2 * BM) >> 2)) * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 2 * WS_BN; c0 += 32) {
+          if (c0 >= WS_BN && !live_hi) continue;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * WS_BN + c0), v);
+          float4* o = colbase + (size_t)(c0 >> 2) * 32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            o[i * 32] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                    __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[acc])) : "memory");
+        else remote_arrive(&tempty_bar[acc], 0);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -938,11 +1131,61 @@ static int launch_blend_fwd_umma_2cta(const DevModel& m, int mode, const __nv_bf
   return 0;
 }
 
+// body-stationary CTA-pair launch: one wave of (body-tile pair) x (row chunk) clusters
+static int launch_blend_fwd_umma_bs2(const DevModel& m, int mode, const __nv_bfloat16* feat, int S, int Sw, float* vpT,
+                                     int row_begin, int row_end, int num_sms, cudaStream_t st) {
+  const int pslabs = m.fl.pseg / BK;
+  const int use_lo = (mode == B200SMPL_MODE_BF16) ? 0 : 1;
+  if (1 + 2 * pslabs > WS_MAX_SLABS) return fail(B200SMPL_ERR_INVALID, "feature pitch too large for the resident operand");
+  CUtensorMap map_w, map_f;
+  int rc;
+  if ((rc = make_map(&map_w, m.Wf, m.fl.pitch, m.n_pad, m.fl.pitch, BM))) return rc;
+  if ((rc = make_map(&map_f, feat, m.fl.pitch, Sw, m.fl.pitch, WS_BN))) return rc;   // rows >= Sw read as zero
+  constexpr int smem = (WS_MAX_SLABS + WS_STAGES) * BM * BK * 2 + 1024 + 256;
+  auto kern = blend_fwd_bs2_kernel<0>;
+  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int mtiles = (row_end - row_begin) / BM;
+  const int wtp_total = (mtiles + 1) / 2;
+  const int ntiles_n = Sw / WS_BN;
+  const int bp_total = (ntiles_n + 1) / 2;
+  // CTA pairs are scheduled per TPC (2 SMs): as many row chunks as keep all clusters in one wave
+  const int tpcs = std::max(1, num_sms / 2);
+  const int chunks = std::max(1, std::min(wtp_total, tpcs / bp_total));
+  const int wpc = (wtp_total + chunks - 1) / chunks;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * bp_total, (wtp_total + wpc - 1) / wpc, 1);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LaunchTimer _timer("blend_fwd_umma", st);
+  B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map_w, map_f, pslabs, (m.fl.k_cs + UMMA_K - 1) / UMMA_K,
+                                   (NPOSE + UMMA_K - 1) / UMMA_K, use_lo, row_begin, mtiles, ntiles_n, wpc,
+                                   reinterpret_cast<float4*>(vpT), m.n_pad / 4));
+  B200_LAUNCH_CHECK("blend_fwd_umma");
+  return 0;
+}
+
 int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat, int S, int Sw, float* vpT,
                           int row_begin, int row_end, cudaStream_t st) {
   constexpr int CL = WS_CLUSTER;
-  static const bool use_2cta = getenv("B200_FWD_2CTA") == nullptr || atoi(getenv("B200_FWD_2CTA")) != 0;
-  if (use_2cta) return launch_blend_fwd_umma_2cta(m, mode, feat, S, Sw, vpT, row_begin, row_end, st);
+  // B200_FWD_2CTA: 2 (default) body-stationary CTA pairs, 1 model-row-stationary CTA pairs, 0 single-CTA kernel
+  // (the latter two are kept for comparison)
+  static const int sel = getenv("B200_FWD_2CTA") == nullptr ? 2 : atoi(getenv("B200_FWD_2CTA"));
+  if (sel >= 2) {
+    int dev = 0, sms = 148;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    B200_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return launch_blend_fwd_umma_bs2(m, mode, feat, S, Sw, vpT, row_begin, row_end, sms, st);
+  }
+  if (sel == 1) return launch_blend_fwd_umma_2cta(m, mode, feat, S, Sw, vpT, row_begin, row_end, st);
   const int pslabs = m.fl.pseg / BK;
   const int use_lo = (mode == B200SMPL_MODE_BF16) ? 0 : 1;
   if (1 + 2 * pslabs > WS_MAX_SLABS) return fail(B200SMPL_ERR_INVALID, "feature pitch too large for the resident operand");
