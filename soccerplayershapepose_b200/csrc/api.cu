@@ -403,7 +403,7 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
     else
       rc = launch_blend_bwd_umma(d, a->mode, dvp_hi, dvp_lo, S, Sw, dfeat_part, k_splits, row_begin, row_end, st);
     if (rc) return rc;
-    if ((rc = launch_pose_bwd(d, a->betas, a->pose, aa, b0, nb, S, dA_part, 1, dtr_part, dfeat_part, k_splits,
+    if ((rc = launch_pose_bwd(d, a->betas, a->pose, aa, b0, nb, S, A_T, dA_part, 1, dtr_part, dfeat_part, k_splits,
                               have_j ? dJ : nullptr, a->grad_betas, a->grad_pose, a->grad_transl, st)))
       return rc;
   }

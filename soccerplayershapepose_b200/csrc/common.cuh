@@ -171,7 +171,7 @@ int launch_pose_fwd(const DevModel& m, const float* betas, const float* pose, bo
                     int Sw, __nv_bfloat16* feat, float* featf, float* A_blk, const float* transl, float* joints,
                     cudaStream_t st);
 int launch_pose_bwd(const DevModel& m, const float* betas, const float* pose, bool axis_angle, int b0, int nb, int S,
-                    const float* dA_part, int n_dA_parts, const float* dtr_part, const float* dfeat_part,
+                    const float* A_blk, const float* dA_part, int n_dA_parts, const float* dtr_part, const float* dfeat_part,
                     int n_dfeat_parts, const float* dJ, float* grad_betas, float* grad_pose,
                     float* grad_transl, cudaStream_t st);
 

@@ -8,6 +8,7 @@
 // Outputs are written body-fastest (A_T[j*12+e][b]) through a shared-memory transpose because
 // the skinning kernels run with lane = body.
 #include "common.cuh"
+#include "skin_common.cuh"
 
 namespace b200smpl {
 
@@ -418,12 +419,467 @@ pose_bwd_kernel(DevModel m, const float* __restrict__ betas, const float* __rest
   }
 }
 
+// =============================================================================================
+// lane = body versions (default).  One warp per 32-body group, each lane walks ITS body's 24 joints
+// sequentially (parents precede children in the SMPL tree), so there is no shuffle, no divergence and no idle
+// lane: ~10x fewer warp instructions per body than the lane = joint kernels above (ncu: 3800 warp instructions
+// per body in pose_bwd, issue-bound at 16 warps per SM).  Per-joint state that is indexed dynamically (local
+// rotations, global transforms, rest joints, gradient accumulators) lives in shared memory as [row][lane]
+// (conflict-free); the group-blocked operands of the skinning kernels (A_blk, dA) are read / written straight
+// from registers, coalesced; row-major per-body tensors (pose, grad_pose) go through a transposing stage.
+// =============================================================================================
+constexpr int LB_P = 33;                     // pitch of the transposed staging rows
+constexpr int LB_MAXB = 20;                  // betas that fit slab 0 of the feature layout
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// stage the group's rows of a row-major (B, W) tensor: sT[k * LB_P + body]; rows >= nlive are left untouched
+__device__ __forceinline__ void lb_stage_in(float* sT, const float* __restrict__ src, int W, int nlive, int lane) {
+  const int n = nlive * W;
+  for (int i = lane; i < n; i += 32) {
+    const int body = i / W, k = i - body * W;
+    sT[k * LB_P + body] = src[i];
+  }
+}
+__device__ __forceinline__ void lb_stage_out(const float* sT, float* __restrict__ dst, int W, int nlive, int lane) {
+  const int n = nlive * W;
+  for (int i = lane; i < n; i += 32) {
+    const int body = i / W, k = i - body * W;
+    dst[i] = sT[k * LB_P + body];
+  }
+}
+
+// forward chain of one body; fills sR (local rotations), sJ (rest joints), sG (global transforms)
+template <bool AA>
+__device__ __forceinline__ void lb_chain_forward(const DevModel& m, const float* sAA, float* sR, float* sJ, float* sG,
+                                                 const float* sB, int lane, bool live) {
+  const int nbeta = m.fl.nb;
+#pragma unroll 1
+  for (int j = 0; j < NJ; ++j) {
+    float R[9];
+    if (AA) {
+      float r[3] = {0.f, 0.f, 0.f};
+      if (live) { r[0] = sAA[(j * 3) * LB_P + lane]; r[1] = sAA[(j * 3 + 1) * LB_P + lane]; r[2] = sAA[(j * 3 + 2) * LB_P + lane]; }
+      rodrigues_fwd(r, R);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) sR[(j * 9 + e) * LB_P + lane] = R[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) R[e] = live ? sR[(j * 9 + e) * LB_P + lane] : ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+    }
+    float Jr[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float acc = __ldg(m.Jt + j * 3 + k);
+      const float* sd = m.Jsd + (j * 3 + k) * nbeta;
+      for (int l = 0; l < nbeta; ++l) acc = fmaf(__ldg(sd + l), sB[l * 32 + lane], acc);
+      Jr[k] = acc;
+      sJ[(j * 3 + k) * 32 + lane] = acc;
+    }
+    const int p = m.chain.parent[j];
+    float G[12];
+    if (p < 0) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) G[r * 4 + c] = R[r * 3 + c];
+        G[r * 4 + 3] = Jr[r];
+      }
+    } else {
+      float P[12];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) P[e] = sG[(p * 12 + e) * 32 + lane];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) G[r * 4 + c] = R[r * 3 + c];
+        G[r * 4 + 3] = Jr[r] - sJ[(p * 3 + r) * 32 + lane];
+      }
+      compose(P, G);
+    }
+#pragma unroll
+    for (int e = 0; e < 12; ++e) sG[(j * 12 + e) * 32 + lane] = G[e];
+  }
+}
+
+template <bool AA>
+__global__ void __launch_bounds__(32)
+pose_fwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __restrict__ pose, int b0, int nb, int S,
+                   __nv_bfloat16* __restrict__ feat, float* __restrict__ featf, float* __restrict__ A_T,
+                   const float* __restrict__ transl, float* __restrict__ joints) {
+  extern __shared__ __align__(16) float lbs_[];
+  float* sR = lbs_;                          // [216][LB_P]
+  float* sG = sR + NJ * 9 * LB_P;            // [288][32]
+  float* sJ = sG + NJ * 12 * 32;             // [72][32]
+  float* sB = sJ + NJ * 3 * 32;              // [LB_MAXB][32]
+  float* sAA = sB + LB_MAXB * 32;            // [72][LB_P] (axis-angle input only)
+  const int lane = threadIdx.x, g = blockIdx.x;
+  const int sc = g * 32 + lane, b = b0 + sc;
+  const bool live = sc < nb;
+  const int nlive = max(0, min(32, nb - g * 32));
+  const FeatLayout fl = m.fl;
+  (void)S;
+  if (AA) lb_stage_in(sAA, pose + (size_t)(b0 + g * 32) * (NJ * 3), NJ * 3, nlive, lane);
+  else lb_stage_in(sR, pose + (size_t)(b0 + g * 32) * (NJ * 9), NJ * 9, nlive, lane);
+  for (int l = 0; l < fl.nb; ++l) sB[l * 32 + lane] = live ? betas[(size_t)b * fl.nb + l] : 0.f;
+  __syncwarp();
+  lb_chain_forward<AA>(m, sAA, sR, sJ, sG, sB, lane, live);
+  // ---- skinning transforms A = [G_R | G_t - G_R Jr] (paired float4 layout, see skin_common.cuh) and posed joints ----
+  float tr[3] = {0.f, 0.f, 0.f};
+  if (live && transl != nullptr) { tr[0] = transl[(size_t)b * 3]; tr[1] = transl[(size_t)b * 3 + 1]; tr[2] = transl[(size_t)b * 3 + 2]; }
+  float4* A4 = reinterpret_cast<float4*>(A_T) + (size_t)g * (NJ * 3 * 32) + lane;
+#pragma unroll 1
+  for (int j = 0; j < NJ; ++j) {
+    float G[12], Jr[3], t[3];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) G[e] = sG[(j * 12 + e) * 32 + lane];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Jr[k] = sJ[(j * 3 + k) * 32 + lane];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) t[r] = G[r * 4 + 3] - (G[r * 4] * Jr[0] + G[r * 4 + 1] * Jr[1] + G[r * 4 + 2] * Jr[2]);
+    const float z = live ? 1.f : 0.f;
+    A4[(j * 3 + 0) * 32] = make_float4(z * G[0], z * G[4], z * G[1], z * G[5]);
+    A4[(j * 3 + 1) * 32] = make_float4(z * G[2], z * G[6], z * t[0], z * t[1]);
+    A4[(j * 3 + 2) * 32] = make_float4(z * G[8], z * G[9], z * G[10], z * t[2]);
+    if (joints != nullptr && live) {
+      float* o = joints + ((size_t)b * m.njout + j) * 3;
+      o[0] = G[3] + tr[0]; o[1] = G[7] + tr[1]; o[2] = G[11] + tr[2];
+    }
+  }
+  // ---- feature row: slab 0 = [1 1 1 | betas hi | betas lo | betas hi], then pose feature hi / lo segments ----
+  uint4* frow = reinterpret_cast<uint4*>(feat + (size_t)sc * fl.pitch);
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = c * 8 + i;
+      float x = 0.f;
+      if (live) {
+        if (k < 3) x = 1.f;
+        else if (k >= fl.off_s0 && k < fl.off_s0 + fl.nb) x = __bfloat162float(bf_hi(sB[(k - fl.off_s0) * 32 + lane]));
+        else if (k >= fl.off_s1 && k < fl.off_s1 + fl.nb) {
+          const float be = sB[(k - fl.off_s1) * 32 + lane];
+          x = be - __bfloat162float(bf_hi(be));
+        } else if (k >= fl.off_s2 && k < fl.off_s2 + fl.nb) x = __bfloat162float(bf_hi(sB[(k - fl.off_s2) * 32 + lane]));
+      }
+      v[i] = x;
+    }
+    frow[c] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+  const int pch = fl.pseg / 8;
+#pragma unroll 1
+  for (int c = 0; c < pch; ++c) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float x[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int idx = c * 8 + i * 2 + u;
+        float pf = 0.f;
+        if (live && idx < NPOSE) {
+          const int e = idx % 9;
+          pf = sR[(9 + idx) * LB_P + lane] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+        }
+        x[u] = pf;
+      }
+      split2(x[0], x[1], h[i], l[i]);
+    }
+    frow[8 + c] = make_uint4(h[0], h[1], h[2], h[3]);
+    frow[8 + pch + c] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+  if (featf != nullptr) {
+    float* fr = featf + (size_t)sc * fl.nf_pad;
+    for (int k = 0; k < fl.nf_pad; ++k) {
+      float x = 0.f;
+      if (live) {
+        if (k < fl.nb) x = sB[k * 32 + lane];
+        else if (k - fl.nb < NPOSE) {
+          const int idx = k - fl.nb, e = idx % 9;
+          x = sR[(9 + idx) * LB_P + lane] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+        }
+      }
+      fr[k] = x;
+    }
+  }
+}
+
+// ---- backward, lane = body.  One CTA (4 warps) per 32-body group:
+//   P1 all threads: every input of the group staged into shared memory with coalesced, batched loads (pose rows,
+//      betas, the group's A block -> global rotations, dA, the split-K partials of dfeat summed, the chain
+//      joints' dJ), accumulators cleared;
+//   P2 all threads: rest joints (and Rodrigues for axis-angle input), G_t = A_t + G_R Jr;
+//   P3 warp 0: the reverse walk over the 24 joints, each lane ITS body, shared memory only (the critical path:
+//      ~200 instructions per joint);
+//   P4 all threads: + pose-blend gradient (Rodrigues backward for axis-angle), betas / transl gradients, coalesced
+//      write-out.
+constexpr int LBB_THREADS = 512;
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+// rotation part (row-major) of one body's transform stored as (r00 r10 r01 r11) (r02 r12 t0 t1) (r20 r21 r22 t2)
+__device__ __forceinline__ void lb_rot_of(const float4* p, float (&R)[9]) {
+  const float4 q0 = p[0], q1 = p[32], q2 = p[64];
+  R[0] = q0.x; R[3] = q0.y; R[1] = q0.z; R[4] = q0.w; R[2] = q1.x; R[5] = q1.y; R[6] = q2.x; R[7] = q2.y; R[8] = q2.z;
+}
+struct LbBwdSmem {
+  float R[NJ * 9 * LB_P];        // local rotations -> dL/dR
+  float AAx[NJ * 3 * LB_P];      // axis-angle input -> its gradient
+  float G[NJ * 12 * 32];         // the group's transforms as stored ([joint][3][lane] float4)
+  float J[NJ * 3 * 32];          // rest joints
+  float B[LB_MAXB * 32];         // betas
+  float DA[NJ * 12 * 32];        // dL/dA (sum of the partials)
+  float D[NJ * 12 * 32];         // dL/dG handed up by the children
+  float DJ[NJ * 3 * 32];         // dL/dJr: handed up by the children, then final
+  float DF[224 * LB_P];          // dL/d[betas | pose feature] (sum of the split-K partials), [k][body]
+  float DJo[NJ * 3 * LB_P];      // dL/d(posed chain joints) from the caller
+  float Jsd[NJ * 3 * LB_MAXB];
+  float Jt[NJ * 3];
+};
+
+template <bool AA>
+__global__ void __launch_bounds__(LBB_THREADS, 1)
+pose_bwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __restrict__ pose, int b0, int nb, int S,
+                   const float* __restrict__ A_blk, const float* __restrict__ dA_part, int n_dA_parts,
+                   const float* __restrict__ dtr_part, const float* __restrict__ dfeat_part, int n_dfeat_parts,
+                   const float* __restrict__ dJ, float* __restrict__ grad_betas, float* __restrict__ grad_pose,
+                   float* __restrict__ grad_transl) {
+  extern __shared__ __align__(16) unsigned char lbraw_[];
+  LbBwdSmem& sm = *reinterpret_cast<LbBwdSmem*>(lbraw_);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = blockIdx.x;
+  const int nlive = max(0, min(32, nb - g * 32));
+  const FeatLayout fl = m.fl;
+  const int nbeta = fl.nb, nf = fl.nf_pad, NG = S / 32;
+  const size_t body0 = (size_t)b0 + (size_t)g * 32;
+  // ---------------- P1: stage ----------------
+  {
+    // (a) straight copies, 16 bytes per cp.async: the group's transforms and dL/dA
+    const float4* A4 = reinterpret_cast<const float4*>(A_blk) + (size_t)g * (NJ * 3 * 32);
+    const float4* dA4 = reinterpret_cast<const float4*>(dA_part + (size_t)g * (NJ * 12 * 32));
+    for (int i = tid; i < NJ * 3 * 32; i += LBB_THREADS) cp_async16(reinterpret_cast<float4*>(sm.G) + i, A4 + i);
+    for (int i = tid; i < NJ * 12 * 8; i += LBB_THREADS) cp_async16(reinterpret_cast<float4*>(sm.DA) + i, dA4 + i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // (b) row-major per-body tensors, transposed through registers: pose rows ...
+    {
+      const int PW = AA ? NJ * 3 : NJ * 9;
+      float* dstT = AA ? sm.AAx : sm.R;
+      const float4* src4 = reinterpret_cast<const float4*>(pose + body0 * PW);      // PW * 4 bytes is a multiple of 16
+      const int n4 = nlive * PW / 4;
+      const bool al = (reinterpret_cast<uintptr_t>(pose) & 15) == 0;
+      if (al) {
+#pragma unroll 4
+        for (int i = tid; i < n4; i += LBB_THREADS) {
+          const float4 v = src4[i];
+          const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = i * 4 + u, body = e / PW, k = e - body * PW;
+            dstT[k * LB_P + body] = x[u];
+          }
+        }
+      } else {
+        const float* src = pose + body0 * PW;
+        for (int i = tid; i < nlive * PW; i += LBB_THREADS) {
+          const int body = i / PW, k = i - body * PW;
+          dstT[k * LB_P + body] = src[i];
+        }
+      }
+    }
+    // ... the split-K partials of the gradient GEMM (rows of this group are contiguous in every partial), summed
+    {
+      const float4* base4 = reinterpret_cast<const float4*>(dfeat_part + (size_t)g * 32 * nf);
+      const size_t pstride4 = (size_t)S * nf / 4;
+      const int n4 = 32 * nf / 4;
+      for (int i = tid; i < n4; i += LBB_THREADS) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        int q = 0;
+        for (; q + 4 <= n_dfeat_parts; q += 4) {
+          const float4 v0 = base4[(size_t)q * pstride4 + i], v1 = base4[(size_t)(q + 1) * pstride4 + i];
+          const float4 v2 = base4[(size_t)(q + 2) * pstride4 + i], v3 = base4[(size_t)(q + 3) * pstride4 + i];
+          v.x += (v0.x + v1.x) + (v2.x + v3.x); v.y += (v0.y + v1.y) + (v2.y + v3.y);
+          v.z += (v0.z + v1.z) + (v2.z + v3.z); v.w += (v0.w + v1.w) + (v2.w + v3.w);
+        }
+        for (; q < n_dfeat_parts; ++q) {
+          const float4 w = base4[(size_t)q * pstride4 + i];
+          v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        const int e = i * 4, body = e / nf, k = e - body * nf;                        // nf is a multiple of 4
+        sm.DF[k * LB_P + body] = v.x; sm.DF[(k + 1) * LB_P + body] = v.y;
+        sm.DF[(k + 2) * LB_P + body] = v.z; sm.DF[(k + 3) * LB_P + body] = v.w;
+      }
+    }
+    // ... the chain joints' own gradient, betas, model constants; accumulators cleared
+    for (int i = tid; i < 32 * NJ * 3; i += LBB_THREADS) {
+      const int body = i / (NJ * 3), k = i - body * (NJ * 3);
+      sm.DJo[k * LB_P + body] = (dJ != nullptr && body < nlive) ? dJ[(body0 + body) * m.njout * 3 + k] : 0.f;
+    }
+    for (int i = tid; i < 32 * nbeta; i += LBB_THREADS) {
+      const int body = i / nbeta, l = i - body * nbeta;
+      sm.B[l * 32 + body] = body < nlive ? betas[body0 * nbeta + i] : 0.f;
+    }
+    for (int i = tid; i < NJ * 3 * nbeta; i += LBB_THREADS) sm.Jsd[i] = m.Jsd[i];
+    if (tid < NJ * 3) sm.Jt[tid] = m.Jt[tid];
+    for (int i = tid; i < NJ * 12 * 8; i += LBB_THREADS) reinterpret_cast<float4*>(sm.D)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < NJ * 3 * 32; i += LBB_THREADS) sm.DJ[i] = 0.f;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+  // ---------------- P2: rest joints, local rotations ----------------
+  for (int k = warp; k < NJ * 3; k += LBB_THREADS / 32) {
+    float acc = sm.Jt[k];
+    for (int l = 0; l < nbeta; ++l) acc = fmaf(sm.Jsd[k * nbeta + l], sm.B[l * 32 + lane], acc);
+    sm.J[k * 32 + lane] = acc;
+  }
+  if (AA) {
+    for (int j = warp; j < NJ; j += LBB_THREADS / 32) {
+      float r[3] = {0.f, 0.f, 0.f}, R[9];
+      if (lane < nlive) { r[0] = sm.AAx[(j * 3) * LB_P + lane]; r[1] = sm.AAx[(j * 3 + 1) * LB_P + lane]; r[2] = sm.AAx[(j * 3 + 2) * LB_P + lane]; }
+      rodrigues_fwd(r, R);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) sm.R[(j * 9 + e) * LB_P + lane] = R[e];
+    }
+  }
+  __syncthreads();
+  // ---------------- P3: reverse walk (warp 0) ----------------
+  if (warp == 0) {
+#pragma unroll 1
+    for (int j = NJ - 1; j >= 0; --j) {
+      float R[9], GR[9], Jr[3], dAr[12], dGR[9], dGt[3], dJr[3];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) R[e] = sm.R[(j * 9 + e) * LB_P + lane];
+      lb_rot_of(reinterpret_cast<const float4*>(sm.G) + (j * 3) * 32 + lane, GR);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Jr[k] = sm.J[(j * 3 + k) * 32 + lane];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) dAr[e] = sm.DA[(j * 12 + e) * 32 + lane];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float dat = dAr[r * 4 + 3];
+        dGt[r] = sm.D[(j * 12 + r * 4 + 3) * 32 + lane] + dat + sm.DJo[(j * 3 + r) * LB_P + lane];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dGR[r * 3 + c] = sm.D[(j * 12 + r * 4 + c) * 32 + lane] + dAr[r * 4 + c] - dat * Jr[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        dJr[c] = sm.DJ[(j * 3 + c) * 32 + lane] - (GR[c] * dAr[3] + GR[3 + c] * dAr[7] + GR[6 + c] * dAr[11]);
+      const int p = m.chain.parent[j];
+      float dRl[9];
+      if (p >= 0) {
+        float PR[9], rel[3];
+        lb_rot_of(reinterpret_cast<const float4*>(sm.G) + (p * 3) * 32 + lane, PR);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) rel[r] = Jr[r] - sm.J[(p * 3 + r) * 32 + lane];
+        // G_j = G_p . [R_j | rel_j]: hand dL/dG_p up, keep dL/dR_j and dL/drel_j
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            sm.D[(p * 12 + r * 4 + c) * 32 + lane] += dGR[r * 3] * R[c * 3] + dGR[r * 3 + 1] * R[c * 3 + 1] +
+                                                      dGR[r * 3 + 2] * R[c * 3 + 2] + dGt[r] * rel[c];
+          sm.D[(p * 12 + r * 4 + 3) * 32 + lane] += dGt[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) dRl[r * 3 + c] = PR[r] * dGR[c] + PR[3 + r] * dGR[3 + c] + PR[6 + r] * dGR[6 + c];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float drel = PR[c] * dGt[0] + PR[3 + c] * dGt[1] + PR[6 + c] * dGt[2];
+          dJr[c] += drel;
+          sm.DJ[(p * 3 + c) * 32 + lane] -= drel;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) dRl[e] = dGR[e];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dJr[c] += dGt[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sm.DJ[(j * 3 + c) * 32 + lane] = dJr[c];       // final
+#pragma unroll
+      for (int e = 0; e < 9; ++e) sm.R[(j * 9 + e) * LB_P + lane] = dRl[e];        // chain part of dL/dR_j
+    }
+  }
+  __syncthreads();
+  // ---------------- P4: blend part, outputs ----------------
+  for (int j = warp; j < NJ; j += LBB_THREADS / 32) {
+    float dRl[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      dRl[e] = sm.R[(j * 9 + e) * LB_P + lane];
+      if (j >= 1) dRl[e] += sm.DF[(nbeta + (j - 1) * 9 + e) * LB_P + lane];
+    }
+    if (AA) {
+      float r[3] = {0.f, 0.f, 0.f}, dr[3];
+      if (lane < nlive) { r[0] = sm.AAx[(j * 3) * LB_P + lane]; r[1] = sm.AAx[(j * 3 + 1) * LB_P + lane]; r[2] = sm.AAx[(j * 3 + 2) * LB_P + lane]; }
+      rodrigues_bwd(r, dRl, dr);
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 3; ++k) sm.AAx[(j * 3 + k) * LB_P + lane] = dr[k];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) sm.R[(j * 9 + e) * LB_P + lane] = dRl[e];
+    }
+  }
+  for (int l = warp; l < nbeta; l += LBB_THREADS / 32) {
+    float v = sm.DF[l * LB_P + lane];
+    for (int k = 0; k < NJ * 3; ++k) v = fmaf(sm.Jsd[k * nbeta + l], sm.DJ[k * 32 + lane], v);
+    if (lane < nlive) grad_betas[(body0 + lane) * nbeta + l] = v;
+  }
+  if (grad_transl != nullptr && warp < 3 && lane < nlive) {
+    const int r = warp;
+    float t = 0.f;
+    for (int j = 0; j < NJ; ++j) t += sm.DJo[(j * 3 + r) * LB_P + lane];
+    for (int q = 0; q < n_dA_parts; ++q) t += dtr_part[(((size_t)q * NG + g) * 3 + r) * 32 + lane];
+    grad_transl[(body0 + lane) * 3 + r] = t;
+  }
+  __syncthreads();
+  {
+    const int PW = AA ? NJ * 3 : NJ * 9;
+    const float* srcT = AA ? sm.AAx : sm.R;
+    float* dst = grad_pose + body0 * PW;
+    const int n = nlive * PW;
+    for (int i = tid; i < n; i += LBB_THREADS) {
+      const int body = i / PW, k = i - body * PW;
+      dst[i] = srcT[k * LB_P + body];
+    }
+  }
+}
+
+constexpr size_t LB_FWD_SMEM = (size_t)(NJ * 9 * LB_P + NJ * 12 * 32 + NJ * 3 * 32 + LB_MAXB * 32 + NJ * 3 * LB_P) * 4;
+constexpr size_t LB_BWD_SMEM = sizeof(LbBwdSmem);
+
+// B200_POSE_LB=0 selects the lane = joint kernels (kept for comparison)
+static int pose_use_lb() {   // bit 0: forward, bit 1: backward
+  static const int v = getenv("B200_POSE_LB") == nullptr ? 2 : atoi(getenv("B200_POSE_LB"));
+  return v;
+}
+
 // Sw = active slab width (multiple of 32, >= nb); columns in [nb, Sw) are written as zeros
 int launch_pose_fwd(const DevModel& m, const float* betas, const float* pose, bool axis_angle, int b0, int nb, int S,
                     int Sw, __nv_bfloat16* feat, float* featf, float* A_T, const float* transl, float* joints,
                     cudaStream_t st) {
-  const size_t smem = (size_t)OUT_ROWS * OUT_PITCH * sizeof(float) + (size_t)POSE_WARPS * m.fl.pitch * 2;
   const int grid = Sw / 32;
+  if (pose_use_lb() & 1) {
+    if (m.fl.nb > LB_MAXB) return fail(B200SMPL_ERR_INVALID, "too many betas for the pose kernels");
+    if (axis_angle) {
+      B200_CUDA_TRY(cudaFuncSetAttribute(pose_fwd_lb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB_FWD_SMEM));
+      LaunchTimer _timer("pose_fwd", st);
+      pose_fwd_lb_kernel<true><<<grid, 32, LB_FWD_SMEM, st>>>(m, betas, pose, b0, nb, S, feat, featf, A_T, transl, joints);
+    } else {
+      B200_CUDA_TRY(cudaFuncSetAttribute(pose_fwd_lb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB_FWD_SMEM));
+      LaunchTimer _timer("pose_fwd", st);
+      pose_fwd_lb_kernel<false><<<grid, 32, LB_FWD_SMEM, st>>>(m, betas, pose, b0, nb, S, feat, featf, A_T, transl, joints);
+    }
+    B200_LAUNCH_CHECK("pose_fwd");
+    return 0;
+  }
+  const size_t smem = (size_t)OUT_ROWS * OUT_PITCH * sizeof(float) + (size_t)POSE_WARPS * m.fl.pitch * 2;
   if (axis_angle) {
     B200_CUDA_TRY(cudaFuncSetAttribute(pose_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LaunchTimer _timer_405("pose_fwd", st);
@@ -438,12 +894,27 @@ int launch_pose_fwd(const DevModel& m, const float* betas, const float* pose, bo
 }
 
 int launch_pose_bwd(const DevModel& m, const float* betas, const float* pose, bool axis_angle, int b0, int nb, int S,
-                    const float* dA_part, int n_dA_parts, const float* dtr_part, const float* dfeat_part,
+                    const float* A_blk, const float* dA_part, int n_dA_parts, const float* dtr_part, const float* dfeat_part,
                     int n_dfeat_parts, const float* dJ, float* grad_betas, float* grad_pose,
                     float* grad_transl, cudaStream_t st) {
   if (nb <= 0) return 0;
-  const size_t smem = (size_t)IN_ROWS * OUT_PITCH * sizeof(float);
   const int grid = (nb + 31) / 32;
+  if ((pose_use_lb() & 2) && A_blk != nullptr && m.fl.nf_pad <= 224 && m.fl.nb <= LB_MAXB) {
+    if (axis_angle) {
+      B200_CUDA_TRY(cudaFuncSetAttribute(pose_bwd_lb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB_BWD_SMEM));
+      LaunchTimer _timer("pose_bwd", st);
+      pose_bwd_lb_kernel<true><<<grid, LBB_THREADS, LB_BWD_SMEM, st>>>(m, betas, pose, b0, nb, S, A_blk, dA_part, n_dA_parts, dtr_part,
+                                                             dfeat_part, n_dfeat_parts, dJ, grad_betas, grad_pose, grad_transl);
+    } else {
+      B200_CUDA_TRY(cudaFuncSetAttribute(pose_bwd_lb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB_BWD_SMEM));
+      LaunchTimer _timer("pose_bwd", st);
+      pose_bwd_lb_kernel<false><<<grid, LBB_THREADS, LB_BWD_SMEM, st>>>(m, betas, pose, b0, nb, S, A_blk, dA_part, n_dA_parts, dtr_part,
+                                                              dfeat_part, n_dfeat_parts, dJ, grad_betas, grad_pose, grad_transl);
+    }
+    B200_LAUNCH_CHECK("pose_bwd");
+    return 0;
+  }
+  const size_t smem = (size_t)IN_ROWS * OUT_PITCH * sizeof(float);
   if (axis_angle) {
     B200_CUDA_TRY(cudaFuncSetAttribute(pose_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LaunchTimer _timer_423("pose_bwd", st);
