@@ -664,64 +664,109 @@ pose_bwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __r
     for (int i = tid; i < NJ * 3 * 32; i += LBB_THREADS) cp_async16(reinterpret_cast<float4*>(sm.G) + i, A4 + i);
     for (int i = tid; i < NJ * 12 * 8; i += LBB_THREADS) cp_async16(reinterpret_cast<float4*>(sm.DA) + i, dA4 + i);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    // (b) row-major per-body tensors, transposed through registers: pose rows ...
+    // (b) row-major per-body tensors go through registers and are stored transposed ([k][body]).  All global
+    // loads of this block are issued before the first store, so the CTA pays about one memory round trip.
+    constexpr int PWc = AA ? NJ * 3 : NJ * 9;
+    constexpr int PIT = (32 * PWc / 4 + LBB_THREADS - 1) / LBB_THREADS;     // float4 per thread: pose rows
+    constexpr int DIT = (32 * 224 / 4 + LBB_THREADS - 1) / LBB_THREADS;     // float4 per thread: dfeat rows (nf <= 224)
+    constexpr int JIT = (32 * NJ * 3 + LBB_THREADS - 1) / LBB_THREADS;      // floats per thread: chain-joint gradient
+    float* dstT = AA ? sm.AAx : sm.R;
+    const bool al = (reinterpret_cast<uintptr_t>(pose) & 15) == 0;
+    float4 pv[PIT];
     {
-      const int PW = AA ? NJ * 3 : NJ * 9;
-      float* dstT = AA ? sm.AAx : sm.R;
-      const float4* src4 = reinterpret_cast<const float4*>(pose + body0 * PW);      // PW * 4 bytes is a multiple of 16
-      const int n4 = nlive * PW / 4;
-      const bool al = (reinterpret_cast<uintptr_t>(pose) & 15) == 0;
-      if (al) {
-#pragma unroll 4
-        for (int i = tid; i < n4; i += LBB_THREADS) {
-          const float4 v = src4[i];
-          const float x[4] = {v.x, v.y, v.z, v.w};
+      const float4* src4 = reinterpret_cast<const float4*>(pose + body0 * PWc);   // PWc * 4 bytes is a multiple of 16
+      const int n4 = nlive * PWc / 4;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int e = i * 4 + u, body = e / PW, k = e - body * PW;
-            dstT[k * LB_P + body] = x[u];
-          }
-        }
-      } else {
-        const float* src = pose + body0 * PW;
-        for (int i = tid; i < nlive * PW; i += LBB_THREADS) {
-          const int body = i / PW, k = i - body * PW;
-          dstT[k * LB_P + body] = src[i];
-        }
+      for (int it = 0; it < PIT; ++it) {
+        const int i = tid + it * LBB_THREADS;
+        pv[it] = (al && i < n4) ? src4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    // ... the split-K partials of the gradient GEMM (rows of this group are contiguous in every partial), summed
+    float4 dv[DIT];
+    const int dn4 = 32 * nf / 4;
     {
       const float4* base4 = reinterpret_cast<const float4*>(dfeat_part + (size_t)g * 32 * nf);
       const size_t pstride4 = (size_t)S * nf / 4;
-      const int n4 = 32 * nf / 4;
-      for (int i = tid; i < n4; i += LBB_THREADS) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        int q = 0;
-        for (; q + 4 <= n_dfeat_parts; q += 4) {
-          const float4 v0 = base4[(size_t)q * pstride4 + i], v1 = base4[(size_t)(q + 1) * pstride4 + i];
-          const float4 v2 = base4[(size_t)(q + 2) * pstride4 + i], v3 = base4[(size_t)(q + 3) * pstride4 + i];
-          v.x += (v0.x + v1.x) + (v2.x + v3.x); v.y += (v0.y + v1.y) + (v2.y + v3.y);
-          v.z += (v0.z + v1.z) + (v2.z + v3.z); v.w += (v0.w + v1.w) + (v2.w + v3.w);
+      if (n_dfeat_parts == 4) {                      // the production split count at full slabs: 4 x DIT loads in flight
+        float4 w[DIT][4];
+#pragma unroll
+        for (int it = 0; it < DIT; ++it) {
+          const int i = tid + it * LBB_THREADS;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) w[it][q] = i < dn4 ? base4[(size_t)q * pstride4 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        for (; q < n_dfeat_parts; ++q) {
-          const float4 w = base4[(size_t)q * pstride4 + i];
-          v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+#pragma unroll
+        for (int it = 0; it < DIT; ++it) {
+          dv[it].x = (w[it][0].x + w[it][1].x) + (w[it][2].x + w[it][3].x);
+          dv[it].y = (w[it][0].y + w[it][1].y) + (w[it][2].y + w[it][3].y);
+          dv[it].z = (w[it][0].z + w[it][1].z) + (w[it][2].z + w[it][3].z);
+          dv[it].w = (w[it][0].w + w[it][1].w) + (w[it][2].w + w[it][3].w);
         }
-        const int e = i * 4, body = e / nf, k = e - body * nf;                        // nf is a multiple of 4
-        sm.DF[k * LB_P + body] = v.x; sm.DF[(k + 1) * LB_P + body] = v.y;
-        sm.DF[(k + 2) * LB_P + body] = v.z; sm.DF[(k + 3) * LB_P + body] = v.w;
+      } else {
+#pragma unroll
+        for (int it = 0; it < DIT; ++it) {
+          const int i = tid + it * LBB_THREADS;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < dn4) {
+            int q = 0;
+            for (; q + 4 <= n_dfeat_parts; q += 4) {
+              const float4 v0 = base4[(size_t)q * pstride4 + i], v1 = base4[(size_t)(q + 1) * pstride4 + i];
+              const float4 v2 = base4[(size_t)(q + 2) * pstride4 + i], v3 = base4[(size_t)(q + 3) * pstride4 + i];
+              v.x += (v0.x + v1.x) + (v2.x + v3.x); v.y += (v0.y + v1.y) + (v2.y + v3.y);
+              v.z += (v0.z + v1.z) + (v2.z + v3.z); v.w += (v0.w + v1.w) + (v2.w + v3.w);
+            }
+            for (; q < n_dfeat_parts; ++q) {
+              const float4 x = base4[(size_t)q * pstride4 + i];
+              v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+            }
+          }
+          dv[it] = v;
+        }
       }
     }
-    // ... the chain joints' own gradient, betas, model constants; accumulators cleared
-    for (int i = tid; i < 32 * NJ * 3; i += LBB_THREADS) {
-      const int body = i / (NJ * 3), k = i - body * (NJ * 3);
-      sm.DJo[k * LB_P + body] = (dJ != nullptr && body < nlive) ? dJ[(body0 + body) * m.njout * 3 + k] : 0.f;
+    float jv[JIT];
+#pragma unroll
+    for (int it = 0; it < JIT; ++it) {
+      const int i = tid + it * LBB_THREADS, body = i / (NJ * 3), k = i - body * (NJ * 3);
+      jv[it] = (dJ != nullptr && body < nlive) ? dJ[(body0 + body) * m.njout * 3 + k] : 0.f;
     }
-    for (int i = tid; i < 32 * nbeta; i += LBB_THREADS) {
-      const int body = i / nbeta, l = i - body * nbeta;
-      sm.B[l * 32 + body] = body < nlive ? betas[body0 * nbeta + i] : 0.f;
+    float bv = 0.f;
+    if (tid < 32 * nbeta && tid / nbeta < nlive) bv = betas[body0 * nbeta + tid];
+    // stores
+#pragma unroll
+    for (int it = 0; it < PIT; ++it) {
+      const int i = tid + it * LBB_THREADS;
+      if (al && i < nlive * PWc / 4) {
+        const float x[4] = {pv[it].x, pv[it].y, pv[it].z, pv[it].w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = i * 4 + u, body = e / PWc, k = e - body * PWc;
+          dstT[k * LB_P + body] = x[u];
+        }
+      }
     }
+    if (!al) {
+      const float* src = pose + body0 * PWc;
+      for (int i = tid; i < nlive * PWc; i += LBB_THREADS) {
+        const int body = i / PWc, k = i - body * PWc;
+        dstT[k * LB_P + body] = src[i];
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < DIT; ++it) {
+      const int i = tid + it * LBB_THREADS;
+      if (i < dn4) {
+        const int e = i * 4, body = e / nf, k = e - body * nf;                        // nf is a multiple of 4
+        sm.DF[k * LB_P + body] = dv[it].x; sm.DF[(k + 1) * LB_P + body] = dv[it].y;
+        sm.DF[(k + 2) * LB_P + body] = dv[it].z; sm.DF[(k + 3) * LB_P + body] = dv[it].w;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < JIT; ++it) {
+      const int i = tid + it * LBB_THREADS, body = i / (NJ * 3), k = i - body * (NJ * 3);
+      if (i < 32 * NJ * 3) sm.DJo[k * LB_P + body] = jv[it];
+    }
+    if (tid < 32 * nbeta) sm.B[(tid % nbeta) * 32 + tid / nbeta] = bv;
     for (int i = tid; i < NJ * 3 * nbeta; i += LBB_THREADS) sm.Jsd[i] = m.Jsd[i];
     if (tid < NJ * 3) sm.Jt[tid] = m.Jt[tid];
     for (int i = tid; i < NJ * 12 * 8; i += LBB_THREADS) reinterpret_cast<float4*>(sm.D)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -899,7 +944,7 @@ int launch_pose_bwd(const DevModel& m, const float* betas, const float* pose, bo
                     float* grad_transl, cudaStream_t st) {
   if (nb <= 0) return 0;
   const int grid = (nb + 31) / 32;
-  if ((pose_use_lb() & 2) && A_blk != nullptr && m.fl.nf_pad <= 224 && m.fl.nb <= LB_MAXB) {
+  if ((pose_use_lb() & 2) && A_blk != nullptr && m.fl.nf_pad <= 224 && m.fl.nb * 32 <= LBB_THREADS) {
     if (axis_angle) {
       B200_CUDA_TRY(cudaFuncSetAttribute(pose_bwd_lb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB_BWD_SMEM));
       LaunchTimer _timer("pose_bwd", st);
