@@ -437,174 +437,201 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
-// stage the group's rows of a row-major (B, W) tensor: sT[k * LB_P + body]; rows >= nlive are left untouched
-__device__ __forceinline__ void lb_stage_in(float* sT, const float* __restrict__ src, int W, int nlive, int lane) {
-  const int n = nlive * W;
-  for (int i = lane; i < n; i += 32) {
-    const int body = i / W, k = i - body * W;
-    sT[k * LB_P + body] = src[i];
-  }
-}
-__device__ __forceinline__ void lb_stage_out(const float* sT, float* __restrict__ dst, int W, int nlive, int lane) {
-  const int n = nlive * W;
-  for (int i = lane; i < n; i += 32) {
-    const int body = i / W, k = i - body * W;
-    dst[i] = sT[k * LB_P + body];
-  }
-}
+constexpr int LBF_THREADS = 512;
+struct LbFwdSmem {
+  float R[NJ * 9 * LB_P];        // local rotations [joint * 9 + e][body]
+  float AAx[NJ * 3 * LB_P];      // axis-angle input
+  float G[NJ * 12 * 32];         // global transforms, row-major [R | t]
+  float J[NJ * 3 * 32];          // rest joints
+  float B[LB_MAXB * 32];         // betas
+  float T[3 * 32];               // translation
+  float Jsd[NJ * 3 * LB_MAXB];
+  float Jt[NJ * 3];
+};
 
-// forward chain of one body; fills sR (local rotations), sJ (rest joints), sG (global transforms)
+// ---- forward, lane = body.  One CTA (16 warps) per 32-body group:
+//   P1 all threads: pose rows (transposed through registers), betas, translation, model constants;
+//   P2 all threads: rest joints (and Rodrigues for axis-angle input);
+//   P3 warp 0: the walk down the 24 joints, each lane ITS body: G_j = G_parent . [R_j | Jr_j - Jr_parent];
+//   P4 all threads: A = [G_R | G_t - G_R Jr] as coalesced float4, posed joints, the bf16 hi / lo feature row.
 template <bool AA>
-__device__ __forceinline__ void lb_chain_forward(const DevModel& m, const float* sAA, float* sR, float* sJ, float* sG,
-                                                 const float* sB, int lane, bool live) {
-  const int nbeta = m.fl.nb;
-#pragma unroll 1
-  for (int j = 0; j < NJ; ++j) {
-    float R[9];
-    if (AA) {
-      float r[3] = {0.f, 0.f, 0.f};
-      if (live) { r[0] = sAA[(j * 3) * LB_P + lane]; r[1] = sAA[(j * 3 + 1) * LB_P + lane]; r[2] = sAA[(j * 3 + 2) * LB_P + lane]; }
-      rodrigues_fwd(r, R);
-#pragma unroll
-      for (int e = 0; e < 9; ++e) sR[(j * 9 + e) * LB_P + lane] = R[e];
-    } else {
-#pragma unroll
-      for (int e = 0; e < 9; ++e) R[e] = live ? sR[(j * 9 + e) * LB_P + lane] : ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
-    }
-    float Jr[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      float acc = __ldg(m.Jt + j * 3 + k);
-      const float* sd = m.Jsd + (j * 3 + k) * nbeta;
-      for (int l = 0; l < nbeta; ++l) acc = fmaf(__ldg(sd + l), sB[l * 32 + lane], acc);
-      Jr[k] = acc;
-      sJ[(j * 3 + k) * 32 + lane] = acc;
-    }
-    const int p = m.chain.parent[j];
-    float G[12];
-    if (p < 0) {
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) G[r * 4 + c] = R[r * 3 + c];
-        G[r * 4 + 3] = Jr[r];
-      }
-    } else {
-      float P[12];
-#pragma unroll
-      for (int e = 0; e < 12; ++e) P[e] = sG[(p * 12 + e) * 32 + lane];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) G[r * 4 + c] = R[r * 3 + c];
-        G[r * 4 + 3] = Jr[r] - sJ[(p * 3 + r) * 32 + lane];
-      }
-      compose(P, G);
-    }
-#pragma unroll
-    for (int e = 0; e < 12; ++e) sG[(j * 12 + e) * 32 + lane] = G[e];
-  }
-}
-
-template <bool AA>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(LBF_THREADS, 1)
 pose_fwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __restrict__ pose, int b0, int nb, int S,
                    __nv_bfloat16* __restrict__ feat, float* __restrict__ featf, float* __restrict__ A_T,
                    const float* __restrict__ transl, float* __restrict__ joints) {
-  extern __shared__ __align__(16) float lbs_[];
-  float* sR = lbs_;                          // [216][LB_P]
-  float* sG = sR + NJ * 9 * LB_P;            // [288][32]
-  float* sJ = sG + NJ * 12 * 32;             // [72][32]
-  float* sB = sJ + NJ * 3 * 32;              // [LB_MAXB][32]
-  float* sAA = sB + LB_MAXB * 32;            // [72][LB_P] (axis-angle input only)
-  const int lane = threadIdx.x, g = blockIdx.x;
-  const int sc = g * 32 + lane, b = b0 + sc;
-  const bool live = sc < nb;
+  extern __shared__ __align__(16) unsigned char lbraw_[];
+  LbFwdSmem& sm = *reinterpret_cast<LbFwdSmem*>(lbraw_);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = blockIdx.x;
+  constexpr int NW = LBF_THREADS / 32;
   const int nlive = max(0, min(32, nb - g * 32));
+  const bool live = lane < nlive;
   const FeatLayout fl = m.fl;
+  const int nbeta = fl.nb;
+  const size_t body0 = (size_t)b0 + (size_t)g * 32;
   (void)S;
-  if (AA) lb_stage_in(sAA, pose + (size_t)(b0 + g * 32) * (NJ * 3), NJ * 3, nlive, lane);
-  else lb_stage_in(sR, pose + (size_t)(b0 + g * 32) * (NJ * 9), NJ * 9, nlive, lane);
-  for (int l = 0; l < fl.nb; ++l) sB[l * 32 + lane] = live ? betas[(size_t)b * fl.nb + l] : 0.f;
-  __syncwarp();
-  lb_chain_forward<AA>(m, sAA, sR, sJ, sG, sB, lane, live);
-  // ---- skinning transforms A = [G_R | G_t - G_R Jr] (paired float4 layout, see skin_common.cuh) and posed joints ----
-  float tr[3] = {0.f, 0.f, 0.f};
-  if (live && transl != nullptr) { tr[0] = transl[(size_t)b * 3]; tr[1] = transl[(size_t)b * 3 + 1]; tr[2] = transl[(size_t)b * 3 + 2]; }
-  float4* A4 = reinterpret_cast<float4*>(A_T) + (size_t)g * (NJ * 3 * 32) + lane;
+  // ---------------- P1 ----------------
+  {
+    constexpr int PWc = AA ? NJ * 3 : NJ * 9;
+    constexpr int PIT = (32 * PWc / 4 + LBF_THREADS - 1) / LBF_THREADS;
+    float* dstT = AA ? sm.AAx : sm.R;
+    const bool al = (reinterpret_cast<uintptr_t>(pose) & 15) == 0;
+    float4 pv[PIT];
+    const float4* src4 = reinterpret_cast<const float4*>(pose + body0 * PWc);
+    const int n4 = nlive * PWc / 4;
+#pragma unroll
+    for (int it = 0; it < PIT; ++it) {
+      const int i = tid + it * LBF_THREADS;
+      pv[it] = (al && i < n4) ? src4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float bv = 0.f, tv = 0.f;
+    if (tid < 32 * nbeta && tid / nbeta < nlive) bv = betas[body0 * nbeta + tid];
+    if (transl != nullptr && tid < 96 && tid / 3 < nlive) tv = transl[body0 * 3 + tid];
+    for (int i = tid; i < NJ * 3 * nbeta; i += LBF_THREADS) sm.Jsd[i] = m.Jsd[i];
+    if (tid < NJ * 3) sm.Jt[tid] = m.Jt[tid];
+#pragma unroll
+    for (int it = 0; it < PIT; ++it) {
+      const int i = tid + it * LBF_THREADS;
+      if (al && i < n4) {
+        const float x[4] = {pv[it].x, pv[it].y, pv[it].z, pv[it].w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = i * 4 + u, body = e / PWc, k = e - body * PWc;
+          dstT[k * LB_P + body] = x[u];
+        }
+      }
+    }
+    if (!al) {
+      const float* src = pose + body0 * PWc;
+      for (int i = tid; i < nlive * PWc; i += LBF_THREADS) {
+        const int body = i / PWc, k = i - body * PWc;
+        dstT[k * LB_P + body] = src[i];
+      }
+    }
+    if (tid < 32 * nbeta) sm.B[(tid % nbeta) * 32 + tid / nbeta] = bv;
+    if (tid < 96) sm.T[(tid % 3) * 32 + tid / 3] = tv;
+  }
+  __syncthreads();
+  // ---------------- P2 ----------------
+  for (int k = warp; k < NJ * 3; k += NW) {
+    float acc = sm.Jt[k];
+    for (int l = 0; l < nbeta; ++l) acc = fmaf(sm.Jsd[k * nbeta + l], sm.B[l * 32 + lane], acc);
+    sm.J[k * 32 + lane] = acc;
+  }
+  for (int j = warp; j < NJ; j += NW) {
+    if (AA) {
+      float r[3] = {0.f, 0.f, 0.f}, R[9];
+      if (live) { r[0] = sm.AAx[(j * 3) * LB_P + lane]; r[1] = sm.AAx[(j * 3 + 1) * LB_P + lane]; r[2] = sm.AAx[(j * 3 + 2) * LB_P + lane]; }
+      rodrigues_fwd(r, R);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) sm.R[(j * 9 + e) * LB_P + lane] = R[e];
+    } else if (!live) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) sm.R[(j * 9 + e) * LB_P + lane] = (e == 0 || e == 4 || e == 8) ? 1.f : 0.f;
+    }
+  }
+  __syncthreads();
+  // ---------------- P3 ----------------
+  if (warp == 0) {
 #pragma unroll 1
-  for (int j = 0; j < NJ; ++j) {
-    float G[12], Jr[3], t[3];
+    for (int j = 0; j < NJ; ++j) {
+      const int p = m.chain.parent[j];
+      float G[12];
 #pragma unroll
-    for (int e = 0; e < 12; ++e) G[e] = sG[(j * 12 + e) * 32 + lane];
+      for (int r = 0; r < 3; ++r) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) Jr[k] = sJ[(j * 3 + k) * 32 + lane];
+        for (int c = 0; c < 3; ++c) G[r * 4 + c] = sm.R[(j * 9 + r * 3 + c) * LB_P + lane];
+        G[r * 4 + 3] = sm.J[(j * 3 + r) * 32 + lane];
+      }
+      if (p >= 0) {
+        float P[12];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) t[r] = G[r * 4 + 3] - (G[r * 4] * Jr[0] + G[r * 4 + 1] * Jr[1] + G[r * 4 + 2] * Jr[2]);
+        for (int e = 0; e < 12; ++e) P[e] = sm.G[(p * 12 + e) * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) G[r * 4 + 3] -= sm.J[(p * 3 + r) * 32 + lane];
+        compose(P, G);
+      }
+#pragma unroll
+      for (int e = 0; e < 12; ++e) sm.G[(j * 12 + e) * 32 + lane] = G[e];
+    }
+  }
+  __syncthreads();
+  // ---------------- P4 ----------------
+  {
+    float4* A4 = reinterpret_cast<float4*>(A_T) + (size_t)g * (NJ * 3 * 32) + lane;
     const float z = live ? 1.f : 0.f;
-    A4[(j * 3 + 0) * 32] = make_float4(z * G[0], z * G[4], z * G[1], z * G[5]);
-    A4[(j * 3 + 1) * 32] = make_float4(z * G[2], z * G[6], z * t[0], z * t[1]);
-    A4[(j * 3 + 2) * 32] = make_float4(z * G[8], z * G[9], z * G[10], z * t[2]);
-    if (joints != nullptr && live) {
-      float* o = joints + ((size_t)b * m.njout + j) * 3;
-      o[0] = G[3] + tr[0]; o[1] = G[7] + tr[1]; o[2] = G[11] + tr[2];
-    }
-  }
-  // ---- feature row: slab 0 = [1 1 1 | betas hi | betas lo | betas hi], then pose feature hi / lo segments ----
-  uint4* frow = reinterpret_cast<uint4*>(feat + (size_t)sc * fl.pitch);
-#pragma unroll 1
-  for (int c = 0; c < 8; ++c) {
-    float v[8];
+    for (int j = warp; j < NJ; j += NW) {
+      float G[12], Jr[3], t[3];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int k = c * 8 + i;
-      float x = 0.f;
-      if (live) {
-        if (k < 3) x = 1.f;
-        else if (k >= fl.off_s0 && k < fl.off_s0 + fl.nb) x = __bfloat162float(bf_hi(sB[(k - fl.off_s0) * 32 + lane]));
-        else if (k >= fl.off_s1 && k < fl.off_s1 + fl.nb) {
-          const float be = sB[(k - fl.off_s1) * 32 + lane];
-          x = be - __bfloat162float(bf_hi(be));
-        } else if (k >= fl.off_s2 && k < fl.off_s2 + fl.nb) x = __bfloat162float(bf_hi(sB[(k - fl.off_s2) * 32 + lane]));
+      for (int e = 0; e < 12; ++e) G[e] = sm.G[(j * 12 + e) * 32 + lane];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Jr[k] = sm.J[(j * 3 + k) * 32 + lane];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) t[r] = G[r * 4 + 3] - (G[r * 4] * Jr[0] + G[r * 4 + 1] * Jr[1] + G[r * 4 + 2] * Jr[2]);
+      A4[(j * 3 + 0) * 32] = make_float4(z * G[0], z * G[4], z * G[1], z * G[5]);
+      A4[(j * 3 + 1) * 32] = make_float4(z * G[2], z * G[6], z * t[0], z * t[1]);
+      A4[(j * 3 + 2) * 32] = make_float4(z * G[8], z * G[9], z * G[10], z * t[2]);
+      if (joints != nullptr && live) {
+        float* o = joints + ((body0 + lane) * m.njout + j) * 3;
+        o[0] = G[3] + sm.T[lane]; o[1] = G[7] + sm.T[32 + lane]; o[2] = G[11] + sm.T[64 + lane];
       }
-      v[i] = x;
     }
-    frow[c] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-  }
-  const int pch = fl.pseg / 8;
-#pragma unroll 1
-  for (int c = 0; c < pch; ++c) {
-    uint32_t h[4], l[4];
+    // feature row: slab 0 = [1 1 1 | betas hi | betas lo | betas hi] (8 chunks), then the pose feature hi / lo
+    // segments (pseg / 8 chunk pairs); one item = one 16-byte chunk (or hi / lo pair) of every body of the group
+    uint4* frow = reinterpret_cast<uint4*>(feat + ((size_t)g * 32 + lane) * fl.pitch);
+    const int pch = fl.pseg / 8;
+    for (int item = warp; item < 8 + pch; item += NW) {
+      if (item < 8) {
+        float v[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float x[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int idx = c * 8 + i * 2 + u;
-        float pf = 0.f;
-        if (live && idx < NPOSE) {
-          const int e = idx % 9;
-          pf = sR[(9 + idx) * LB_P + lane] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+        for (int i = 0; i < 8; ++i) {
+          const int k = item * 8 + i;
+          float x = 0.f;
+          if (live) {
+            if (k < 3) x = 1.f;
+            else if (k >= fl.off_s0 && k < fl.off_s0 + nbeta) x = __bfloat162float(bf_hi(sm.B[(k - fl.off_s0) * 32 + lane]));
+            else if (k >= fl.off_s1 && k < fl.off_s1 + nbeta) {
+              const float be = sm.B[(k - fl.off_s1) * 32 + lane];
+              x = be - __bfloat162float(bf_hi(be));
+            } else if (k >= fl.off_s2 && k < fl.off_s2 + nbeta) x = __bfloat162float(bf_hi(sm.B[(k - fl.off_s2) * 32 + lane]));
+          }
+          v[i] = x;
         }
-        x[u] = pf;
-      }
-      split2(x[0], x[1], h[i], l[i]);
-    }
-    frow[8 + c] = make_uint4(h[0], h[1], h[2], h[3]);
-    frow[8 + pch + c] = make_uint4(l[0], l[1], l[2], l[3]);
-  }
-  if (featf != nullptr) {
-    float* fr = featf + (size_t)sc * fl.nf_pad;
-    for (int k = 0; k < fl.nf_pad; ++k) {
-      float x = 0.f;
-      if (live) {
-        if (k < fl.nb) x = sB[k * 32 + lane];
-        else if (k - fl.nb < NPOSE) {
-          const int idx = k - fl.nb, e = idx % 9;
-          x = sR[(9 + idx) * LB_P + lane] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+        frow[item] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      } else {
+        const int c = item - 8;
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float x[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int idx = c * 8 + i * 2 + u;
+            float pf = 0.f;
+            if (live && idx < NPOSE) {
+              const int e = idx % 9;
+              pf = sm.R[(9 + idx) * LB_P + lane] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+            }
+            x[u] = pf;
+          }
+          split2(x[0], x[1], h[i], l[i]);
         }
+        frow[8 + c] = make_uint4(h[0], h[1], h[2], h[3]);
+        frow[8 + pch + c] = make_uint4(l[0], l[1], l[2], l[3]);
       }
-      fr[k] = x;
+    }
+    if (featf != nullptr) {
+      float* fr = featf + ((size_t)g * 32 + lane) * fl.nf_pad;
+      for (int k = warp; k < fl.nf_pad; k += NW) {
+        float x = 0.f;
+        if (live) {
+          if (k < nbeta) x = sm.B[k * 32 + lane];
+          else if (k - nbeta < NPOSE) {
+            const int idx = k - nbeta, e = idx % 9;
+            x = sm.R[(9 + idx) * LB_P + lane] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+          }
+        }
+        fr[k] = x;
+      }
     }
   }
 }
@@ -896,12 +923,12 @@ pose_bwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __r
   }
 }
 
-constexpr size_t LB_FWD_SMEM = (size_t)(NJ * 9 * LB_P + NJ * 12 * 32 + NJ * 3 * 32 + LB_MAXB * 32 + NJ * 3 * LB_P) * 4;
+constexpr size_t LB_FWD_SMEM = sizeof(LbFwdSmem);
 constexpr size_t LB_BWD_SMEM = sizeof(LbBwdSmem);
 
 // B200_POSE_LB=0 selects the lane = joint kernels (kept for comparison)
 static int pose_use_lb() {   // bit 0: forward, bit 1: backward
-  static const int v = getenv("B200_POSE_LB") == nullptr ? 2 : atoi(getenv("B200_POSE_LB"));
+  static const int v = getenv("B200_POSE_LB") == nullptr ? 3 : atoi(getenv("B200_POSE_LB"));
   return v;
 }
 
@@ -910,16 +937,15 @@ int launch_pose_fwd(const DevModel& m, const float* betas, const float* pose, bo
                     int Sw, __nv_bfloat16* feat, float* featf, float* A_T, const float* transl, float* joints,
                     cudaStream_t st) {
   const int grid = Sw / 32;
-  if (pose_use_lb() & 1) {
-    if (m.fl.nb > LB_MAXB) return fail(B200SMPL_ERR_INVALID, "too many betas for the pose kernels");
+  if ((pose_use_lb() & 1) && m.fl.nb * 32 <= LBF_THREADS) {
     if (axis_angle) {
       B200_CUDA_TRY(cudaFuncSetAttribute(pose_fwd_lb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB_FWD_SMEM));
       LaunchTimer _timer("pose_fwd", st);
-      pose_fwd_lb_kernel<true><<<grid, 32, LB_FWD_SMEM, st>>>(m, betas, pose, b0, nb, S, feat, featf, A_T, transl, joints);
+      pose_fwd_lb_kernel<true><<<grid, LBF_THREADS, LB_FWD_SMEM, st>>>(m, betas, pose, b0, nb, S, feat, featf, A_T, transl, joints);
     } else {
       B200_CUDA_TRY(cudaFuncSetAttribute(pose_fwd_lb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB_FWD_SMEM));
       LaunchTimer _timer("pose_fwd", st);
-      pose_fwd_lb_kernel<false><<<grid, 32, LB_FWD_SMEM, st>>>(m, betas, pose, b0, nb, S, feat, featf, A_T, transl, joints);
+      pose_fwd_lb_kernel<false><<<grid, LBF_THREADS, LB_FWD_SMEM, st>>>(m, betas, pose, b0, nb, S, feat, featf, A_T, transl, joints);
     }
     B200_LAUNCH_CHECK("pose_fwd");
     return 0;
