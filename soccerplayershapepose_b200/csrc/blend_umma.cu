@@ -15,6 +15,7 @@
 // of STAGES x (128x64 + BNx64) bf16 tiles in the 128-byte swizzle; two CTAs can share an SM in
 // the forward configuration so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -861,11 +862,17 @@ blend_fwd_ws2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 // instead of once per 4 tiles (measured with clock64 counters in the MMA warp: 8-9 k of 35 k cycles waiting for
 // the resident slice, another 12 k refilling the ring, ~10 k draining).
 // ---------------------------------------------------------------------------------------------
+// work list of the body-stationary kernel: cluster c = body-tile pair bp[c], model-row tile pairs [w0[c], w1[c])
+constexpr int BS_MAX_WORK = 160;
+struct BsWork {
+  uint16_t bp[BS_MAX_WORK], w0[BS_MAX_WORK], w1[BS_MAX_WORK];
+};
+
 template <int DUMMY>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 blend_fwd_bs2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_f, int pslabs,
-                     int ksteps_cs, int ksteps_p, int use_lo, int row0, int mtiles, int ntiles_n, int wpairs_per_chunk,
-                     float4* __restrict__ vpB, int nc4) {
+                     int ksteps_cs, int ksteps_p, int use_lo, int row0, int mtiles, int ntiles_n,
+                     const __grid_constant__ BsWork work, float4* __restrict__ vpB, int nc4) {
   constexpr int SLAB = BM * BK * 2;
   constexpr int KS = BK / UMMA_K;
   constexpr uint32_t TMEM_COLS = 512;
@@ -887,10 +894,9 @@ blend_fwd_bs2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int btile = (int)blockIdx.x;                                  // this CTA's body tile (pair = blockIdx.x >> 1)
-  const int wtp_total = (mtiles + 1) / 2;
-  const int wtp_begin = blockIdx.y * wpairs_per_chunk;
-  const int wtp_end = min(wtp_total, wtp_begin + wpairs_per_chunk);
+  const int piece = (int)(blockIdx.x >> 1);
+  const int btile = (int)work.bp[piece] * 2 + (int)rank;              // this CTA's body tile
+  const int wtp_begin = work.w0[piece], wtp_end = work.w1[piece];
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_w);
@@ -1148,13 +1154,49 @@ static int launch_blend_fwd_umma_bs2(const DevModel& m, int mode, const __nv_bfl
   const int wtp_total = (mtiles + 1) / 2;
   const int ntiles_n = Sw / WS_BN;
   const int bp_total = (ntiles_n + 1) / 2;
-  // CTA pairs are scheduled per TPC (2 SMs): as many row chunks as keep all clusters in one wave
+  // CTA pairs are scheduled per TPC (2 SMs).  The (body pair, row-tile pair) list, body pair major, is cut into
+  // one equal range per TPC; a range that crosses into the next body pair becomes two clusters (the resident
+  // operand changes), longest pieces first so that the short ones fill the tail of the wave.
   const int tpcs = std::max(1, num_sms / 2);
-  const int chunks = std::max(1, std::min(wtp_total, tpcs / bp_total));
-  const int wpc = (wtp_total + chunks - 1) / chunks;
+  BsWork work;
+  int npieces = 0;
+  {
+    const long long total = (long long)bp_total * wtp_total;
+    const int nranges = (int)std::min<long long>(total, std::max(tpcs, bp_total));
+    struct Piece { int bp, w0, w1; };
+    std::vector<Piece> pieces;
+    for (int r = 0; r < nranges; ++r) {
+      long long lo = total * r / nranges, hi = total * (r + 1) / nranges;
+      while (lo < hi) {
+        const int bp = (int)(lo / wtp_total);
+        const long long end = std::min<long long>(hi, (long long)(bp + 1) * wtp_total);
+        pieces.push_back({bp, (int)(lo - (long long)bp * wtp_total), (int)(end - (long long)bp * wtp_total)});
+        lo = end;
+      }
+    }
+    // the plain rectangular split (every body pair cut into the same number of row chunks, one wave) is kept when
+    // its longest cluster is no longer than the flattened one plus a prologue, and for very wide slabs
+    const int rect_chunks = std::max(1, std::min(wtp_total, tpcs / std::max(1, bp_total)));
+    const int rect_len = (wtp_total + rect_chunks - 1) / rect_chunks;
+    const int flat_len = (int)((total + nranges - 1) / nranges);
+    if ((int)pieces.size() > BS_MAX_WORK || rect_len <= flat_len + 1) {
+      pieces.clear();
+      const int chunks = std::max(1, std::min(rect_chunks, BS_MAX_WORK / bp_total));
+      const int wpc = (wtp_total + chunks - 1) / chunks;
+      for (int bp = 0; bp < bp_total; ++bp)
+        for (int w = 0; w < wtp_total; w += wpc) pieces.push_back({bp, w, std::min(wtp_total, w + wpc)});
+      if ((int)pieces.size() > BS_MAX_WORK) return fail(B200SMPL_ERR_INVALID, "slab too wide for the forward GEMM work list");
+    }
+    std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& a, const Piece& b) { return a.w1 - a.w0 > b.w1 - b.w0; });
+    memset(&work, 0, sizeof(work));
+    for (const Piece& pc : pieces) {
+      work.bp[npieces] = (uint16_t)pc.bp; work.w0[npieces] = (uint16_t)pc.w0; work.w1[npieces] = (uint16_t)pc.w1;
+      ++npieces;
+    }
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(2 * bp_total, (wtp_total + wpc - 1) / wpc, 1);
+  cfg.gridDim = dim3(2 * npieces, 1, 1);
   cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -1167,7 +1209,7 @@ static int launch_blend_fwd_umma_bs2(const DevModel& m, int mode, const __nv_bfl
   cfg.numAttrs = 1;
   LaunchTimer _timer("blend_fwd_umma", st);
   B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map_w, map_f, pslabs, (m.fl.k_cs + UMMA_K - 1) / UMMA_K,
-                                   (NPOSE + UMMA_K - 1) / UMMA_K, use_lo, row_begin, mtiles, ntiles_n, wpc,
+                                   (NPOSE + UMMA_K - 1) / UMMA_K, use_lo, row_begin, mtiles, ntiles_n, work,
                                    reinterpret_cast<float4*>(vpT), m.n_pad / 4));
   B200_LAUNCH_CHECK("blend_fwd_umma");
   return 0;
@@ -1179,13 +1221,13 @@ int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat
   // B200_FWD_2CTA: 2 (default) body-stationary CTA pairs, 1 model-row-stationary CTA pairs, 0 single-CTA kernel
   // (the latter two are kept for comparison)
   static const int sel = getenv("B200_FWD_2CTA") == nullptr ? 2 : atoi(getenv("B200_FWD_2CTA"));
-  if (sel >= 2) {
+  if (sel >= 2 && (Sw / WS_BN + 1) / 2 <= BS_MAX_WORK) {     // wider slabs than 160 body-tile pairs: row-stationary kernel
     int dev = 0, sms = 148;
     B200_CUDA_TRY(cudaGetDevice(&dev));
     B200_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     return launch_blend_fwd_umma_bs2(m, mode, feat, S, Sw, vpT, row_begin, row_end, sms, st);
   }
-  if (sel == 1) return launch_blend_fwd_umma_2cta(m, mode, feat, S, Sw, vpT, row_begin, row_end, st);
+  if (sel >= 1) return launch_blend_fwd_umma_2cta(m, mode, feat, S, Sw, vpT, row_begin, row_end, st);
   const int pslabs = m.fl.pseg / BK;
   const int use_lo = (mode == B200SMPL_MODE_BF16) ? 0 : 1;
   if (1 + 2 * pslabs > WS_MAX_SLABS) return fail(B200SMPL_ERR_INVALID, "feature pitch too large for the resident operand");
