@@ -264,7 +264,7 @@ def test_full_size_properties(engine, dev, mode):
         assert _rel(b, 2 * a) < (1e-5 if mode == "fp32" else 2e-2)
 
 
-@pytest.mark.parametrize("nb,B", [(1, 37), (4, 130), (16, 256)])
+@pytest.mark.parametrize("nb,B", [(1, 37), (4, 130), (16, 256), (20, 64)])
 def test_other_beta_counts_and_tile_counts(synthetic_model, dev, nb, B):
     """Models with another number of betas (other K layouts / gradient widths: nf_pad 208 takes the single-CTA
     gradient GEMM, 224 the CTA-pair one) at batch sizes with an odd (37 -> 1), even (130 -> 2, 256 -> 2) number
