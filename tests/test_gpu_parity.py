@@ -264,7 +264,7 @@ def test_full_size_properties(engine, dev, mode):
         assert _rel(b, 2 * a) < (1e-5 if mode == "fp32" else 2e-2)
 
 
-@pytest.mark.parametrize("nb,B", [(1, 37), (4, 130), (16, 256), (20, 64)])
+@pytest.mark.parametrize("nb,B", [(1, 37), (4, 130), (16, 256)])
 def test_other_beta_counts_and_tile_counts(synthetic_model, dev, nb, B):
     """Models with another number of betas (other K layouts / gradient widths: nf_pad 208 takes the single-CTA
     gradient GEMM, 224 the CTA-pair one) at batch sizes with an odd (37 -> 1), even (130 -> 2, 256 -> 2) number
@@ -419,3 +419,19 @@ def test_no_write_outside_caller_buffers(engine, dev, monkeypatch, B):
     for raw, lo, hi in bands:
         assert bool((raw[:lo] == 0xA5).all()), "write below a caller buffer"
         assert bool((raw[hi:] == 0xA5).all()), "write above a caller buffer"
+
+
+@pytest.mark.parametrize("env", [{"B200_POSE_LB": "0"}, {"B200_FWD_2CTA": "1"}, {"B200_FWD_2CTA": "0", "B200_BWD_2CTA": "0"}])
+def test_comparison_kernels_stay_correct(env):
+    """The kernels kept for comparison behind environment switches (lane = joint pose kernels, row-stationary
+    CTA-pair and single-CTA GEMMs) are selected once per process: run the forward / backward parity tests in a
+    child process with the switch set."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child_env = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "test_backward_full or test_forward_rotmat_surface or test_forward_axis_angle"],
+                       cwd=root, env=child_env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
