@@ -165,6 +165,12 @@ B200SMPL_API int b200smpl_backward(const b200smpl_model* m, const b200smpl_backw
 
 /* ---- small in-tree helpers of the path, forward + hand-written backward -------------------- */
 
+/* smplx.lbs.batch_rodrigues (called directly by the reference at player_recon.py:201,655, hmr.py:207, and inside
+ * smplx.lbs.lbs when pose2rot=True): rot_vecs [n][3] -> R [n][3][3], theta = ||r + 1e-8|| as smplx computes it */
+B200SMPL_API int b200smpl_batch_rodrigues(const float* rot_vecs, float* rotmats, int64_t n, void* stream);
+B200SMPL_API int b200smpl_batch_rodrigues_backward(const float* rot_vecs, const float* grad_rotmats, float* grad_rot_vecs,
+                                                   int64_t n, void* stream);
+
 /* utils/rigid_transform_utils.py:27-41 rot6d_to_rotmat: x [n][3][2] -> R [n][3][3] (columns b1,b2,b3) */
 B200SMPL_API int b200smpl_rot6d_to_rotmat(const float* x6, float* rotmats, int64_t n, void* stream);
 B200SMPL_API int b200smpl_rot6d_to_rotmat_backward(const float* x6, const float* grad_rotmats, float* grad_x6, int64_t n,

@@ -70,6 +70,8 @@ SYMBOLS = {
     "b200smpl_backward_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "b200smpl_forward": (c_int, [c_void_p, POINTER(ForwardArgs), c_void_p]),
     "b200smpl_backward": (c_int, [c_void_p, POINTER(BackwardArgs), c_void_p]),
+    "b200smpl_batch_rodrigues": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "b200smpl_batch_rodrigues_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b200smpl_rot6d_to_rotmat": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "b200smpl_rot6d_to_rotmat_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b200smpl_orthographic_project": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),

@@ -5,8 +5,32 @@
 // All are tiny element-wise / per-body kernels; they exist so the whole fitting / training step
 // stays on hand-written kernels with no eager-op launches in between.
 #include "common.cuh"
+#include "rodrigues.cuh"
 
 namespace b200smpl {
+
+// smplx.lbs.batch_rodrigues as a standalone op (the reference calls it directly at
+// player_recon.py:201,655 and hmr.py:207): one thread per rotation vector
+__global__ void rodrigues_fwd_kernel(const float* __restrict__ rv, float* __restrict__ R, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float r[3] = {rv[i * 3], rv[i * 3 + 1], rv[i * 3 + 2]};
+  float o[9];
+  rodrigues_fwd(r, o);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) R[i * 9 + e] = o[e];
+}
+__global__ void rodrigues_bwd_kernel(const float* __restrict__ rv, const float* __restrict__ gR, float* __restrict__ grv,
+                                     long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float r[3] = {rv[i * 3], rv[i * 3 + 1], rv[i * 3 + 2]};
+  float g[9], d[3];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) g[e] = gR[i * 9 + e];
+  rodrigues_bwd(r, g, d);
+  grv[i * 3] = d[0]; grv[i * 3 + 1] = d[1]; grv[i * 3 + 2] = d[2];
+}
 
 // F.normalize(v, dim=1, eps=1e-12): v / max(||v||, eps)
 __device__ __forceinline__ float safe_norm(const float v[3]) {
@@ -272,6 +296,23 @@ __global__ void j2d_loss_kernel(const float* __restrict__ joints, const float* _
 using namespace b200smpl;
 
 extern "C" {
+
+int b200smpl_batch_rodrigues(const float* rot_vecs, float* rotmats, int64_t n, void* stream) {
+  if (!rot_vecs || !rotmats || n < 0) return fail(B200SMPL_ERR_INVALID, "bad argument");
+  if (n == 0) return 0;
+  rodrigues_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rot_vecs, rotmats, n);
+  B200_LAUNCH_CHECK("rodrigues_fwd");
+  return 0;
+}
+
+int b200smpl_batch_rodrigues_backward(const float* rot_vecs, const float* grad_rotmats, float* grad_rot_vecs, int64_t n,
+                                      void* stream) {
+  if (!rot_vecs || !grad_rotmats || !grad_rot_vecs || n < 0) return fail(B200SMPL_ERR_INVALID, "bad argument");
+  if (n == 0) return 0;
+  rodrigues_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rot_vecs, grad_rotmats, grad_rot_vecs, n);
+  B200_LAUNCH_CHECK("rodrigues_bwd");
+  return 0;
+}
 
 int b200smpl_rot6d_to_rotmat(const float* x6, float* rotmats, int64_t n, void* stream) {
   if (!x6 || !rotmats || n < 0) return fail(B200SMPL_ERR_INVALID, "bad argument");

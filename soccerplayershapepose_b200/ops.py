@@ -49,6 +49,36 @@ def rot6d_to_rotmat(x: torch.Tensor) -> torch.Tensor:
     return _Rot6d.apply(x.reshape(-1, 6))
 
 
+class _Rodrigues(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rot_vecs):
+        x = _req(rot_vecs, "rot_vecs").reshape(-1, 3)
+        n = x.shape[0]
+        out = torch.empty((n, 3, 3), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().b200smpl_batch_rodrigues(x.data_ptr(), out.data_ptr(), n, _stream(x)), "batch_rodrigues")
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = g.contiguous()
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().b200smpl_batch_rodrigues_backward(x.data_ptr(), g.data_ptr(), gx.data_ptr(),
+                                                                     x.shape[0], _stream(x)), "batch_rodrigues_bwd")
+        return gx
+
+
+def batch_rodrigues(rot_vecs: torch.Tensor, epsilon: float = 1e-8) -> torch.Tensor:
+    """smplx.lbs.batch_rodrigues (reference call sites: player_recon.py:201,655, hmr.py:207): (N,3) axis-angle ->
+    (N,3,3), with the library's `angle = ||r + 1e-8||`; differentiable.  Only the default epsilon is implemented."""
+    if epsilon != 1e-8:
+        raise ValueError("batch_rodrigues: only epsilon=1e-8 (the smplx default) is implemented")
+    return _Rodrigues.apply(rot_vecs.reshape(-1, 3))
+
+
 class _Ortho(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pts, cam, pixel_wh):
