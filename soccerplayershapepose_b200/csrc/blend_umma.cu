@@ -86,6 +86,30 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* src, uint32
                ::"r"(smem_u32(smem_dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// the same two copies with an L2 eviction-priority hint (createpolicy): a stream that is read once must not push
+// the small operand every cluster re-reads out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(smem_dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
 // cluster helpers: multicast TMA load (same smem / mbarrier offsets in every CTA of the mask), multicast commit
 __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                                uint16_t cta_mask) {
@@ -388,6 +412,8 @@ umma_gemm2_kernel(const __grid_constant__ GemmOps ops, int split3, int nc8, int 
 
   if (warp == 0) {
     // ===== producer (both CTAs): own dvp tiles + own halves of the Wb slabs =====
+    // dvp is read once, the model slabs by every body pair: keep the latter in L2
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     int stage = 0;
     uint32_t phase = 0;
     for (int it = 0; it < total_iters; ++it) {
@@ -397,11 +423,11 @@ umma_gemm2_kernel(const __grid_constant__ GemmOps ops, int split3, int nc8, int 
       if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
         const size_t aoff = (((size_t)blockIdx.x * nc8 + (size_t)slab * 8) * 128) * 8;
-        bulk_g2s(sa, ops.a[0] + aoff, A_BYTES, &full_bar[stage]);
-        tma_load_2d(sa + off_bhi, &ops.b[0], &full_bar[stage], slab * BK, (int)rank * BNH);
+        bulk_g2s_hint(sa, ops.a[0] + aoff, A_BYTES, &full_bar[stage], pol_stream);
+        tma_load_2d_hint(sa + off_bhi, &ops.b[0], &full_bar[stage], slab * BK, (int)rank * BNH, pol_keep);
         if (split3) {
-          bulk_g2s(sa + off_alo, ops.a[1] + aoff, A_BYTES, &full_bar[stage]);
-          tma_load_2d(sa + off_blo, &ops.b[2], &full_bar[stage], slab * BK, (int)rank * BNH);
+          bulk_g2s_hint(sa + off_alo, ops.a[1] + aoff, A_BYTES, &full_bar[stage], pol_stream);
+          tma_load_2d_hint(sa + off_blo, &ops.b[2], &full_bar[stage], slab * BK, (int)rank * BNH, pol_keep);
         }
       }
       __syncwarp();
