@@ -961,6 +961,7 @@ blend_fwd_bs2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
       for (int s = 0; s < nslab_f; ++s) tma_load_2d(f_s + s * SLAB, &map_f, f_full, s * BK, btile * WS_BN);
     }
     __syncwarp();
+    const uint64_t pol_keep = l2_policy_evict_last();       // the model slabs are re-read by every body pair
     int stage = 0;
     uint32_t phase = 0;
     for (int wtp = wtp_begin; wtp < wtp_end; ++wtp)
@@ -969,7 +970,7 @@ blend_fwd_bs2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
         if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], SLAB);
           // a row tile beyond the model (odd number of row tiles) is zero-filled by the TMA unit
-          tma_load_2d(w_s + stage * SLAB, &map_w, &full_bar[stage], s * BK, row0 + (wtp * 2 + (int)rank) * BM);
+          tma_load_2d_hint(w_s + stage * SLAB, &map_w, &full_bar[stage], s * BK, row0 + (wtp * 2 + (int)rank) * BM, pol_keep);
         }
         __syncwarp();
         if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
