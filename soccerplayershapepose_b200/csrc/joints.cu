@@ -96,7 +96,7 @@ joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
 
 // backward over virtual tiles.  dJ: total joint gradient (B, NJout, 3).
 //   dq -> virtual rows of dvp ; dA, dtransl -> fp32 REDs into the slab accumulators
-__global__ void __launch_bounds__(JT, 3)
+__global__ void __launch_bounds__(JT, 2)
 joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const float4* __restrict__ A_blk, int b0, int nb,
                   int pitch, const float* __restrict__ dJ, __nv_bfloat16* __restrict__ dvp_hi,
                   __nv_bfloat16* __restrict__ dvp_lo, float* __restrict__ dA_acc, float* __restrict__ dtr_acc) {
