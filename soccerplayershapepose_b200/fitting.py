@@ -142,3 +142,168 @@ class BatchedFitter:
                "last_loss": st["loss"]}
         self._state = st
         return out
+
+
+class MultiViewFitter:
+    """Batched restatement of the reference's `multi_view_optimization`
+    (PlayerReconstruction/player_recon.py:1568-1999) for P independent players seen from V views each.
+
+    Per player, as there: body pose and betas are shared by the views, global orientation and weak-perspective
+    camera are per view.  `rounds` (3, player_recon.py:1721) times: phase A optimises the per-view cameras and
+    global orientations with a fresh Adam (:1734-1740), phase B the body pose -- hands / feet joints frozen
+    (:1706-1708, 1723-1732) -- and the betas with another fresh Adam (:1863-1869).  An epoch walks the views in a
+    shuffled order with ONE optimiser step per view (:1746-1749, 1813-1814); because the per-view parameters are
+    stacked tensors, a step on view v also moves the other views by their Adam momentum (zero gradient), exactly as
+    `optim.Adam([cam_wp_mult, global_orient_mult])` does.  After the training pass every view is evaluated again
+    (the `is_train = False` pass) and the parameters of the epoch are kept when the summed validation loss is the
+    best the player has seen in any phase so far (:1823-1838, 1938-1954); each phase ends by restoring its
+    parameters to their best epoch (:1846-1847, 1961-1962).  Differences, stated: the loss is the joints2D term only
+    (the silhouette term needs the reference's renderer), model selection uses that loss instead of the
+    metrics tracker's joints2D / silhouette metrics, and the shuffled view order of an epoch is shared by all
+    players of the batch (the reference shuffles per player).
+
+    Every step is the C-ABI sequence of `BatchedFitter` (joints-only forward, fused loss, backward, fused Adam);
+    the glue between steps (slice copies, the per-epoch comparison) is a handful of tiny elementwise torch ops.
+    """
+
+    def __init__(self, smpl: SMPL, lr: float = 1e-3, rounds: int = 3, shape_weight: float = 0.0,
+                 joints2d_log_var: float = 0.0, proj_wh: float = 512.0, norm_wh: float = float(config.REGRESSOR_IMG_WH),
+                 betas: tuple = (0.9, 0.999), eps: float = 1e-8, mode: Optional[str] = None):
+        self.base = BatchedFitter(smpl, lr=lr, shape_weight=shape_weight, joints2d_log_var=joints2d_log_var,
+                                  proj_wh=proj_wh, norm_wh=norm_wh, betas=betas, eps=eps, use_cuda_graph=False, mode=mode)
+        self.rounds = int(rounds)
+        dev = self.base.dev
+        frozen = torch.zeros(23, 9, dtype=torch.uint8)
+        for j in (6, 7, 21, 22):                     # body_pose[:, 6:8] and body_pose[:, 21:]
+            frozen[j] = 1
+        self.frozen_bp = frozen.reshape(-1).to(dev)
+        self._inc = torch.tensor([0, 1], dtype=torch.int32, device=dev)
+
+    # one Adam step of `p` (rows, cols) through the C-ABI; `step` holds [committed, current]
+    def _adam(self, p, g, extra, m, v, step, frozen, never):
+        b = self.base
+        _lib.check(b.lib.b200smpl_fit_adam_step(
+            p.data_ptr(), g.data_ptr(), None if extra is None else extra.data_ptr(), m.data_ptr(), v.data_ptr(),
+            p.data_ptr(), never.data_ptr(), None if frozen is None else frozen.data_ptr(), step.data_ptr(), 0,
+            p.shape[0], p.shape[1], b.lr, b.b1, b.b2, b.eps,
+            ctypes.c_void_p(torch.cuda.current_stream(b.dev).cuda_stream)), "fit_adam_step")
+
+    def _loss(self, st, v, need_grad):
+        """Forward of view v with the current parameters; fills st['loss'] (and the gradients)."""
+        b = self.base
+        st["rot"][:, :9] = st["go"][v]
+        _, joints, _ = b.eng.forward(st["betas"], st["rot"], None, None, axis_angle=False, mode=b.mode, want_vertices=False)
+        vis = st.get("vis")
+        stream = ctypes.c_void_p(torch.cuda.current_stream(b.dev).cuda_stream)
+        P = st["rot"].shape[0]
+        _lib.check(b.lib.b200smpl_fit_loss(
+            joints.data_ptr(), st["cam"][v].data_ptr(), b.jmap.data_ptr(), st["label"][v].data_ptr(),
+            None if vis is None else vis[v].data_ptr(), st["betas"].data_ptr(), P, joints.shape[1], b.jmap.numel(),
+            st["betas"].shape[1], b.proj_wh, b.norm_wh, b.log_var, b.shape_weight, st["loss"].data_ptr(),
+            st["gj"].data_ptr(), st["gcam"].data_ptr(), st["gbetas_prior"].data_ptr(), stream), "fit_loss")
+        if not need_grad:
+            return None
+        gb, gp, _, _ = b.eng.backward(st["betas"], st["rot"], None, None, None, None, st["gj"], None,
+                                      axis_angle=False, mode=b.mode, need_transl=False, need_cam=False)
+        return gb, gp
+
+    def fit(self, body_pose: torch.Tensor, betas: torch.Tensor, global_orient: torch.Tensor, cam: torch.Tensor,
+            keypoints2d: torch.Tensor, vis: Optional[torch.Tensor] = None, iterations: int = 10,
+            view_orders=None, seed: int = 0) -> Dict[str, torch.Tensor]:
+        """body_pose (P,23,3,3) and betas (P,10) shared by the views; global_orient (P,V,3,3), cam (P,V,3),
+        keypoints2d (P,V,17,2) [, vis (P,V,17)] per view.  `iterations` epochs per phase.  `view_orders`: optional
+        list (one per epoch, in execution order: round 0 phase A, round 0 phase B, ...) of view permutations."""
+        b = self.base
+        dev = b.dev
+        f32 = dict(dtype=torch.float32, device=dev)
+        P, V = global_orient.shape[0], global_orient.shape[1]
+        st = {"go": global_orient.to(**f32).reshape(P, V, 9).transpose(0, 1).contiguous(),          # (V,P,9)
+              "cam": cam.to(**f32).transpose(0, 1).contiguous(),                                    # (V,P,3)
+              "label": keypoints2d.to(**f32).transpose(0, 1).contiguous(),                          # (V,P,17,2)
+              "bp": body_pose.to(**f32).reshape(P, 207).clone().contiguous(),
+              "betas": betas.to(**f32).clone().contiguous()}
+        if vis is not None:
+            st["vis"] = vis.to(device=dev, dtype=torch.uint8).transpose(0, 1).contiguous()
+        st["rot"] = torch.empty((P, 216), **f32)
+        st["rot"][:, 9:] = st["bp"]
+        st["loss"] = torch.zeros(P, **f32)
+        st["gj"] = torch.zeros((P, b.eng.num_joints_out, 3), **f32)
+        st["gcam"] = torch.zeros((P, 3), **f32)
+        st["gbetas_prior"] = torch.zeros((P, st["betas"].shape[1]), **f32)
+        g_go, g_cam = torch.zeros_like(st["go"]), torch.zeros_like(st["cam"])
+        g_bp = torch.zeros_like(st["bp"])
+        mom = {k: (torch.zeros_like(st[k]), torch.zeros_like(st[k])) for k in ("go", "cam", "bp", "betas")}
+        step = torch.zeros(2, dtype=torch.int32, device=dev)
+        never_vp = torch.zeros(V * P, dtype=torch.uint8, device=dev)
+        best_metric = torch.full((P,), float("inf"), **f32)
+        best = {k: st[k].clone() for k in ("go", "cam", "bp", "betas")}          # per-phase restore points
+        final = {k: st[k].clone() for k in ("go", "cam", "bp", "betas")}         # everything at the best epoch
+        gen = torch.Generator().manual_seed(seed)
+        first_val = None
+        epoch_no = 0
+
+        def order():
+            nonlocal epoch_no
+            o = list(view_orders[epoch_no]) if view_orders is not None else torch.randperm(V, generator=gen).tolist()
+            epoch_no += 1
+            return o
+
+        def validate(phase_keys):
+            nonlocal best_metric, first_val
+            val = torch.zeros(P, **f32)
+            for v in range(V):
+                self._loss(st, v, need_grad=False)
+                val += st["loss"]
+            if first_val is None:
+                first_val = val.clone()
+            improved = val < best_metric
+            best_metric = torch.where(improved, val, best_metric)
+            for k in ("go", "cam", "bp", "betas"):
+                mask = improved.view(1, P, 1) if k in ("go", "cam") else improved.view(P, 1)
+                final[k] = torch.where(mask, st[k], final[k])
+                if k in phase_keys:
+                    best[k] = torch.where(mask, st[k], best[k])
+
+        for _ in range(self.rounds):
+            # ---- phase A: per-view camera and global orientation ----
+            for k in ("go", "cam"):
+                mom[k][0].zero_(); mom[k][1].zero_()
+            step.zero_()
+            for _e in range(iterations):
+                for v in order():
+                    _, gp = self._loss(st, v, need_grad=True)
+                    g_go.zero_(); g_cam.zero_()
+                    g_go[v] = gp[:, :9]
+                    g_cam[v] = st["gcam"]
+                    step += self._inc
+                    self._adam(st["go"].view(V * P, 9), g_go.view(V * P, 9), None, mom["go"][0].view(V * P, 9),
+                               mom["go"][1].view(V * P, 9), step, None, never_vp)
+                    self._adam(st["cam"].view(V * P, 3), g_cam.view(V * P, 3), None, mom["cam"][0].view(V * P, 3),
+                               mom["cam"][1].view(V * P, 3), step, None, never_vp)
+                validate(("go", "cam"))
+            st["go"].copy_(best["go"]); st["cam"].copy_(best["cam"])
+            # ---- phase B: shared body pose (hands / feet frozen) and betas ----
+            for k in ("bp", "betas"):
+                mom[k][0].zero_(); mom[k][1].zero_()
+            step.zero_()
+            for _e in range(iterations):
+                for v in order():
+                    gb, gp = self._loss(st, v, need_grad=True)
+                    g_bp.copy_(gp[:, 9:])
+                    step += self._inc
+                    self._adam(st["bp"], g_bp, None, mom["bp"][0], mom["bp"][1], step, self.frozen_bp, never_vp)
+                    self._adam(st["betas"], gb, st["gbetas_prior"], mom["betas"][0], mom["betas"][1], step, None, never_vp)
+                    st["rot"][:, 9:] = st["bp"]
+                validate(("bp", "betas"))
+            st["bp"].copy_(best["bp"]); st["betas"].copy_(best["betas"])
+            st["rot"][:, 9:] = st["bp"]
+
+        go = final["go"].transpose(0, 1).reshape(P, V, 3, 3).contiguous()
+        cam_out = final["cam"].transpose(0, 1).contiguous()
+        return {"body_pose": final["bp"].reshape(P, 23, 3, 3), "betas": final["betas"], "global_orient": go,
+                "cam": cam_out,
+                "translation": convert_weak_perspective_to_camera_translation_torch(
+                    cam_out.reshape(P * V, 3), config.FOCAL_LENGTH, b.proj_wh).reshape(P, V, 3),
+                "best_loss": best_metric, "initial_loss": first_val,
+                "last": {"body_pose": st["bp"].reshape(P, 23, 3, 3), "betas": st["betas"],
+                         "global_orient": st["go"].transpose(0, 1).reshape(P, V, 3, 3), "cam": st["cam"].transpose(0, 1)}}

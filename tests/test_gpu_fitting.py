@@ -115,3 +115,118 @@ def test_fit_result_keys_and_translation(setup):
     assert res["betas"].shape == (B, 10) and res["translation"].shape == (B, 3)
     t = O.weak_perspective_to_translation(res["cam"].cpu().double(), config.FOCAL_LENGTH, 512)
     np.testing.assert_allclose(res["translation"].cpu().double().numpy(), t.numpy(), rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-view optimisation (player_recon.py:1568-1999)
+# ---------------------------------------------------------------------------------------------
+def _ref_multiview(model, bp0, betas0, go0, cam0, label, iters, lr, rounds, orders):
+    """The reference's alternating loop restated on the oracle (float64, CPU), joints2D loss only: stacked per-view
+    tensors under ONE Adam (so a step on one view moves the others by momentum), fresh optimisers per phase, a
+    validation pass per epoch, per-phase restore to the best epoch, global best kept for the result."""
+    from soccerplayershapepose_b200.fitting import MultiViewFitter  # noqa: F401  (same module is under test)
+    orc = O.SMPLOracle(model, dtype=torch.float64)
+    P, V = go0.shape[0], go0.shape[1]
+    go = go0.double().transpose(0, 1).contiguous().clone()          # (V,P,3,3)
+    cam = cam0.double().transpose(0, 1).contiguous().clone()        # (V,P,3)
+    bp = bp0.double().clone()
+    betas = betas0.double().clone()
+    lab = label.double().transpose(0, 1)
+    frozen = [6, 7, 21, 22]
+
+    def loss_view(v):
+        rot = torch.cat([go[v][:, None], bp], 1)
+        out = orc.forward_flat(betas, rot, None, pose2rot=False)
+        j2d = O.orthographic_project(out.joints, cam[v])[:, config.SMPL_TO_KPRCNN_MAP, :]
+        px = O.undo_keypoint_normalisation(j2d, 512)
+        d = (2.0 * px / config.REGRESSOR_IMG_WH - 1.0) - (2.0 * lab[v] / config.REGRESSOR_IMG_WH - 1.0)
+        return (d * d).mean(dim=(1, 2))
+
+    best_metric = torch.full((P,), float("inf"), dtype=torch.float64)
+    best = {"go": go.clone(), "cam": cam.clone(), "bp": bp.clone(), "betas": betas.clone()}
+    final = {k: t.clone() for k, t in best.items()}
+    e = 0
+    first_val = None
+    for _ in range(rounds):
+        for phase in ("A", "B"):
+            params = {"A": {"cam": cam, "go": go}, "B": {"bp": bp, "betas": betas}}[phase]
+            for t in params.values():
+                t.requires_grad_(True)
+            opt = torch.optim.Adam(list(params.values()), lr=lr)
+            for _e in range(iters):
+                for v in orders[e]:
+                    opt.zero_grad()
+                    loss_view(v).sum().backward()
+                    if phase == "B":
+                        bp.grad[:, frozen] = 0.0
+                    opt.step()
+                e += 1
+                with torch.no_grad():
+                    val = sum(loss_view(v) for v in range(V))
+                    if first_val is None:
+                        first_val = val.clone()
+                    imp = val < best_metric
+                    best_metric = torch.where(imp, val, best_metric)
+                    cur = {"go": go, "cam": cam, "bp": bp, "betas": betas}
+                    for k in cur:
+                        dst = [final[k]] + ([best[k]] if k in params else [])
+                        for d_ in dst:
+                            if k in ("go", "cam"):
+                                d_[:, imp] = cur[k].detach()[:, imp]
+                            else:
+                                d_[imp] = cur[k].detach()[imp]
+            for t in params.values():
+                t.requires_grad_(False)
+            with torch.no_grad():
+                for k in params:
+                    params[k].copy_(best[k])
+    return {"final": final, "best_metric": best_metric, "first_val": first_val,
+            "last": {"go": go, "cam": cam, "bp": bp, "betas": betas}}
+
+
+def test_multi_view_fit_matches_reference_loop(setup):
+    from soccerplayershapepose_b200.fitting import MultiViewFitter
+    model, smpl, dev = setup
+    P, V, iters, rounds, lr = 4, 3, 3, 2, 2e-3
+    g = torch.Generator().manual_seed(5)
+    betas_t = torch.randn(P, 10, generator=g) * 0.8
+    bp_aa = torch.randn(P, 69, generator=g) * 0.25
+    go_aa = torch.randn(P, V, 3, generator=g) * 0.6
+    cam_t = torch.stack([0.6 + 0.6 * torch.rand(P, V, generator=g), 0.4 * torch.rand(P, V, generator=g) - 0.2,
+                         0.4 * torch.rand(P, V, generator=g) - 0.2], -1)
+    bp_t = O.batch_rodrigues(bp_aa.reshape(-1, 3)).reshape(P, 23, 3, 3)
+    go_t = O.batch_rodrigues(go_aa.reshape(-1, 3)).reshape(P, V, 3, 3)
+    orc = O.SMPLOracle(model, dtype=torch.float64)
+    label = torch.empty(P, V, 17, 2)
+    for v in range(V):
+        out = orc.forward_flat(betas_t.double(), torch.cat([go_t[:, v:v + 1], bp_t], 1).double(), None, pose2rot=False)
+        j2d = O.orthographic_project(out.joints, cam_t[:, v].double())[:, config.SMPL_TO_KPRCNN_MAP, :]
+        label[:, v] = O.undo_keypoint_normalisation(j2d, 512).float()
+    betas0 = betas_t + 0.5 * torch.randn(P, 10, generator=g)
+    bp0 = O.batch_rodrigues((bp_aa + 0.15 * torch.randn(P, 69, generator=g)).reshape(-1, 3)).reshape(P, 23, 3, 3)
+    go0 = O.batch_rodrigues((go_aa + 0.1 * torch.randn(P, V, 3, generator=g)).reshape(-1, 3)).reshape(P, V, 3, 3)
+    cam0 = cam_t + 0.05 * torch.randn(P, V, 3, generator=g)
+    rng = np.random.default_rng(0)
+    orders = [rng.permutation(V).tolist() for _ in range(rounds * 2 * iters)]
+    ref = _ref_multiview(model, bp0, betas0, go0, cam0, label, iters, lr, rounds, orders)
+    res = MultiViewFitter(smpl, lr=lr, rounds=rounds).fit(bp0.to(dev), betas0.to(dev), go0.to(dev), cam0.to(dev),
+                                                          label.to(dev), iterations=iters, view_orders=orders)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(res["initial_loss"].cpu().double().numpy(), ref["first_val"].numpy(), rtol=2e-3)
+    np.testing.assert_allclose(res["best_loss"].cpu().double().numpy(), ref["best_metric"].numpy(), rtol=5e-3)
+    nsteps = rounds * iters * V
+    pairs = ((res["body_pose"].reshape(P, 207), ref["final"]["bp"].reshape(P, 207)),
+             (res["betas"], ref["final"]["betas"]),
+             (res["global_orient"].reshape(P, V, 9), ref["final"]["go"].transpose(0, 1).reshape(P, V, 9)),
+             (res["cam"], ref["final"]["cam"].transpose(0, 1)),
+             (res["last"]["body_pose"].reshape(P, 207), ref["last"]["bp"].reshape(P, 207)),
+             (res["last"]["global_orient"].reshape(P, V, 9), ref["last"]["go"].transpose(0, 1).reshape(P, V, 9)))
+    for got, want in pairs:
+        diff = (got.cpu().double() - want.detach()).abs()
+        assert diff.median().item() < 2e-5 and diff.max().item() < 2 * lr * nsteps
+        assert torch.quantile(diff.flatten(), 0.99).item() < 3e-3
+    # hands and feet of the shared body pose never move; the result carries the reference's keys
+    fz = [6, 7, 21, 22]
+    assert torch.equal(res["last"]["body_pose"][:, fz].cpu(), bp0[:, fz])
+    assert res["translation"].shape == (P, V, 3) and res["global_orient"].shape == (P, V, 3, 3)
+    assert (res["best_loss"] < res["initial_loss"]).all()
