@@ -19,7 +19,8 @@ Restates the optimisation loop of the reference's `single_view_optimization`
     translation (`convert_weak_perspective_to_camera_translation`, cam_utils.py:44-52).
 
 Only the joints are computed (virtual rows of the blend GEMM, no vertex is skinned).  One iteration = 9 kernel
-launches through the C-ABI; after one eager iteration the iteration is captured in a CUDA graph and replayed.
+launches through the C-ABI; after one eager iteration, twenty consecutive iterations are captured in one CUDA
+graph (kept, with its state buffers, for later calls of the same shape) and replayed.
 CUDA float32 only: there is no CPU path.
 """
 from __future__ import annotations
@@ -40,7 +41,7 @@ class BatchedFitter:
     def __init__(self, smpl: SMPL, lr: float = 1e-3, shape_weight: float = 0.0, joints2d_log_var: float = 0.0,
                  proj_wh: float = 512.0, norm_wh: float = float(config.REGRESSOR_IMG_WH),
                  betas: tuple = (0.9, 0.999), eps: float = 1e-8, use_cuda_graph: bool = True,
-                 frozen_joints=FROZEN_FULL_JOINTS, mode: Optional[str] = None):
+                 frozen_joints=FROZEN_FULL_JOINTS, mode: Optional[str] = None, graph_iterations: int = 20):
         dev = next(smpl.buffers()).device
         if dev.type != "cuda":
             raise RuntimeError("BatchedFitter needs the SMPL module on a CUDA device (no CPU path)")
@@ -52,12 +53,13 @@ class BatchedFitter:
         self.proj_wh, self.norm_wh = float(proj_wh), float(norm_wh)
         self.b1, self.b2, self.eps = float(betas[0]), float(betas[1]), float(eps)
         self.use_graph = use_cuda_graph
+        self.graph_iterations = int(graph_iterations)
         self.jmap = torch.tensor(config.SMPL_TO_KPRCNN_MAP, dtype=torch.int32, device=dev)
         frozen = torch.zeros(24, 9, dtype=torch.uint8)
         for j in frozen_joints:
             frozen[j] = 1
         self.frozen_rot = frozen.reshape(-1).to(dev)
-        self._graph = None
+        self._cache = {}
         self._state = None
 
     # ---- one iteration: every call below is one C-ABI entry point on the current stream ----------------
@@ -94,52 +96,74 @@ class BatchedFitter:
         dev = self.dev
         B = rotmats.shape[0]
         f32 = dict(dtype=torch.float32, device=dev)
-        st = {"rot": rotmats.to(**f32).reshape(B, 216).clone().contiguous(), "betas": betas.to(**f32).clone().contiguous(),
-              "cam": cam.to(**f32).clone().contiguous(), "label": keypoints2d.to(**f32).contiguous()}
+        # the state buffers (and the graph captured over them) are kept per problem shape and reused by later calls
+        key = (B, int(betas.shape[1]), vis is not None)
+        cached = self._cache.get(key)
+        if cached is None:
+            st = {"rot": torch.empty((B, 216), **f32), "betas": torch.empty((B, betas.shape[1]), **f32),
+                  "cam": torch.empty((B, 3), **f32), "label": torch.empty((B, self.jmap.numel(), 2), **f32)}
+            if vis is not None:
+                st["vis"] = torch.empty((B, self.jmap.numel()), dtype=torch.uint8, device=dev)
+            for name in ("rot", "betas", "cam"):
+                st["m_" + name] = torch.empty_like(st[name])
+                st["v_" + name] = torch.empty_like(st[name])
+                st["best_" + name] = torch.empty_like(st[name])
+            st["loss"] = torch.empty(B, **f32)
+            st["best_loss"] = torch.empty(B, **f32)
+            st["best_iter"] = torch.empty(B, dtype=torch.int32, device=dev)
+            st["improved"] = torch.empty(B, dtype=torch.uint8, device=dev)
+            st["step"] = torch.empty(2, dtype=torch.int32, device=dev)
+            st["gj"] = torch.empty((B, self.eng.num_joints_out, 3), **f32)
+            st["gcam"] = torch.empty((B, 3), **f32)
+            st["gbetas_prior"] = torch.empty((B, betas.shape[1]), **f32)
+            cached = {"st": st, "graph": None, "per": 0}
+            self._cache[key] = cached
+        st = cached["st"]
+        st["rot"].copy_(rotmats.to(**f32).reshape(B, 216))
+        st["betas"].copy_(betas.to(**f32))
+        st["cam"].copy_(cam.to(**f32))
+        st["label"].copy_(keypoints2d.to(**f32))
         if vis is not None:
-            st["vis"] = vis.to(device=dev, dtype=torch.uint8).contiguous()
+            st["vis"].copy_(vis.to(device=dev, dtype=torch.uint8))
         for name in ("rot", "betas", "cam"):
-            st["m_" + name] = torch.zeros_like(st[name])
-            st["v_" + name] = torch.zeros_like(st[name])
-            st["best_" + name] = st[name].clone()
-        st["loss"] = torch.zeros(B, **f32)
-        st["best_loss"] = torch.full((B,), float("inf"), **f32)
-        st["best_iter"] = torch.zeros(B, dtype=torch.int32, device=dev)
-        st["improved"] = torch.zeros(B, dtype=torch.uint8, device=dev)
-        st["step"] = torch.zeros(2, dtype=torch.int32, device=dev)
-        st["gj"] = torch.zeros((B, self.eng.num_joints_out, 3), **f32)
-        st["gcam"] = torch.zeros((B, 3), **f32)
-        st["gbetas_prior"] = torch.zeros((B, st["betas"].shape[1]), **f32)
+            st["m_" + name].zero_()
+            st["v_" + name].zero_()
+            st["best_" + name].copy_(st[name])
+        for name in ("loss", "best_iter", "improved", "step", "gj", "gcam", "gbetas_prior"):
+            st[name].zero_()
+        st["best_loss"].fill_(float("inf"))
         first_loss = None
         if iterations > 0:
-            if self.use_graph and iterations > 2:
-                side = torch.cuda.Stream(device=dev)
-                side.wait_stream(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(side):
-                    self._iteration(st)                       # eager warm-up: allocations, attribute set-up
-                    first_loss = st["loss"].clone()
-                torch.cuda.current_stream(dev).wait_stream(side)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    self._iteration(st)
-                for _ in range(iterations - 2):
-                    graph.replay()
-                # the capture itself does not execute: iterations = 1 eager + (iterations - 2) replays + 1 below
-                graph.replay()
-                self._graph = graph
-            else:
-                for i in range(iterations):
-                    self._iteration(st)
-                    if i == 0:
-                        first_loss = st["loss"].clone()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._iteration(st)                           # eager: allocations, attribute set-up, first loss
+                first_loss = st["loss"].clone()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            left = iterations - 1
+            per = self.graph_iterations if cached["graph"] is None else cached["per"]
+            if self.use_graph and left >= per:               # shorter fits stay eager: a capture costs more than it saves
+                # one graph = `per` consecutive iterations (consecutive replays of a one-iteration graph leave a
+                # launch gap between iterations); the capture itself does not execute
+                if cached["graph"] is None:
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        for _ in range(per):
+                            self._iteration(st)
+                    cached["graph"], cached["per"] = graph, per
+                for _ in range(left // per):
+                    cached["graph"].replay()
+                left = left % per
+            for _ in range(left):
+                self._iteration(st)
         best_rot = st["best_rot"].reshape(B, 24, 3, 3)
         out = {"body_pose": best_rot[:, 1:].contiguous(), "global_orient": best_rot[:, :1].contiguous(),
-               "betas": st["best_betas"], "cam": st["best_cam"],
+               "betas": st["best_betas"].clone(), "cam": st["best_cam"].clone(),
                "translation": convert_weak_perspective_to_camera_translation_torch(
                    st["best_cam"], config.FOCAL_LENGTH, self.proj_wh),
-               "best_loss": st["best_loss"], "best_iter": st["best_iter"], "initial_loss": first_loss,
-               "final_rotmats": st["rot"].reshape(B, 24, 3, 3), "final_betas": st["betas"], "final_cam": st["cam"],
-               "last_loss": st["loss"]}
+               "best_loss": st["best_loss"].clone(), "best_iter": st["best_iter"].clone(), "initial_loss": first_loss,
+               "final_rotmats": st["rot"].reshape(B, 24, 3, 3).clone(), "final_betas": st["betas"].clone(),
+               "final_cam": st["cam"].clone(), "last_loss": st["loss"].clone()}
         self._state = st
         return out
 

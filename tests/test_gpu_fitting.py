@@ -81,7 +81,7 @@ def test_fit_matches_reference_loop(setup, graph):
     betas_t, rot_t, cam_t, betas0, rot0, cam0 = _problem(B)
     label = _labels(model, rot_t, betas_t, cam_t)
     ref = _ref_fit(model, rot0, betas0, cam0, label, iters, lr, sw)
-    fitter = BatchedFitter(smpl, lr=lr, shape_weight=sw, use_cuda_graph=graph)
+    fitter = BatchedFitter(smpl, lr=lr, shape_weight=sw, use_cuda_graph=graph, graph_iterations=4)
     res = fitter.fit(rot0.to(dev), betas0.to(dev), cam0.to(dev), label.to(dev), iterations=iters)
     torch.cuda.synchronize()
     # loss of the first and of the last iteration, per player
