@@ -235,6 +235,25 @@ B200SMPL_API int b200smpl_fit_adam_step(float* params, const float* grad, const 
                            int32_t* step, int commit_step, int batch, int cols, float lr, float beta1, float beta2,
                            float eps, void* stream);
 
+/* fit_update: fit_mark_best and the fit_adam_step of up to B200SMPL_FIT_MAX_GROUPS parameter tensors in one launch
+ * (the per-iteration tail of the fitting loop, player_recon.py:1254-1266 + 1281).  The step counter is double-buffered:
+ * the call reads step[parity] and writes step[1 - parity]; the caller alternates the parity from a zeroed counter.
+ * first_loss (may be NULL) receives the loss of iteration 1. */
+#define B200SMPL_FIT_MAX_GROUPS 4
+typedef struct b200smpl_fit_group {
+  float* params;              /* [batch][cols] */
+  const float* grad;          /* [batch][cols] */
+  const float* grad_extra;    /* [batch][cols] added to grad, or NULL */
+  float* exp_avg;             /* Adam first moment */
+  float* exp_avg_sq;          /* Adam second moment */
+  float* best_params;         /* rows of improved bodies are copied here before the update */
+  const uint8_t* frozen_cols; /* [cols] 1 = never updated, or NULL */
+  int32_t cols;
+} b200smpl_fit_group;
+B200SMPL_API int b200smpl_fit_update(const b200smpl_fit_group* groups, int ngroups, const float* loss_per_body,
+                                     float* best_loss, int32_t* best_iter, float* first_loss, int32_t* step, int parity,
+                                     int batch, float lr, float beta1, float beta2, float eps, void* stream);
+
 B200SMPL_API const char* b200smpl_last_error(void);
 B200SMPL_API int b200smpl_abi_version(void);
 

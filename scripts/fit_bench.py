@@ -31,7 +31,7 @@ cam0 = torch.tensor([0.9, 0.0, 0.0], device=dev).repeat(B, 1)
 res = {}
 for use_graph in (True, False):
     fitter = BatchedFitter(smpl, lr=1e-2, shape_weight=1e-3, use_cuda_graph=use_graph)
-    fitter.fit(rot0, betas0, cam0, label, iterations=41)      # warm-up (captures the 20-iteration graph)
+    fitter.fit(rot0, betas0, cam0, label, iterations=41)      # warm-up (captures the 20-iteration graph, kept per shape)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     r = fitter.fit(rot0, betas0, cam0, label, iterations=iters)

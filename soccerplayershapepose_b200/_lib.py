@@ -59,6 +59,13 @@ class BackwardArgs(Structure):
     ]
 
 
+class FitGroup(Structure):
+    _fields_ = [
+        ("params", c_void_p), ("grad", c_void_p), ("grad_extra", c_void_p), ("exp_avg", c_void_p),
+        ("exp_avg_sq", c_void_p), ("best_params", c_void_p), ("frozen_cols", c_void_p), ("cols", c_int32),
+    ]
+
+
 # every symbol include/b200smpl.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "b200smpl_model_create": (c_int, [POINTER(ModelDesc), c_int, POINTER(c_void_p)]),
@@ -88,6 +95,8 @@ SYMBOLS = {
     "b200smpl_fit_mark_best": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "b200smpl_fit_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_void_p]),
+    "b200smpl_fit_update": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                                    c_float, c_float, c_float, c_void_p]),
     "b200smpl_last_error": (c_char_p, []),
     "b200smpl_abi_version": (c_int, []),
     "b200smpl_launch_count": (c_int64, []),

@@ -6,6 +6,8 @@
 // fused masked Adam step (torch.optim.Adam arithmetic, player_recon.py:1199).  Everything reads its
 // step counter and flags from device memory so that one iteration can be captured in a CUDA graph
 // and replayed.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace b200smpl {
@@ -115,6 +117,60 @@ __global__ void fit_adam_kernel(float* __restrict__ p, const float* __restrict__
   if (commit_step && blockIdx.x == 0 && threadIdx.x == 0) step[0] = t;
 }
 
+// mark_best + the Adam step of every parameter tensor in ONE launch.  A CTA owns FIT_BPC whole bodies: it decides
+// "improved" for them from the old best loss (shared memory), then updates their rows of every tensor.  The step
+// counter is double-buffered (read step[parity], write step[1 - parity]) so that no CTA can read a counter another
+// CTA has already advanced.
+constexpr int FIT_BPC = 8;
+struct FitGroups {
+  b200smpl_fit_group g[B200SMPL_FIT_MAX_GROUPS];
+  int n;
+};
+__global__ void __launch_bounds__(256)
+fit_update_kernel(FitGroups G, const float* __restrict__ loss, float* __restrict__ best_loss,
+                  int32_t* __restrict__ best_iter, float* __restrict__ first_loss, int32_t* __restrict__ step, int parity,
+                  int batch, float lr, float beta1, float beta2, float eps) {
+  __shared__ uint8_t imp[FIT_BPC];
+  const int t = step[parity] + 1;
+  const int b0 = blockIdx.x * FIT_BPC;
+  if (threadIdx.x < FIT_BPC) {
+    const int b = b0 + threadIdx.x;
+    bool im = false;
+    if (b < batch) {
+      const float l = loss[b];
+      im = l < best_loss[b];
+      if (im) { best_loss[b] = l; best_iter[b] = t; }
+      if (t == 1 && first_loss != nullptr) first_loss[b] = l;
+    }
+    imp[threadIdx.x] = im ? 1 : 0;
+  }
+  __syncthreads();
+  const float bc1 = 1.f - powf(beta1, (float)t), bc2 = 1.f - powf(beta2, (float)t);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+#pragma unroll
+  for (int k = 0; k < B200SMPL_FIT_MAX_GROUPS; ++k) {          // unrolled: the groups stay in the parameter bank
+    if (k >= G.n) break;
+    const b200smpl_fit_group& q = G.g[k];
+    const int P = q.cols;
+    for (int idx = threadIdx.x; idx < FIT_BPC * P; idx += blockDim.x) {
+      const int bl = idx / P, c = idx - bl * P, b = b0 + bl;
+      if (b >= batch) break;
+      const long long i = (long long)b * P + c;
+      const float x = q.params[i];
+      if (imp[bl]) q.best_params[i] = x;
+      if (q.frozen_cols != nullptr && q.frozen_cols[c]) continue;
+      float gr = q.grad[i];
+      if (q.grad_extra != nullptr) gr += q.grad_extra[i];
+      const float mi = beta1 * q.exp_avg[i] + (1.f - beta1) * gr;
+      const float vi = beta2 * q.exp_avg_sq[i] + (1.f - beta2) * gr * gr;
+      q.exp_avg[i] = mi;
+      q.exp_avg_sq[i] = vi;
+      q.params[i] = x - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) step[1 - parity] = t;
+}
+
 }  // namespace b200smpl
 
 using namespace b200smpl;
@@ -158,6 +214,27 @@ int b200smpl_fit_adam_step(float* params, const float* grad, const float* grad_e
                                                           improved, frozen_cols, step, commit_step, batch, cols, lr, beta1,
                                                           beta2, eps);
   B200_LAUNCH_CHECK("fit_adam");
+  return 0;
+}
+
+int b200smpl_fit_update(const b200smpl_fit_group* groups, int ngroups, const float* loss_per_body, float* best_loss,
+                        int32_t* best_iter, float* first_loss, int32_t* step, int parity, int batch, float lr, float beta1,
+                        float beta2, float eps, void* stream) {
+  if (!groups || ngroups < 1 || ngroups > B200SMPL_FIT_MAX_GROUPS || !loss_per_body || !best_loss || !best_iter || !step ||
+      batch < 1 || (parity != 0 && parity != 1))
+    return fail(B200SMPL_ERR_INVALID, "bad argument");
+  FitGroups G;
+  memset(&G, 0, sizeof(G));
+  G.n = ngroups;
+  for (int k = 0; k < ngroups; ++k) {
+    const b200smpl_fit_group& q = groups[k];
+    if (!q.params || !q.grad || !q.exp_avg || !q.exp_avg_sq || !q.best_params || q.cols < 1)
+      return fail(B200SMPL_ERR_INVALID, "bad parameter group");
+    G.g[k] = q;
+  }
+  fit_update_kernel<<<(batch + FIT_BPC - 1) / FIT_BPC, 256, 0, (cudaStream_t)stream>>>(G, loss_per_body, best_loss, best_iter, first_loss,
+                                                                                      step, parity, batch, lr, beta1, beta2, eps);
+  B200_LAUNCH_CHECK("fit_update");
   return 0;
 }
 

@@ -116,7 +116,8 @@ class SMPLEngine:
     # ---- forward / backward through the C-ABI -----------------------------------------------
     def forward(self, betas: torch.Tensor, pose: torch.Tensor, transl: Optional[torch.Tensor] = None,
                 cam: Optional[torch.Tensor] = None, *, axis_angle: bool = False, mode: int = _lib.MODE_FP32,
-                want_vertices: bool = True, slab: int = 0, save: bool = False):
+                want_vertices: bool = True, slab: int = 0, save: bool = False,
+                saved_buffer: Optional[torch.Tensor] = None):
         """betas (B,nb); pose (B,24,3,3) or (B,72); transl (B,3)|None; cam (B,3)|None.
         Returns vertices (B,V,3)|None, joints (B,NJ,3), joints2d (B,NJ,2)|None (and, with save=True,
         the opaque saved-for-backward buffer as a 4th element)."""
@@ -135,8 +136,11 @@ class SMPLEngine:
             ws = self._workspace("fwd", B, mode, slab)
             saved = None
             if save:
-                saved = torch.empty(int(self.lib.b200smpl_saved_bytes(self.handle, B, slab)), dtype=torch.uint8,
-                                    device=dev)
+                nsaved = int(self.lib.b200smpl_saved_bytes(self.handle, B, slab))
+                if saved_buffer is not None and saved_buffer.numel() >= nsaved and saved_buffer.dtype == torch.uint8:
+                    saved = saved_buffer                      # caller-owned (e.g. the fitting loop reuses one)
+                else:
+                    saved = torch.empty(nsaved, dtype=torch.uint8, device=dev)
             args = ForwardArgs(batch=B, mode=mode, pose_is_axis_angle=int(axis_angle), slab_bodies=slab,
                                betas=_ptr(betas), pose=_ptr(pose), transl=_ptr(transl), cam=_ptr(cam),
                                vertices=_ptr(verts), joints=_ptr(joints), joints2d=_ptr(j2d),

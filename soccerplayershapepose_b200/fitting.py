@@ -18,8 +18,8 @@ Restates the optimisation loop of the reference's `single_view_optimization`
   * results under the reference's `.npz` keys (player_recon.py:1293-1294): body_pose, global_orient, betas,
     translation (`convert_weak_perspective_to_camera_translation`, cam_utils.py:44-52).
 
-Only the joints are computed (virtual rows of the blend GEMM, no vertex is skinned).  One iteration = 9 kernel
-launches through the C-ABI; after one eager iteration, twenty consecutive iterations are captured in one CUDA
+Only the joints are computed (virtual rows of the blend GEMM, no vertex is skinned).  One iteration = 7 kernel
+launches through the C-ABI (the backward reuses the forward's transforms and blend rows); after one eager iteration, twenty consecutive iterations are captured in one CUDA
 graph (kept, with its state buffers, for later calls of the same shape) and replayed.
 CUDA float32 only: there is no CPU path.
 """
@@ -53,7 +53,7 @@ class BatchedFitter:
         self.proj_wh, self.norm_wh = float(proj_wh), float(norm_wh)
         self.b1, self.b2, self.eps = float(betas[0]), float(betas[1]), float(eps)
         self.use_graph = use_cuda_graph
-        self.graph_iterations = int(graph_iterations)
+        self.graph_iterations = max(2, int(graph_iterations) // 2 * 2)   # even: the step counter's parity repeats per replay
         self.jmap = torch.tensor(config.SMPL_TO_KPRCNN_MAP, dtype=torch.int32, device=dev)
         frozen = torch.zeros(24, 9, dtype=torch.uint8)
         for j in frozen_joints:
@@ -61,13 +61,16 @@ class BatchedFitter:
         self.frozen_rot = frozen.reshape(-1).to(dev)
         self._cache = {}
         self._state = None
+        self._parity = 0
 
     # ---- one iteration: every call below is one C-ABI entry point on the current stream ----------------
     def _iteration(self, st: Dict[str, torch.Tensor]) -> None:
         lib, B = self.lib, st["rot"].shape[0]
         stream = ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
-        _, joints, _ = self.eng.forward(st["betas"], st["rot"], None, None, axis_angle=False, mode=self.mode,
-                                        want_vertices=False)
+        # the transforms and the virtual rows of the blend output are kept for the backward (no recomputation)
+        _, joints, _, saved = self.eng.forward(st["betas"], st["rot"], None, None, axis_angle=False, mode=self.mode,
+                                               want_vertices=False, save=True, saved_buffer=st.get("saved"))
+        st["saved"] = saved
         vis = st.get("vis")
         _lib.check(lib.b200smpl_fit_loss(
             joints.data_ptr(), st["cam"].data_ptr(), self.jmap.data_ptr(), st["label"].data_ptr(),
@@ -75,19 +78,21 @@ class BatchedFitter:
             st["betas"].shape[1], self.proj_wh, self.norm_wh, self.log_var, self.shape_weight, st["loss"].data_ptr(),
             st["gj"].data_ptr(), st["gcam"].data_ptr(), st["gbetas_prior"].data_ptr(), stream), "fit_loss")
         gb, gp, _, _ = self.eng.backward(st["betas"], st["rot"], None, None, None, None, st["gj"], None,
-                                         axis_angle=False, mode=self.mode, need_transl=False, need_cam=False)
-        _lib.check(lib.b200smpl_fit_mark_best(st["loss"].data_ptr(), st["best_loss"].data_ptr(),
-                                              st["best_iter"].data_ptr(), st["improved"].data_ptr(),
-                                              st["step"].data_ptr(), B, stream), "fit_mark_best")
-        for name, grad, extra, frozen, commit in (("rot", gp, None, self.frozen_rot, 0),
-                                                  ("betas", gb, st["gbetas_prior"], None, 0),
-                                                  ("cam", st["gcam"], None, None, 1)):
+                                         axis_angle=False, mode=self.mode, need_transl=False, need_cam=False, saved=saved)
+        # best-iterate bookkeeping + the Adam step of the three parameter tensors: one launch
+        groups = (_lib.FitGroup * 3)()
+        for k, (name, grad, extra, frozen) in enumerate((("rot", gp, None, self.frozen_rot),
+                                                         ("betas", gb, st["gbetas_prior"], None),
+                                                         ("cam", st["gcam"], None, None))):
             p = st[name]
-            _lib.check(lib.b200smpl_fit_adam_step(
-                p.data_ptr(), grad.data_ptr(), None if extra is None else extra.data_ptr(), st["m_" + name].data_ptr(),
-                st["v_" + name].data_ptr(), st["best_" + name].data_ptr(), st["improved"].data_ptr(),
-                None if frozen is None else frozen.data_ptr(), st["step"].data_ptr(), commit, B,
-                p.numel() // B, self.lr, self.b1, self.b2, self.eps, stream), "fit_adam_step")
+            groups[k] = _lib.FitGroup(p.data_ptr(), grad.data_ptr(), None if extra is None else extra.data_ptr(),
+                                      st["m_" + name].data_ptr(), st["v_" + name].data_ptr(), st["best_" + name].data_ptr(),
+                                      None if frozen is None else frozen.data_ptr(), p.numel() // B)
+        _lib.check(lib.b200smpl_fit_update(ctypes.cast(groups, ctypes.c_void_p), 3, st["loss"].data_ptr(),
+                                           st["best_loss"].data_ptr(), st["best_iter"].data_ptr(), st["first_loss"].data_ptr(),
+                                           st["step"].data_ptr(), self._parity, B, self.lr, self.b1, self.b2, self.eps, stream),
+                   "fit_update")
+        self._parity ^= 1
 
     def fit(self, rotmats: torch.Tensor, betas: torch.Tensor, cam: torch.Tensor, keypoints2d: torch.Tensor,
             vis: Optional[torch.Tensor] = None, iterations: int = 200) -> Dict[str, torch.Tensor]:
@@ -109,6 +114,7 @@ class BatchedFitter:
                 st["v_" + name] = torch.empty_like(st[name])
                 st["best_" + name] = torch.empty_like(st[name])
             st["loss"] = torch.empty(B, **f32)
+            st["first_loss"] = torch.empty(B, **f32)
             st["best_loss"] = torch.empty(B, **f32)
             st["best_iter"] = torch.empty(B, dtype=torch.int32, device=dev)
             st["improved"] = torch.empty(B, dtype=torch.uint8, device=dev)
@@ -129,33 +135,42 @@ class BatchedFitter:
             st["m_" + name].zero_()
             st["v_" + name].zero_()
             st["best_" + name].copy_(st[name])
-        for name in ("loss", "best_iter", "improved", "step", "gj", "gcam", "gbetas_prior"):
+        for name in ("loss", "first_loss", "best_iter", "improved", "step", "gj", "gcam", "gbetas_prior"):
             st[name].zero_()
         st["best_loss"].fill_(float("inf"))
-        first_loss = None
-        if iterations > 0:
+        self._parity = 0                                      # the double-buffered step counter starts at step[0]
+        left = iterations
+        if self.use_graph and cached["graph"] is not None:
+            # later calls of a known shape: replays only (the graph was captured after one eager iteration, i.e. its
+            # first iteration reads step[1]; from a zeroed counter either slot is a valid start)
+            per = cached["per"]
+            for _ in range(left // per):
+                cached["graph"].replay()
+            if left // per:
+                self._parity = 1
+            left = left % per
+        elif left > 0:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
-                self._iteration(st)                           # eager: allocations, attribute set-up, first loss
-                first_loss = st["loss"].clone()
+                self._iteration(st)                           # eager: allocations, attribute set-up
             torch.cuda.current_stream(dev).wait_stream(side)
-            left = iterations - 1
-            per = self.graph_iterations if cached["graph"] is None else cached["per"]
-            if self.use_graph and left >= per:               # shorter fits stay eager: a capture costs more than it saves
+            left -= 1
+            per = self.graph_iterations
+            if self.use_graph and left >= per:                # shorter fits stay eager: a capture costs more than it saves
                 # one graph = `per` consecutive iterations (consecutive replays of a one-iteration graph leave a
                 # launch gap between iterations); the capture itself does not execute
-                if cached["graph"] is None:
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        for _ in range(per):
-                            self._iteration(st)
-                    cached["graph"], cached["per"] = graph, per
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    for _ in range(per):
+                        self._iteration(st)
+                cached["graph"], cached["per"] = graph, per
                 for _ in range(left // per):
-                    cached["graph"].replay()
+                    graph.replay()
                 left = left % per
-            for _ in range(left):
-                self._iteration(st)
+        for _ in range(left):
+            self._iteration(st)
+        first_loss = st["first_loss"].clone() if iterations > 0 else None
         best_rot = st["best_rot"].reshape(B, 24, 3, 3)
         out = {"body_pose": best_rot[:, 1:].contiguous(), "global_orient": best_rot[:, :1].contiguous(),
                "betas": st["best_betas"].clone(), "cam": st["best_cam"].clone(),

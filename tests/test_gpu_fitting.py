@@ -99,6 +99,13 @@ def test_fit_matches_reference_loop(setup, graph):
     assert torch.equal(res["final_rotmats"][:, list(FROZEN_FULL_JOINTS)].cpu(), rot0[:, list(FROZEN_FULL_JOINTS)])
     # the loss goes down
     assert (res["best_loss"] < res["initial_loss"]).all()
+    # a second call of the same shape reuses the state buffers (and the cached graph: replays only)
+    res2 = fitter.fit(rot0.to(dev), betas0.to(dev), cam0.to(dev), label.to(dev), iterations=iters)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(res2["initial_loss"].cpu().numpy(), res["initial_loss"].cpu().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(res2["best_loss"].cpu().numpy(), res["best_loss"].cpu().numpy(), rtol=1e-3)
+    assert torch.equal(res2["best_iter"], res["best_iter"])
+    assert (res2["final_betas"] - res["final_betas"]).abs().max().item() < 1e-3
 
 
 def test_fit_result_keys_and_translation(setup):
