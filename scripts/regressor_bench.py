@@ -39,7 +39,7 @@ class Step(torch.nn.Module):
 
 
 model = Step()
-if world > 1:
+if world > 1 and os.environ.get("B200_REGRESSOR_GRAPH", "1") == "0":
     model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
 opt = torch.optim.Adam(model.parameters(), lr=1e-4)
 x = make_smpl_inputs(B, rank)
@@ -61,8 +61,17 @@ def step():
     return loss
 
 
+graphed = os.environ.get("B200_REGRESSOR_GRAPH", "1") != "0"
+if graphed:
+    # one CUDA graph per step: head, SMPL layer, loss, backward, flat-bucket NCCL all-reduce, capturable Adam
+    r6, proj = regressor.gpu_ops()
+    gstep = regressor.GraphedTrainStep(head, crit, smpl, feats, labels, r6, proj, lr=1e-4, world_size=world)
+
+    def step():
+        return gstep(feats, labels)
+
 for _ in range(5):
-    l0 = step()
+    l0 = step().clone()
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
@@ -76,8 +85,16 @@ ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
 nparams = sum(p.numel() for p in model.parameters())
 if rank == 0:
     print(json.dumps({"workload": "regressor step: 512-d features -> IEF head (1024,1024) -> SMPL -> 5-term multi-task loss, "
-                                  "batch %d per GPU x %d GPU(s)" % (B, world), "ms_per_step": ms / steps,
+                                  "batch %d per GPU x %d GPU(s)%s" % (B, world, ", one CUDA graph per step" if graphed else ", eager"),
+                      "ms_per_step": ms / steps,
                       "crops_per_s": B * world * steps / (ms / 1e3), "allreduced_params": nparams if world > 1 else 0,
                       "loss_first": float(l0), "loss_last": float(l1)}))
 if world > 1:
+    torch.cuda.synchronize()
+    dist.barrier()
+    if graphed:
+        # a process group whose collectives are referenced by a live CUDA graph can block in its destructor:
+        # everything is flushed and synchronised, leave without running it
+        sys.stdout.flush()
+        os._exit(0)
     dist.destroy_process_group()

@@ -152,3 +152,29 @@ def test_gpu_step_matches_oracle(synthetic_model):
         g = getattr(head, name).weight.grad.cpu().double()
         g64 = getattr(head64, name).weight.grad
         assert (g - g64).abs().max().item() < 2e-4 * g64.abs().max().item()
+
+
+@pytest.mark.gpu
+def test_graphed_step_matches_eager_steps(synthetic_model):
+    """The CUDA-graph-captured training step (flat gradient bucket, capturable Adam) follows the eager
+    `train_step` with torch.optim.Adam: same losses and parameters after several steps."""
+    from soccerplayershapepose_b200.smpl import SMPL
+    dev = torch.device("cuda", 0)
+    feats, labels = _batch(synthetic_model, 6, 9)
+    feats, labels = feats.to(dev), {k: v.to(dev) for k, v in labels.items()}
+    smpl = SMPL(model_data=synthetic_model, mode="fp32").to(dev)
+    g6, gproj = regressor.gpu_ops()
+    head_a, crit_a = _make()
+    head_a, crit_a = head_a.to(dev), crit_a.to(dev)
+    head_b, crit_b = _make()
+    head_b, crit_b = head_b.to(dev), crit_b.to(dev)
+    head_b.load_state_dict(head_a.state_dict())
+    crit_b.load_state_dict(crit_a.state_dict())
+    lr, warm, n = 1e-3, 2, 3
+    opt = torch.optim.Adam(list(head_a.parameters()) + list(crit_a.parameters()), lr=lr)
+    eager = [regressor.train_step(head_a, crit_a, opt, smpl, feats, labels, g6, gproj).item() for _ in range(warm + n)]
+    gs = regressor.GraphedTrainStep(head_b, crit_b, smpl, feats, labels, g6, gproj, lr=lr, warmup=warm)
+    graphed = [gs(feats, labels).item() for _ in range(n)]
+    np.testing.assert_allclose(graphed, eager[warm:], rtol=2e-4)
+    for pa, pb in zip(head_a.parameters(), head_b.parameters()):
+        assert (pa - pb).abs().max().item() < 5e-3 * lr + 1e-6 + 2e-3 * pa.abs().max().item() * 0 + 2e-5
