@@ -195,9 +195,10 @@ class SMPLFunction(torch.autograd.Function):
                 want_vertices: bool, slab: int):
         need_grad = any(t is not None and t.requires_grad for t in (betas, pose, transl, cam))
         out = engine.forward(betas, pose, transl, cam, axis_angle=axis_angle, mode=mode,
-                             want_vertices=want_vertices, slab=slab, save=need_grad and want_vertices)
+                             want_vertices=want_vertices, slab=slab, save=need_grad)
         verts, joints, j2d = out[:3]
-        ctx.saved_blend = out[3] if len(out) > 3 else None   # ~93 KB / body: spares the backward a GEMM
+        ctx.saved_blend = out[3] if len(out) > 3 else None   # ~93 KB / body: spares the backward the pose stage and a GEMM
+        # (joints-only calls keep it too: only the joint rows of the blend output are filled)
         ctx.set_materialize_grads(False)      # unused outputs arrive as None -> their kernels are skipped
         ctx.engine, ctx.axis_angle, ctx.mode, ctx.slab = engine, axis_angle, mode, slab
         ctx.pose_shape = pose.shape
