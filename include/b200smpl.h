@@ -254,6 +254,11 @@ B200SMPL_API int b200smpl_fit_update(const b200smpl_fit_group* groups, int ngrou
                                      float* best_loss, int32_t* best_iter, float* first_loss, int32_t* step, int parity,
                                      int batch, float lr, float beta1, float beta2, float eps, void* stream);
 
+/* Test hook (host arithmetic only, no device): the cluster work list of the forward blend GEMM for `body_tiles`
+ * 128-body tiles x `row_tiles` 128-row tiles on a device with `num_sms` SMs.  Writes (body-tile pair, first row-tile
+ * pair, end row-tile pair) per cluster into out[3 * capacity]; returns the number of clusters or -1. */
+B200SMPL_API int b200smpl_debug_fwd_gemm_worklist(int body_tiles, int row_tiles, int num_sms, uint16_t* out, int capacity);
+
 B200SMPL_API const char* b200smpl_last_error(void);
 B200SMPL_API int b200smpl_abi_version(void);
 

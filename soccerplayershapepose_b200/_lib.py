@@ -97,6 +97,7 @@ SYMBOLS = {
                                        c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_void_p]),
     "b200smpl_fit_update": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                     c_float, c_float, c_float, c_void_p]),
+    "b200smpl_debug_fwd_gemm_worklist": (c_int, [c_int, c_int, c_int, c_void_p, c_int]),
     "b200smpl_last_error": (c_char_p, []),
     "b200smpl_abi_version": (c_int, []),
     "b200smpl_launch_count": (c_int64, []),

@@ -1164,6 +1164,49 @@ static int launch_blend_fwd_umma_2cta(const DevModel& m, int mode, const __nv_bf
   return 0;
 }
 
+// Work list of the body-stationary forward GEMM (host side; pure arithmetic, also exposed to the CPU tests through
+// b200smpl_debug_fwd_gemm_worklist).  CTA pairs are scheduled per TPC (2 SMs).  The (body pair, row-tile pair) list,
+// body pair major, is cut into one equal range per TPC; a range that crosses into the next body pair becomes two
+// clusters (the resident operand changes), longest pieces first so that the short ones fill the tail of the wave.
+// Returns the number of clusters, or -1 when the list does not fit.
+static int build_bs_work(int bp_total, int wtp_total, int tpcs, BsWork& work) {
+  if (bp_total < 1 || wtp_total < 1) return -1;
+  const long long total = (long long)bp_total * wtp_total;
+  const int nranges = (int)std::min<long long>(total, std::max(tpcs, bp_total));
+  struct Piece { int bp, w0, w1; };
+  std::vector<Piece> pieces;
+  for (int r = 0; r < nranges; ++r) {
+    long long lo = total * r / nranges, hi = total * (r + 1) / nranges;
+    while (lo < hi) {
+      const int bp = (int)(lo / wtp_total);
+      const long long end = std::min<long long>(hi, (long long)(bp + 1) * wtp_total);
+      pieces.push_back({bp, (int)(lo - (long long)bp * wtp_total), (int)(end - (long long)bp * wtp_total)});
+      lo = end;
+    }
+  }
+  // the plain rectangular split (every body pair cut into the same number of row chunks, one wave) is kept when
+  // its longest cluster is no longer than the flattened one plus a prologue, and for very wide slabs
+  const int rect_chunks = std::max(1, std::min(wtp_total, tpcs / std::max(1, bp_total)));
+  const int rect_len = (wtp_total + rect_chunks - 1) / rect_chunks;
+  const int flat_len = (int)((total + nranges - 1) / nranges);
+  if ((int)pieces.size() > BS_MAX_WORK || rect_len <= flat_len + 1) {
+    pieces.clear();
+    const int chunks = std::max(1, std::min(rect_chunks, BS_MAX_WORK / bp_total));
+    const int wpc = (wtp_total + chunks - 1) / chunks;
+    for (int bp = 0; bp < bp_total; ++bp)
+      for (int w = 0; w < wtp_total; w += wpc) pieces.push_back({bp, w, std::min(wtp_total, w + wpc)});
+    if ((int)pieces.size() > BS_MAX_WORK) return -1;
+  }
+  std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& a, const Piece& b) { return a.w1 - a.w0 > b.w1 - b.w0; });
+  memset(&work, 0, sizeof(work));
+  int npieces = 0;
+  for (const Piece& pc : pieces) {
+    work.bp[npieces] = (uint16_t)pc.bp; work.w0[npieces] = (uint16_t)pc.w0; work.w1[npieces] = (uint16_t)pc.w1;
+    ++npieces;
+  }
+  return npieces;
+}
+
 // body-stationary CTA-pair launch: one wave of (body-tile pair) x (row chunk) clusters
 static int launch_blend_fwd_umma_bs2(const DevModel& m, int mode, const __nv_bfloat16* feat, int S, int Sw, float* vpT,
                                      int row_begin, int row_end, int num_sms, cudaStream_t st) {
@@ -1181,46 +1224,9 @@ static int launch_blend_fwd_umma_bs2(const DevModel& m, int mode, const __nv_bfl
   const int wtp_total = (mtiles + 1) / 2;
   const int ntiles_n = Sw / WS_BN;
   const int bp_total = (ntiles_n + 1) / 2;
-  // CTA pairs are scheduled per TPC (2 SMs).  The (body pair, row-tile pair) list, body pair major, is cut into
-  // one equal range per TPC; a range that crosses into the next body pair becomes two clusters (the resident
-  // operand changes), longest pieces first so that the short ones fill the tail of the wave.
-  const int tpcs = std::max(1, num_sms / 2);
   BsWork work;
-  int npieces = 0;
-  {
-    const long long total = (long long)bp_total * wtp_total;
-    const int nranges = (int)std::min<long long>(total, std::max(tpcs, bp_total));
-    struct Piece { int bp, w0, w1; };
-    std::vector<Piece> pieces;
-    for (int r = 0; r < nranges; ++r) {
-      long long lo = total * r / nranges, hi = total * (r + 1) / nranges;
-      while (lo < hi) {
-        const int bp = (int)(lo / wtp_total);
-        const long long end = std::min<long long>(hi, (long long)(bp + 1) * wtp_total);
-        pieces.push_back({bp, (int)(lo - (long long)bp * wtp_total), (int)(end - (long long)bp * wtp_total)});
-        lo = end;
-      }
-    }
-    // the plain rectangular split (every body pair cut into the same number of row chunks, one wave) is kept when
-    // its longest cluster is no longer than the flattened one plus a prologue, and for very wide slabs
-    const int rect_chunks = std::max(1, std::min(wtp_total, tpcs / std::max(1, bp_total)));
-    const int rect_len = (wtp_total + rect_chunks - 1) / rect_chunks;
-    const int flat_len = (int)((total + nranges - 1) / nranges);
-    if ((int)pieces.size() > BS_MAX_WORK || rect_len <= flat_len + 1) {
-      pieces.clear();
-      const int chunks = std::max(1, std::min(rect_chunks, BS_MAX_WORK / bp_total));
-      const int wpc = (wtp_total + chunks - 1) / chunks;
-      for (int bp = 0; bp < bp_total; ++bp)
-        for (int w = 0; w < wtp_total; w += wpc) pieces.push_back({bp, w, std::min(wtp_total, w + wpc)});
-      if ((int)pieces.size() > BS_MAX_WORK) return fail(B200SMPL_ERR_INVALID, "slab too wide for the forward GEMM work list");
-    }
-    std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& a, const Piece& b) { return a.w1 - a.w0 > b.w1 - b.w0; });
-    memset(&work, 0, sizeof(work));
-    for (const Piece& pc : pieces) {
-      work.bp[npieces] = (uint16_t)pc.bp; work.w0[npieces] = (uint16_t)pc.w0; work.w1[npieces] = (uint16_t)pc.w1;
-      ++npieces;
-    }
-  }
+  const int npieces = build_bs_work(bp_total, wtp_total, std::max(1, num_sms / 2), work);
+  if (npieces < 0) return fail(B200SMPL_ERR_INVALID, "slab too wide for the forward GEMM work list");
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * npieces, 1, 1);
@@ -1302,6 +1308,17 @@ int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat
   B200_LAUNCH_CHECK("blend_fwd_umma");
   return 0;
 }
+
+}  // namespace b200smpl
+extern "C" int b200smpl_debug_fwd_gemm_worklist(int body_tiles, int row_tiles, int num_sms, uint16_t* out, int capacity) {
+  using namespace b200smpl;
+  BsWork work;
+  const int n = build_bs_work((body_tiles + 1) / 2, (row_tiles + 1) / 2, std::max(1, num_sms / 2), work);
+  if (n < 0 || out == nullptr || n > capacity) return n < 0 ? -1 : n;
+  for (int c = 0; c < n; ++c) { out[c * 3] = work.bp[c]; out[c * 3 + 1] = work.w0[c]; out[c * 3 + 2] = work.w1[c]; }
+  return n;
+}
+namespace b200smpl {
 
 // number of split-K partials the backward GEMM writes for slab width S
 // CTA-pair kernels are the default; B200_BWD_2CTA=0 selects the single-CTA kernel (kept for comparison)

@@ -206,3 +206,35 @@ def test_bf16_split_operand(host_engine):
     scale = np.abs(W32[1:]).max()
     assert np.abs(rec - W32[1:]).max() < scale * 2.0 ** -15
     assert not Wb_hi[nf:].any() and not Wb_lo[nf:].any()
+
+
+def test_forward_gemm_worklist_covers_every_tile_once():
+    """Host arithmetic of the forward blend GEMM's cluster work list (no device): for every slab width and row
+    range, every (body-tile pair, row-tile pair) is covered exactly once, no cluster is empty, the list fits one
+    wave of CTA pairs whenever the tile count allows, and the longest cluster is within one tile of the ideal."""
+    import ctypes
+    lib = _lib.load()
+    cap = 160
+    buf = (ctypes.c_uint16 * (3 * cap))()
+    for num_sms in (148, 132, 2):
+        tpcs = max(1, num_sms // 2)
+        for body_tiles in (1, 2, 3, 8, 15, 16, 29, 30, 31, 32, 64):
+            for row_tiles in (1, 2, 3, 17, 162, 177, 178):
+                n = lib.b200smpl_debug_fwd_gemm_worklist(body_tiles, row_tiles, num_sms, ctypes.cast(buf, ctypes.c_void_p), cap)
+                bp_total, wtp_total = (body_tiles + 1) // 2, (row_tiles + 1) // 2
+                assert 0 < n <= cap, (num_sms, body_tiles, row_tiles, n)
+                seen = np.zeros((bp_total, wtp_total), np.int32)
+                longest = 0
+                for c in range(n):
+                    bp, w0, w1 = buf[3 * c], buf[3 * c + 1], buf[3 * c + 2]
+                    assert bp < bp_total and w0 < w1 <= wtp_total
+                    seen[bp, w0:w1] += 1
+                    longest = max(longest, w1 - w0)
+                assert (seen == 1).all(), (num_sms, body_tiles, row_tiles)
+                total = bp_total * wtp_total
+                if bp_total <= tpcs:
+                    ideal = -(-total // min(total, tpcs))
+                    # rectangular or flattened, whichever was chosen: never worse than the rectangular split
+                    rect_chunks = max(1, min(wtp_total, tpcs // bp_total))
+                    assert longest <= -(-wtp_total // rect_chunks)
+                    assert longest >= min(ideal, wtp_total) - 0
