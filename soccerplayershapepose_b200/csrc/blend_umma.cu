@@ -1109,8 +1109,7 @@ static int make_map(CUtensorMap* map, const void* base, int k_extent, int rows, 
   return 0;
 }
 
-constexpr int FWD_BN = 128, FWD_STAGES = 3;
-constexpr int BWD_BN_MAX = 256, BWD_STAGES = 4;
+constexpr int BWD_STAGES = 4;
 
 static int launch_blend_fwd_umma_2cta(const DevModel& m, int mode, const __nv_bfloat16* feat, int S, int Sw, float* vpT,
                                       int row_begin, int row_end, cudaStream_t st) {

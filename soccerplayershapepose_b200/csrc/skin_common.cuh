@@ -108,12 +108,14 @@ __device__ __forceinline__ f2 mk2(float lo, float hi) {
   return r;
 }
 __device__ __forceinline__ float lo2(f2 v) {
-  float lo, hi;
+  float lo;
+  [[maybe_unused]] float hi;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
   return lo;
 }
 __device__ __forceinline__ float hi2(f2 v) {
-  float lo, hi;
+  [[maybe_unused]] float lo;
+  float hi;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
   return hi;
 }
