@@ -214,3 +214,11 @@ def test_oracle_gradcheck_small(synthetic_model):
             args_p[k], args_m[k] = xp, xm
             fd = (loss(*args_p) - loss(*args_m)) / (2 * eps)
             assert abs(fd.item() - gx[0, i].item()) <= 1e-5 * max(1.0, abs(fd.item())), (k, i)
+
+
+def test_vertices2joints_helper_matches_oracle():
+    from soccerplayershapepose_b200.lbs import vertices2joints
+    g = torch.Generator().manual_seed(0)
+    v = torch.randn(3, 50, 3, generator=g, dtype=torch.float64)
+    J = torch.rand(7, 50, generator=g, dtype=torch.float64)
+    assert torch.allclose(vertices2joints(J, v), O.vertices2joints(J, v), rtol=0, atol=1e-12)
