@@ -123,7 +123,9 @@ typedef struct b200smpl_forward_args {
   float* joints2d;             /* out [B][num_joints_out][2] = s*(x+tx), s*(y+ty); NULL if cam is NULL */
   void* workspace;
   size_t workspace_bytes;
-  void* saved;                 /* out, optional: b200smpl_saved_bytes(B, slab) bytes kept for backward */
+  void* saved;                 /* out, optional: b200smpl_saved_bytes(B, slab) bytes kept for backward; a joints-only
+                                  call (vertices == NULL) fills only the joint rows: pass grad_vertices = NULL to
+                                  the backward that receives it */
   size_t saved_bytes;
 } b200smpl_forward_args;
 

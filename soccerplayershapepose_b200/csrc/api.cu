@@ -283,8 +283,9 @@ int b200smpl_forward(const b200smpl_model* m, const b200smpl_forward_args* a, vo
   float* vpT = (float*)(ws + p.off_vpT);
   const int S = p.S, B = a->batch;
   const bool aa = a->pose_is_axis_angle != 0;
-  // with a saved buffer the whole blend output is kept, so every row is computed
-  const int row_begin = (a->vertices || a->saved) ? 0 : d.n_virt0;
+  // joints-only calls blend only the virtual (joint) rows, also when the products are kept for the backward:
+  // without a vertices output no grad_vertices can arrive, and b200smpl_backward rejects that combination
+  const int row_begin = a->vertices ? 0 : d.n_virt0;
   char* saved = nullptr;
   if (a->saved) {
     if (a->saved_bytes < b200smpl_saved_bytes(m, B, a->slab_bodies)) return fail(B200SMPL_ERR_WORKSPACE, "saved buffer too small");

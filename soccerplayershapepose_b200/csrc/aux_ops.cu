@@ -268,7 +268,7 @@ __global__ void j2d_loss_kernel(const float* __restrict__ joints, const float* _
       lsum += d * d;
       // d loss / d u
       const float gu = 2.f * d * inv_count * ew * (2.0f / norm_wh) * (proj_wh / 2.0f);
-      if (gjoints != nullptr) gjoints[((size_t)b * nj + J) * 3 + k] = s * gu;
+      if (gjoints != nullptr) atomicAdd(&gjoints[((size_t)b * nj + J) * 3 + k], s * gu);   // a map may repeat a joint
       gs += gu * (p[k] + t[k]);
       if (k == 0) gtx += s * gu; else gty += s * gu;
     }

@@ -150,6 +150,9 @@ class SMPLEngine:
             _lib.check(self.lib.b200smpl_forward(self.handle, ctypes.byref(args), ctypes.c_void_p(stream)),
                        "b200smpl_forward")
         if save:
+            # a joints-only forward blends (and keeps) only the virtual joint rows: such a buffer cannot serve a
+            # backward with vertex gradients
+            saved._b200_joints_only = not want_vertices
             return verts, joints, j2d, saved
         return verts, joints, j2d
 
@@ -167,6 +170,8 @@ class SMPLEngine:
         gj = self._check_in(grad_joints, (B, self.num_joints_out, 3), "grad_joints")
         g2 = self._check_in(grad_joints2d, (B, self.num_joints_out, 2), "grad_joints2d")
         joints = self._check_in(joints, (B, self.num_joints_out, 3), "joints") if g2 is not None else None
+        if gv is not None and saved is not None and getattr(saved, "_b200_joints_only", False):
+            raise RuntimeError("grad_vertices given with a saved buffer of a joints-only forward (it holds no vertex rows)")
         g_betas = torch.empty((B, self.num_betas), dtype=torch.float32, device=dev)
         g_pose = torch.empty((B, 72 if axis_angle else 216), dtype=torch.float32, device=dev)
         g_transl = torch.empty((B, 3), dtype=torch.float32, device=dev) if need_transl else None
@@ -198,7 +203,7 @@ class SMPLFunction(torch.autograd.Function):
                              want_vertices=want_vertices, slab=slab, save=need_grad)
         verts, joints, j2d = out[:3]
         ctx.saved_blend = out[3] if len(out) > 3 else None   # ~93 KB / body: spares the backward the pose stage and a GEMM
-        # (joints-only calls keep it too: only the joint rows of the blend output are filled)
+        # (joints-only calls keep it too; only the joint rows of the blend output are computed and filled)
         ctx.set_materialize_grads(False)      # unused outputs arrive as None -> their kernels are skipped
         ctx.engine, ctx.axis_angle, ctx.mode, ctx.slab = engine, axis_angle, mode, slab
         ctx.pose_shape = pose.shape

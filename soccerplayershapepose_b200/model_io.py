@@ -87,8 +87,13 @@ def _graph_parts(faces: np.ndarray, nv: int, nparts: int, rng: np.random.Generat
     return part, dists, adj
 
 
-def make_synthetic_smpl(seed: int = 1234, use_topology: bool = True) -> Dict[str, np.ndarray]:
+def make_synthetic_smpl(seed: int = 1234, use_topology: bool = True, statistics: str = "compact") -> Dict[str, np.ndarray]:
     """Seeded synthetic SMPL-shaped model.
+
+    `statistics="wide"` is the harder variant for the packed layouts (the number of virtual joint rows and the
+    skinning plan's slot reloads depend on the sparsity structure): regressor rows that draw from many mesh parts
+    (H36M 6-10 parts and ~200 non-zeros, COCO-plus 3-6 parts, extra 2-3, J_regressor own part + tree neighbours)
+    and skinning rows with 1, 2 or 3 influences next to the usual 4 (real SMPL weights have such rows).
 
     Magnitudes are body-like so that the 1e-5 m / 1e-4 m tolerances are meaningful:
     template extents ~[0.25, 0.45, 0.12] m, shapedirs sigma 0.03*0.7^l, posedirs sigma 0.002.
@@ -147,10 +152,22 @@ def make_synthetic_smpl(seed: int = 1234, use_topology: bool = True) -> Dict[str
             lbs_weights[v, j0] = w[0]
             lbs_weights[v, others] = w[1:]
 
+    wide = statistics == "wide"
+    if statistics not in ("compact", "wide"):
+        raise ValueError("statistics must be 'compact' or 'wide'")
+    if wide:
+        # rows with fewer than 4 influences: drop the smallest weights of ~half of the vertices and renormalise
+        keepn = rng.choice([1, 2, 3, 4], size=V, p=[0.15, 0.15, 0.2, 0.5])
+        order_w = np.argsort(-lbs_weights, axis=1)
+        for v in range(V):
+            lbs_weights[v, order_w[v, keepn[v]:]] = 0.0
+        lbs_weights /= lbs_weights.sum(1, keepdims=True)
+
     def sparse_rows(nrows, nnz, parts_per_row):
         R = np.zeros((nrows, V), np.float64)
         for r in range(nrows):
-            ps = rng.choice(J, parts_per_row, replace=False)
+            npart = parts_per_row if np.isscalar(parts_per_row) else int(rng.integers(parts_per_row[0], parts_per_row[1] + 1))
+            ps = rng.choice(J, npart, replace=False)
             pool = np.nonzero(np.isin(part, ps))[0]
             if len(pool) < nnz:
                 pool = np.arange(V)
@@ -161,7 +178,7 @@ def make_synthetic_smpl(seed: int = 1234, use_topology: bool = True) -> Dict[str
 
     J_regressor = np.zeros((J, V), np.float64)
     for j in range(J):
-        pool = np.nonzero(part == j)[0]
+        pool = np.nonzero(np.isin(part, [j] + nbrs[j]) if wide else part == j)[0]
         if len(pool) < 32:
             pool = np.arange(V)
         idx = rng.choice(pool, 32, replace=False)
@@ -177,9 +194,9 @@ def make_synthetic_smpl(seed: int = 1234, use_topology: bool = True) -> Dict[str
         parents=parents,
         faces=faces.astype(np.int64),
         extra_joints_idxs=SMPL_EXTRA_JOINT_VERTEX_IDS.copy(),
-        J_regressor_extra=sparse_rows(9, 32, 1).astype(np.float32),
-        J_regressor_cocoplus=sparse_rows(19, 32, 2).astype(np.float32),
-        J_regressor_h36m=sparse_rows(17, 200, 2).astype(np.float32),
+        J_regressor_extra=sparse_rows(9, 32, (2, 3) if wide else 1).astype(np.float32),
+        J_regressor_cocoplus=sparse_rows(19, 64 if wide else 32, (3, 6) if wide else 2).astype(np.float32),
+        J_regressor_h36m=sparse_rows(17, 200, (6, 10) if wide else 2).astype(np.float32),
     )
     return model
 

@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import Optional
 
 import torch
@@ -144,12 +145,45 @@ def perspective_project(points, rotation, translation, focal_length: float, img_
     return _Persp.apply(points, rotation, translation, focal_length, img_wh)
 
 
+_JOINT_MAP_OK = {}
+
+
+def _checked_joint_map(joint_map: torch.Tensor, device: torch.device, nj: int) -> torch.Tensor:
+    """The loss kernel reads the map as int32 and indexes joints / grad_joints with it unchecked: convert integer
+    maps to int32 and check the range once per (tensor, version) -- the range check is a host read, so it is cached
+    and skipped inside a CUDA-graph capture."""
+    if not isinstance(joint_map, torch.Tensor) or joint_map.device != device:
+        raise RuntimeError("joint_map must be a tensor on {}".format(device))
+    key = (joint_map.data_ptr(), joint_map.numel(), joint_map._version, str(joint_map.dtype), nj)
+    hit = _JOINT_MAP_OK.get(key)
+    if hit is not None and hit[0]() is joint_map:             # the very tensor that was checked, unmodified since
+        return hit[1]
+    if joint_map.dtype not in (torch.int32, torch.int64, torch.int16, torch.uint8, torch.int8):
+        raise TypeError("joint_map must be an integer tensor, got {}".format(joint_map.dtype))
+    m32 = joint_map.to(torch.int32).contiguous().view(-1)
+    if torch.cuda.is_current_stream_capturing():
+        return m32                                            # unchecked (and uncached) inside a capture
+    if m32.numel() and (int(m32.min()) < 0 or int(m32.max()) >= nj):
+        raise IndexError("joint_map entries must lie in [0, {})".format(nj))
+    if len(_JOINT_MAP_OK) > 64:
+        _JOINT_MAP_OK.clear()
+    _JOINT_MAP_OK[key] = (weakref.ref(joint_map), m32)
+    return m32
+
+
 class _J2dLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, joints, cam, joint_map, label, vis, proj_wh, norm_wh, log_var):
         joints, cam, label = _req(joints, "joints"), _req(cam, "cam"), _req(label, "label")
         B, NJ = joints.shape[0], joints.shape[1]
         nmap = joint_map.numel()
+        joint_map = _checked_joint_map(joint_map, joints.device, NJ)
+        if tuple(cam.shape) != (B, 3):
+            raise ValueError("cam has shape {}, expected {}".format(tuple(cam.shape), (B, 3)))
+        if tuple(label.shape) != (B, nmap, 2):
+            raise ValueError("label has shape {}, expected {}".format(tuple(label.shape), (B, nmap, 2)))
+        if vis is not None and tuple(vis.shape) != (B, nmap):
+            raise ValueError("vis has shape {}, expected {}".format(tuple(vis.shape), (B, nmap)))
         loss = torch.zeros(2, dtype=torch.float32, device=joints.device)
         gj = torch.empty_like(joints)
         gc = torch.empty_like(cam)
@@ -173,5 +207,6 @@ def joints2d_loss(joints: torch.Tensor, cam: torch.Tensor, joint_map: torch.Tens
                   log_var: float = 0.0) -> torch.Tensor:
     """Fused reprojection loss: orthographic_project_torch(joints, cam)[:, joint_map] ->
     undo_keypoint_normalisation(., proj_wh) -> joints2D term of the multi-task loss
-    (losses/multi_task_loss.py:97-113) with a fixed log-variance.  joint_map: int32 CUDA tensor."""
+    (losses/multi_task_loss.py:97-113) with a fixed log-variance.  joint_map: integer CUDA tensor with entries in
+    [0, NJ) (converted to int32; a repeated joint accumulates its gradient)."""
     return _J2dLoss.apply(joints, cam, joint_map, label_pixels, vis, proj_wh, norm_wh, log_var)

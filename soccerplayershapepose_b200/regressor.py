@@ -52,8 +52,11 @@ class IEFModule(nn.Module):
             torch.nn.init.zeros_(fc.bias)
         self.ief_layers = nn.Sequential(self.fc1, self.relu, self.fc2, self.relu, self.fc3)
         self.iterations = iterations
+        # a plain (non-persistent) buffer: the reference keeps it as an attribute (models/ief_module.py:30), so its
+        # checkpoints carry fc1/fc2/fc3 and ief_layers.* keys only and state_dicts interchange in both directions
         self.register_buffer("initial_params_estimate",
-                             default_mean_params() if mean_params is None else mean_params.float().clone())
+                             default_mean_params() if mean_params is None else mean_params.float().clone(),
+                             persistent=False)
 
     def forward(self, img_features: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         params = self.initial_params_estimate.repeat([img_features.size(0), 1])

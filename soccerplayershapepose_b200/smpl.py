@@ -11,7 +11,7 @@ CUDA device: there is no CPU implementation.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Union
+from typing import Dict, Optional, Tuple, Union
 
 import numpy as np
 import torch
@@ -38,6 +38,15 @@ class SMPLOutput(dict):
             raise AttributeError(k) from e
 
 
+class VertexJointSelector(nn.Module):
+    """Holder of smplx's picked-vertex joint ids under smplx's own name
+    (`vertex_joint_selector.extra_joints_idxs`); the picking itself happens in the kernels."""
+
+    def __init__(self, extra_joints_idxs):
+        super().__init__()
+        self.register_buffer("extra_joints_idxs", torch.tensor(np.asarray(extra_joints_idxs), dtype=torch.long))
+
+
 class SMPL(nn.Module):
     NUM_BODY_JOINTS = 23
 
@@ -58,7 +67,6 @@ class SMPL(nn.Module):
             model_data = load_smpl_model(model_path, gender=gender,
                                          extra_regressor_paths=kwargs.get("extra_regressor_paths"))
         validate_model(model_data)
-        self._model_data = model_data
         self.batch_size = batch_size
         self.mode = _lib.MODES[mode] if isinstance(mode, str) else int(mode)
         self.slab_bodies = int(slab_bodies)
@@ -72,8 +80,8 @@ class SMPL(nn.Module):
         self.register_buffer("J_regressor", f32("J_regressor"))
         self.register_buffer("lbs_weights", f32("lbs_weights"))
         self.register_buffer("parents", torch.tensor(np.asarray(model_data["parents"]), dtype=torch.long))
-        self.register_buffer("extra_joints_idxs", torch.tensor(np.asarray(model_data["extra_joints_idxs"]),
-                                                                dtype=torch.long))
+        # smplx keeps the picked-vertex ids in a submodule: state_dict key `vertex_joint_selector.extra_joints_idxs`
+        self.vertex_joint_selector = VertexJointSelector(model_data["extra_joints_idxs"])
         for k in ("J_regressor_extra", "J_regressor_cocoplus", "J_regressor_h36m"):
             self.register_buffer(k, f32(k))
         nb = self.shapedirs.shape[-1]
@@ -82,20 +90,48 @@ class SMPL(nn.Module):
         self.global_orient = nn.Parameter(torch.zeros(batch_size, 3))
         self.body_pose = nn.Parameter(torch.zeros(batch_size, self.NUM_BODY_JOINTS * 3))
         self.transl = nn.Parameter(torch.zeros(batch_size, 3))
-        self._engines: Dict[torch.device, SMPLEngine] = {}
+        # identity + version 0 = "still the untouched zero default" (kept outside nn.Module's parameter registry)
+        object.__setattr__(self, "_transl_default", self.transl)
+        self._engines: Dict[torch.device, Tuple[tuple, SMPLEngine]] = {}
 
-    # one packed handle per device the module has been moved to
+    # the tensors the packed device model is built from; any change to them (load_state_dict, in-place edit,
+    # re-assignment) must reach the kernels, so the engine is keyed on their identity and version
+    _MODEL_BUFFERS = ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights", "parents",
+                      "J_regressor_extra", "J_regressor_cocoplus", "J_regressor_h36m")
+
+    @property
+    def extra_joints_idxs(self) -> torch.Tensor:
+        return self.vertex_joint_selector.extra_joints_idxs
+
+    def _model_tensors(self) -> Dict[str, torch.Tensor]:
+        d = {k: getattr(self, k) for k in self._MODEL_BUFFERS}
+        d["extra_joints_idxs"] = self.vertex_joint_selector.extra_joints_idxs
+        return d
+
+    # one packed handle per device the module has been moved to, rebuilt when a model buffer changes
     def _engine(self, device: torch.device) -> SMPLEngine:
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("b200 SMPL runs on CUDA only (module is on {}); call .to('cuda')".format(device))
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        eng = self._engines.get(device)
-        if eng is None:
-            eng = SMPLEngine(self._model_data, device)
-            self._engines[device] = eng
+        tensors = self._model_tensors()
+        key = tuple((id(t), t._version) for t in tensors.values())
+        hit = self._engines.get(device)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        model = {k: t.detach().cpu().numpy() for k, t in tensors.items()}
+        validate_model(model)
+        eng = SMPLEngine(model, device)
+        self._engines[device] = (key, eng)
         return eng
+
+    def _transl_is_untouched_default(self) -> bool:
+        """True while self.transl is the zeros Parameter created in __init__ (never assigned, loaded, stepped or
+        edited in place): adding it is the identity, so the call may skip it.  `.to(device)` keeps identity and
+        version, so a moved module still qualifies."""
+        t = self.transl
+        return t is self._transl_default and t._version == 0
 
     @staticmethod
     def _expand(t: torch.Tensor, B: int) -> torch.Tensor:
@@ -128,10 +164,12 @@ class SMPL(nn.Module):
             bp = self._expand(body_pose.reshape(body_pose.shape[0], -1, 3, 3), B)
             full_pose = torch.cat([go, bp], dim=1)                           # (B, 24, 3, 3)
         betas_b = self._expand(betas, B)
-        # the default transl Parameter is zeros (smplx adds it; adding zeros is the identity, skip it
-        # unless it has been trained / set)
-        tr = None
-        if not apply_default_transl or bool(self.transl.requires_grad and torch.is_grad_enabled()):
+        # smplx always adds transl (argument or its own Parameter).  The only case skipped here is the untouched
+        # zeros default outside of training (no gradient can be asked for it): adding zeros is the identity.
+        if apply_default_transl and self._transl_is_untouched_default() and not (
+                self.transl.requires_grad and torch.is_grad_enabled()):
+            tr = None
+        else:
             tr = self._expand(transl, B)
         verts, joints, j2d = SMPLFunction.apply(eng, betas_b.float().contiguous(), full_pose.float().contiguous(),
                                                 None if tr is None else tr.float().contiguous(),

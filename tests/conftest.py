@@ -37,6 +37,13 @@ def synthetic_model():
 
 
 @pytest.fixture(scope="session")
+def wide_model():
+    """Harder sparsity statistics: regressors over many mesh parts, skinning rows with 1-4 influences."""
+    from soccerplayershapepose_b200.model_io import make_synthetic_smpl
+    return make_synthetic_smpl(seed=1234, statistics="wide")
+
+
+@pytest.fixture(scope="session")
 def intree_golden():
     return dict(np.load(os.path.join(GOLDEN_DIR, "intree_golden.npz")))
 

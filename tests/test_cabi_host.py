@@ -69,7 +69,19 @@ def _f32_to_bf16_rn(x):
 
 def test_packed_model_emulation_matches_oracle(host_engine, synthetic_model):
     """Emulate the GPU dataflow in numpy from the PACKED arrays only and compare with the oracle."""
-    eng, model = host_engine, synthetic_model
+    _check_packed_emulation(host_engine, synthetic_model)
+
+
+def test_packed_model_emulation_wide_statistics(wide_model):
+    """The same on the 'wide' synthetic model: regressor rows spread over 6-10 mesh parts (twice the virtual joint
+    rows) and skinning rows with 1-3 influences (the compact model may flatter the virtual-row trick)."""
+    assert set(np.unique((wide_model["lbs_weights"] > 0).sum(1))) == {1, 2, 3, 4}
+    eng = SMPLEngine(wide_model, device=None)
+    assert eng.info.num_virtual_groups > 1000
+    _check_packed_emulation(eng, wide_model)
+
+
+def _check_packed_emulation(eng, model):
     info = eng.info
     V, n_pad, nq = info.num_verts, info.num_blend_rows_padded, info.num_virtual_groups
     nb, nf = 10, 217
