@@ -46,8 +46,12 @@ extern "C" {
 
 /* arithmetic modes of the blend-shape contraction (BASELINE.json north_star: fp32 / bf16-GEMM) */
 #define B200SMPL_MODE_FP32 0       /* tcgen05 bf16x3 error-compensated split, fp32 accumulate (~fp32 accuracy) */
-#define B200SMPL_MODE_BF16 1       /* tcgen05 bf16 pose-corrective operands; template+shape still split-exact */
+#define B200SMPL_MODE_BF16 1       /* bf16-GEMM mode: forward blend with bf16 pose-corrective operands (template+shape
+                                      still split-exact; positions within 1e-4 m); the gradient GEMM keeps the bf16x3
+                                      split so that gradients stay within 1e-4 relative */
 #define B200SMPL_MODE_FP32_SIMT 2  /* plain fp32 FFMA kernels (verification mode, slow) */
+#define B200SMPL_MODE_BF16_FAST 3  /* MODE_BF16 forward + single-product bf16 gradient GEMM: grad_betas ~2e-3 relative,
+                                      i.e. OUTSIDE the 1e-4 gradient tolerance; 9 % faster step */
 
 typedef struct b200smpl_model b200smpl_model; /* opaque */
 

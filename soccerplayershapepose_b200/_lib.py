@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(HERE, "libb200smpl.so")
 MODE_FP32 = 0
 MODE_BF16 = 1
 MODE_FP32_SIMT = 2
-MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "fp32_simt": MODE_FP32_SIMT}
+MODE_BF16_FAST = 3
+MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "fp32_simt": MODE_FP32_SIMT, "bf16_fast": MODE_BF16_FAST}
 
 ERR_INVALID, ERR_CUDA, ERR_WORKSPACE = -1, -2, -3
 

@@ -40,6 +40,15 @@ LaunchTimer::~LaunchTimer() {
   g_timing_recs.push_back({name_, start_, stop});
 }
 
+// The public modes name the precision of the FORWARD blend GEMM.  The gradient GEMM of the bf16-GEMM mode runs the
+// bf16x3 split like the fp32 mode: with single bf16 products grad_betas is 2.2e-3 relative off the fp64 oracle
+// (BASELINE.json north_star: 1e-4), with the split it is 2e-5 for +9 % step time.  The single-product backward stays
+// available as B200SMPL_MODE_BF16_FAST.
+static int fwd_gemm_mode(int mode) { return mode == B200SMPL_MODE_BF16_FAST ? B200SMPL_MODE_BF16 : mode; }
+static int bwd_gemm_mode(int mode) {
+  return mode == B200SMPL_MODE_BF16 ? B200SMPL_MODE_FP32 : (mode == B200SMPL_MODE_BF16_FAST ? B200SMPL_MODE_BF16 : mode);
+}
+
 constexpr int DEFAULT_SLAB = 4096;   // bodies per pass (vpT slab = n_pad * S * 4 B)
 
 struct Plan {
@@ -73,9 +82,10 @@ static Plan make_plan(const b200smpl_model* m, int batch, int mode, int slab_bod
   p.off_vpT = take((size_t)d.n_pad * S_ * 4);
   p.saved_slab_bytes = align_up((size_t)NJ * AELEMS * S_ * 4, 1024) + align_up((size_t)d.n_pad * S_ * 4, 1024);
   if (backward) {
-    p.k_splits = mode == B200SMPL_MODE_FP32_SIMT ? 1 : blend_bwd_umma_splits(d, mode, p.S, m->num_sms);
+    const int bmode = bwd_gemm_mode(mode);
+    p.k_splits = bmode == B200SMPL_MODE_FP32_SIMT ? 1 : blend_bwd_umma_splits(d, bmode, p.S, m->num_sms);
     p.off_dvp_hi = take(S_ * d.n_pad * 2);
-    p.off_dvp_lo = take(mode == B200SMPL_MODE_BF16 ? 0 : S_ * d.n_pad * 2);
+    p.off_dvp_lo = take(bmode == B200SMPL_MODE_BF16 ? 0 : S_ * d.n_pad * 2);
     // dA accumulator [S/32][288][32] directly followed by the dtransl accumulator [S/32][3][32]
     p.off_dA = take((size_t)(NJ * AELEMS + 3) * S_ * 4);
     p.off_dtr = p.off_dA + (size_t)NJ * AELEMS * S_ * 4;
@@ -90,7 +100,8 @@ static int check_common(const b200smpl_model* m, int batch, int mode, const void
   if (m == nullptr) return fail(B200SMPL_ERR_INVALID, "null model handle");
   if (m->device < 0) return fail(B200SMPL_ERR_CUDA, "host-only model handle: no CUDA device (there is no CPU fallback)");
   if (batch < 1) return fail(B200SMPL_ERR_INVALID, "batch must be >= 1");
-  if (mode != B200SMPL_MODE_FP32 && mode != B200SMPL_MODE_BF16 && mode != B200SMPL_MODE_FP32_SIMT)
+  if (mode != B200SMPL_MODE_FP32 && mode != B200SMPL_MODE_BF16 && mode != B200SMPL_MODE_FP32_SIMT &&
+      mode != B200SMPL_MODE_BF16_FAST)
     return fail(B200SMPL_ERR_INVALID, "unknown mode");
   if (ws == nullptr) return fail(B200SMPL_ERR_WORKSPACE, "null workspace");
   return 0;
@@ -303,7 +314,7 @@ int b200smpl_forward(const b200smpl_model* m, const b200smpl_forward_args* a, vo
     if (a->mode == B200SMPL_MODE_FP32_SIMT)
       rc = launch_blend_fwd_simt(d, featf, S, Sw, vpT, row_begin, d.n_pad, st);
     else
-      rc = launch_blend_fwd_umma(d, a->mode, feat, S, Sw, vpT, row_begin, d.n_pad, st);
+      rc = launch_blend_fwd_umma(d, fwd_gemm_mode(a->mode), feat, S, Sw, vpT, row_begin, d.n_pad, st);
     if (rc) return rc;
     if (a->vertices)
       if ((rc = launch_lbs_fwd(d, vpT, S, A_T, b0, nb, a->transl, a->vertices, m->num_sms, st))) return rc;
@@ -343,7 +354,8 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
   float* A_T = (float*)(ws + p.off_A);
   float* vpT = (float*)(ws + p.off_vpT);
   __nv_bfloat16* dvp_hi = (__nv_bfloat16*)(ws + p.off_dvp_hi);
-  __nv_bfloat16* dvp_lo = a->mode == B200SMPL_MODE_BF16 ? nullptr : (__nv_bfloat16*)(ws + p.off_dvp_lo);
+  const int bmode = bwd_gemm_mode(a->mode);
+  __nv_bfloat16* dvp_lo = bmode == B200SMPL_MODE_BF16 ? nullptr : (__nv_bfloat16*)(ws + p.off_dvp_lo);
   float* dA_part = (float*)(ws + p.off_dA);
   float* dtr_part = (float*)(ws + p.off_dtr);
   float* dJtot = (float*)(ws + p.off_dJtot);
@@ -382,7 +394,7 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
       if (a->mode == B200SMPL_MODE_FP32_SIMT)
         rc = launch_blend_fwd_simt(d, featf, S, Sw, vpT, row_begin, d.n_pad, st);
       else
-        rc = launch_blend_fwd_umma(d, a->mode, feat, S, Sw, vpT, row_begin, d.n_pad, st);
+        rc = launch_blend_fwd_umma(d, fwd_gemm_mode(a->mode), feat, S, Sw, vpT, row_begin, d.n_pad, st);
       if (rc) return rc;
     }
     {  // the gradient GEMM reads whole 64-row K slabs: rows between row_end and the slab boundary must be finite
@@ -402,7 +414,7 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
     if (a->mode == B200SMPL_MODE_FP32_SIMT)
       rc = launch_blend_bwd_simt(d, dvp_hi, dvp_lo, S, Sw, dfeat_part, row_begin, row_end, st);
     else
-      rc = launch_blend_bwd_umma(d, a->mode, dvp_hi, dvp_lo, S, Sw, dfeat_part, k_splits, row_begin, row_end, st);
+      rc = launch_blend_bwd_umma(d, bmode, dvp_hi, dvp_lo, S, Sw, dfeat_part, k_splits, row_begin, row_end, st);
     if (rc) return rc;
     if ((rc = launch_pose_bwd(d, a->betas, a->pose, aa, b0, nb, S, A_T, dA_part, 1, dtr_part, dfeat_part, k_splits,
                               have_j ? dJ : nullptr, a->grad_betas, a->grad_pose, a->grad_transl, st)))

@@ -3,8 +3,10 @@ library, against the CPU oracle on the same seeded inputs, against the committed
 and -- at BASELINE.json's batch sizes -- through size-independent properties.
 
 Tolerances (BASELINE.json north_star): vertices / joints 1e-5 m absolute in fp32 modes, 1e-4 m in
-bf16-GEMM mode; gradients 1e-4 relative in fp32 modes (bf16 mode: 3e-2, its operands carry 8
-mantissa bits); index / topology work bit-exact.
+bf16-GEMM mode; gradients 1e-4 relative in every mode the north_star names (the bf16-GEMM mode runs its gradient
+GEMM in the bf16x3 split for that; measured 2e-5).  "Relative" = max |error| / max |reference| per gradient
+tensor (`_rel`).  The extra `bf16_fast` mode (single-product bf16 gradient GEMM) is OUTSIDE that bound by design:
+measured 2.2e-3 on grad_betas, tested at 5e-3.  Index / topology work bit-exact.
 """
 import numpy as np
 import pytest
@@ -17,9 +19,9 @@ from soccerplayershapepose_b200.smpl import SMPL, SMPLLayer, SMPLOutput
 
 pytestmark = pytest.mark.gpu
 
-POS_TOL = {"fp32": 1e-5, "fp32_simt": 1e-5, "bf16": 1e-4}
-GRAD_TOL = {"fp32": 1e-4, "fp32_simt": 1e-4, "bf16": 3e-2}
-MODES = ["fp32_simt", "fp32", "bf16"]
+POS_TOL = {"fp32": 1e-5, "fp32_simt": 1e-5, "bf16": 1e-4, "bf16_fast": 1e-4}
+GRAD_TOL = {"fp32": 1e-4, "fp32_simt": 1e-4, "bf16": 1e-4, "bf16_fast": 5e-3}
+MODES = ["fp32_simt", "fp32", "bf16", "bf16_fast"]
 
 
 @pytest.fixture(scope="module")
@@ -261,7 +263,7 @@ def test_full_size_properties(engine, dev, mode):
     ga = engine.backward(betas[sl], pose_aa[sl], trans[sl], None, None, dV, dJ, None, axis_angle=True, mode=m)
     gb = engine.backward(betas[sl], pose_aa[sl], trans[sl], None, None, 2 * dV, 2 * dJ, None, axis_angle=True, mode=m)
     for a, b in zip(ga[:3], gb[:3]):
-        assert _rel(b, 2 * a) < (1e-5 if mode == "fp32" else 2e-2)
+        assert _rel(b, 2 * a) < 1e-5
 
 
 @pytest.mark.parametrize("nb,B", [(1, 37), (4, 130), (16, 256)])
@@ -344,6 +346,59 @@ def test_batch_past_int32_element_index(engine, dev):
         assert _rel(last, a) < 1e-4
         assert _rel(b[:P], a) < 1e-4
         assert torch.isfinite(b).all()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_forward_full_size_vs_oracle(engine, oracle64, dev, mode):
+    """BASELINE.json config 2 size (B = 4096): vertices and joints of 64 random bodies of the batch against the
+    fp64 oracle run on just those bodies, both pose surfaces."""
+    B = 4096
+    m = _lib.MODES[mode]
+    betas, pose_aa, trans, _ = make_inputs(B, 31)
+    pick = torch.randperm(B, generator=torch.Generator().manual_seed(32))[:64]
+    pick[:4] = torch.tensor([0, 127, 128, 4095])
+    d = lambda x: x.to(dev)  # noqa: E731
+    for axis_angle in (True, False):
+        pose = pose_aa if axis_angle else rotmats_of(pose_aa)
+        v, j, _ = engine.forward(d(betas), d(pose), d(trans), None, axis_angle=axis_angle, mode=m)
+        ref = oracle64.forward_flat(betas[pick].double(), pose[pick].double(), trans[pick].double(), pose2rot=axis_angle)
+        ev = (v[pick.to(dev)].cpu().double() - ref.vertices).abs().max().item()
+        ej = (j[pick.to(dev)].cpu().double() - ref.joints).abs().max().item()
+        print("full-size forward errors vs fp64 oracle, 64 bodies (vertices, joints) [m]:", mode, axis_angle, ev, ej)
+        assert ev < POS_TOL[mode] and ej < POS_TOL[mode]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_wide_statistics_model_parity(wide_model, dev, mode):
+    """The 'wide' synthetic model (H36M / COCO-plus regressor rows over 6-10 mesh parts -> twice the virtual joint
+    rows; skinning rows with 1-3 influences): forward and backward against the fp64 oracle at a ragged batch, and
+    a 4096-body batch against the same bodies computed in small batches."""
+    eng = SMPLEngine(wide_model, dev)
+    orc = O.SMPLOracle(wide_model, dtype=torch.float64)
+    m = _lib.MODES[mode]
+    B = 70
+    betas, pose_aa, trans, cam = make_inputs(B, 41)
+    rot = rotmats_of(pose_aa)
+    g = torch.Generator().manual_seed(42)
+    dV, dJ, dJ2 = torch.randn(B, 6890, 3, generator=g), torch.randn(B, 90, 3, generator=g), torch.randn(B, 90, 2, generator=g)
+    d = lambda x: x.to(dev)  # noqa: E731
+    out = eng.forward(d(betas), d(rot), d(trans), d(cam), mode=m, save=True)
+    ref = orc.forward_flat(betas.double(), rot.double(), trans.double(), pose2rot=False)
+    assert (out[0].cpu().double() - ref.vertices).abs().max().item() < POS_TOL[mode]
+    assert (out[1].cpu().double() - ref.joints).abs().max().item() < POS_TOL[mode]
+    rb, rp, rt, rc = _oracle_grads(orc, betas, rot, trans, cam, dV, dJ, dJ2, False)
+    for saved in (out[3], None):
+        gb, gp, gt, gc = eng.backward(d(betas), d(rot), d(trans), d(cam), out[1], d(dV), d(dJ), d(dJ2), mode=m, saved=saved)
+        errs = (_rel(gb.cpu().double(), rb), _rel(gp.cpu().double().reshape(rp.shape), rp), _rel(gt.cpu().double(), rt),
+                _rel(gc.cpu().double(), rc))
+        assert max(errs) < GRAD_TOL[mode], errs
+    # production size: the same body inside a 4096 batch and inside a small batch
+    B2 = 4096
+    betas2, pose2, trans2, _ = make_inputs(B2, 43)
+    v, j, _ = eng.forward(d(betas2), d(pose2), d(trans2), None, axis_angle=True, mode=m)
+    for i in (0, 2500, 4095):
+        vi, ji, _ = eng.forward(d(betas2[i:i + 1]), d(pose2[i:i + 1]), d(trans2[i:i + 1]), None, axis_angle=True, mode=m)
+        assert torch.equal(vi[0], v[i]) and torch.equal(ji[0], j[i])
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])

@@ -93,8 +93,8 @@ def test_kernels_follow_the_live_buffers(synthetic_model, wide_model):
     with torch.no_grad():
         a.v_template.add_(torch.tensor([0.0, 1.0, 0.0], device=dev))
     assert torch.allclose(a(**kw).vertices[..., 1], vb.vertices[..., 1] + 1.0, atol=1e-5)
-    orc = O.SMPLOracle({k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v)
-                        for k, v in a._model_tensors().items()}, dtype=torch.float64)
+    orc = O.SMPLOracle(dict({k: v.detach().cpu().numpy() for k, v in a._model_tensors().items()}, faces=a.faces),
+                       dtype=torch.float64)
     ref = orc.forward(betas.cpu().double(), pose[:, 3:].cpu().double(), pose[:, :3].cpu().double(), None, True)
     assert (a(**kw).vertices.cpu().double() - ref.vertices).abs().max() < 1e-5
 
