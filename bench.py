@@ -551,8 +551,8 @@ def main():
         extras["e2e_forward_vertices_to_host"] = {
             "value": fwd_val, "unit": "meshes/s (forward only)", "h2d_bytes_per_step": io_bytes,
             "d2h_bytes_per_step": d2h_bytes,
-            "roofline": {"bound": "pcie d2h", "achieved": fwd_val * d2h_bytes / 1e9, "peak": d2h_gbs, "unit": "GB/s",
-                         "frac": fwd_val * d2h_bytes / 1e9 / d2h_gbs,
+            "roofline": {"bound": "pcie d2h", "achieved": fwd_val * (d2h_bytes / B) / 1e9, "peak": d2h_gbs, "unit": "GB/s",
+                         "frac": fwd_val * (d2h_bytes / B) / 1e9 / d2h_gbs,
                          "peak_source": "pinned D2H copy of one step's vertices, measured in this run"}}
 
     cpu_baseline = None

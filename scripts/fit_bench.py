@@ -12,9 +12,12 @@ from soccerplayershapepose_b200.smpl import SMPL                                
 from soccerplayershapepose_b200.synthetic_inputs import make_smpl_inputs        # noqa: E402
 from soccerplayershapepose_b200 import ops                                      # noqa: E402
 
+from bench import ClockSampler                                                  # noqa: E402
+
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 mode = sys.argv[3] if len(sys.argv) > 3 else "fp32"
+lr = float(sys.argv[4]) if len(sys.argv) > 4 else 1e-3        # the reference's fitting rate (Python/Soccer/global_var.py:71)
 dev = torch.device("cuda", 0)
 smpl = SMPL(model_data=make_synthetic_smpl(1234), mode=mode).to(dev)
 x = make_smpl_inputs(B, 0)
@@ -30,17 +33,24 @@ rot0, betas0 = y["rotmats"].to(dev), torch.zeros_like(betas_t)
 cam0 = torch.tensor([0.9, 0.0, 0.0], device=dev).repeat(B, 1)
 res = {}
 for use_graph in (True, False):
-    fitter = BatchedFitter(smpl, lr=1e-2, shape_weight=1e-3, use_cuda_graph=use_graph)
+    fitter = BatchedFitter(smpl, lr=lr, shape_weight=1e-3, use_cuda_graph=use_graph)
     fitter.fit(rot0, betas0, cam0, label, iterations=41)      # warm-up (captures the 20-iteration graph, kept per shape)
     torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
     t0 = time.perf_counter()
     r = fitter.fit(rot0, betas0, cam0, label, iterations=iters)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    if use_graph:
+        clocks_graph = clocks
     res["graph" if use_graph else "eager"] = dt
     if use_graph:
         l0, l1 = r["initial_loss"].mean().item(), r["best_loss"].mean().item()
-print(json.dumps({"workload": "fit %d players x %d Adam iterations, joints2D loss + shape prior, %s mode" % (B, iters, mode),
+print(json.dumps({"workload": "BASELINE.json configs[2]: fit %d players x %d Adam iterations (lr %g), joints2D loss + shape "
+                              "prior, %s mode, joints-only SMPL path" % (B, iters, lr, mode),
+                  "clocks": clocks_graph,
                   "seconds_cuda_graph": res["graph"], "seconds_eager": res["eager"],
                   "player_iterations_per_s": B * iters / res["graph"], "ms_per_iteration": res["graph"] / iters * 1e3,
                   "mean_loss_initial": l0, "mean_loss_best": l1}))

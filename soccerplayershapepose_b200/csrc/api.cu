@@ -5,9 +5,14 @@
 #include <map>
 #include <mutex>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace b200smpl {
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 static thread_local std::string g_last_error;
 static std::atomic<long long> g_launches{0};
@@ -25,7 +30,7 @@ static std::mutex g_timing_mu;
 struct TimingRec { const char* name; cudaEvent_t a, b; };
 static std::vector<TimingRec> g_timing_recs;
 
-LaunchTimer::LaunchTimer(const char* name, cudaStream_t st) : name_(name), st_(st) {
+LaunchTimer::LaunchTimer(const char* name, cudaStream_t st) : name_(name), st_(st), nvtx_(name) {
   if (g_timing.load(std::memory_order_relaxed)) {
     if (cudaEventCreate(&start_) == cudaSuccess) cudaEventRecord(start_, st_);
     else start_ = nullptr;
@@ -147,6 +152,7 @@ size_t b200smpl_timing_report(char* buf, size_t cap) {
 }
 
 int b200smpl_model_create(const b200smpl_model_desc* desc, int device, b200smpl_model** out) {
+  B200_NVTX("b200smpl_model_create");
   if (desc == nullptr || out == nullptr) return fail(B200SMPL_ERR_INVALID, "null argument");
   *out = nullptr;
   b200smpl_model* m = new b200smpl_model();
@@ -278,6 +284,7 @@ size_t b200smpl_backward_workspace_bytes(const b200smpl_model* m, int batch, int
 }
 
 int b200smpl_forward(const b200smpl_model* m, const b200smpl_forward_args* a, void* stream) {
+  B200_NVTX("b200smpl_forward");
   if (a == nullptr) return fail(B200SMPL_ERR_INVALID, "null args");
   int rc = check_common(m, a->batch, a->mode, a->workspace);
   if (rc) return rc;
@@ -326,6 +333,7 @@ int b200smpl_forward(const b200smpl_model* m, const b200smpl_forward_args* a, vo
 }
 
 int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, void* stream) {
+  B200_NVTX("b200smpl_backward");
   if (a == nullptr) return fail(B200SMPL_ERR_INVALID, "null args");
   int rc = check_common(m, a->batch, a->mode, a->workspace);
   if (rc) return rc;

@@ -298,6 +298,7 @@ using namespace b200smpl;
 extern "C" {
 
 int b200smpl_batch_rodrigues(const float* rot_vecs, float* rotmats, int64_t n, void* stream) {
+  B200_NVTX("b200smpl_batch_rodrigues");
   if (!rot_vecs || !rotmats || n < 0) return fail(B200SMPL_ERR_INVALID, "bad argument");
   if (n == 0) return 0;
   rodrigues_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rot_vecs, rotmats, n);
@@ -307,6 +308,7 @@ int b200smpl_batch_rodrigues(const float* rot_vecs, float* rotmats, int64_t n, v
 
 int b200smpl_batch_rodrigues_backward(const float* rot_vecs, const float* grad_rotmats, float* grad_rot_vecs, int64_t n,
                                       void* stream) {
+  B200_NVTX("b200smpl_batch_rodrigues_backward");
   if (!rot_vecs || !grad_rotmats || !grad_rot_vecs || n < 0) return fail(B200SMPL_ERR_INVALID, "bad argument");
   if (n == 0) return 0;
   rodrigues_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rot_vecs, grad_rotmats, grad_rot_vecs, n);
@@ -315,6 +317,7 @@ int b200smpl_batch_rodrigues_backward(const float* rot_vecs, const float* grad_r
 }
 
 int b200smpl_rot6d_to_rotmat(const float* x6, float* rotmats, int64_t n, void* stream) {
+  B200_NVTX("b200smpl_rot6d_to_rotmat");
   if (!x6 || !rotmats || n < 0) return fail(B200SMPL_ERR_INVALID, "bad argument");
   if (n == 0) return 0;
   rot6d_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x6, rotmats, n);
@@ -324,6 +327,7 @@ int b200smpl_rot6d_to_rotmat(const float* x6, float* rotmats, int64_t n, void* s
 
 int b200smpl_rot6d_to_rotmat_backward(const float* x6, const float* grad_rotmats, float* grad_x6, int64_t n,
                                       void* stream) {
+  B200_NVTX("b200smpl_rot6d_to_rotmat_backward");
   if (!x6 || !grad_rotmats || !grad_x6 || n < 0) return fail(B200SMPL_ERR_INVALID, "bad argument");
   if (n == 0) return 0;
   rot6d_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x6, grad_rotmats, grad_x6, n);
@@ -333,6 +337,7 @@ int b200smpl_rot6d_to_rotmat_backward(const float* x6, const float* grad_rotmats
 
 int b200smpl_orthographic_project(const float* points, const float* cam, float* out, int batch, int n, float pixel_wh,
                                   void* stream) {
+  B200_NVTX("b200smpl_orthographic_project");
   if (!points || !cam || !out || batch < 1 || n < 1) return fail(B200SMPL_ERR_INVALID, "bad argument");
   ortho_fwd_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(points, cam, out, n, pixel_wh);
   B200_LAUNCH_CHECK("ortho_fwd");
@@ -342,6 +347,7 @@ int b200smpl_orthographic_project(const float* points, const float* cam, float* 
 int b200smpl_orthographic_project_backward(const float* points, const float* cam, const float* grad_out,
                                            float* grad_points, float* grad_cam, int batch, int n, float pixel_wh,
                                            void* stream) {
+  B200_NVTX("b200smpl_orthographic_project_backward");
   if (!points || !cam || !grad_out || batch < 1 || n < 1) return fail(B200SMPL_ERR_INVALID, "bad argument");
   ortho_bwd_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(points, cam, grad_out, grad_points, grad_cam, n, pixel_wh);
   B200_LAUNCH_CHECK("ortho_bwd");
@@ -350,6 +356,7 @@ int b200smpl_orthographic_project_backward(const float* points, const float* cam
 
 int b200smpl_perspective_project(const float* points, const float* rotation, const float* translation, float* out,
                                  int batch, int n, float focal_length, float img_wh, void* stream) {
+  B200_NVTX("b200smpl_perspective_project");
   if (!points || !rotation || !translation || !out || batch < 1 || n < 1)
     return fail(B200SMPL_ERR_INVALID, "bad argument");
   persp_fwd_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(points, rotation, translation, out, n, focal_length,
@@ -362,6 +369,7 @@ int b200smpl_perspective_project_backward(const float* points, const float* rota
                                           const float* grad_out, float* grad_points, float* grad_rotation,
                                           float* grad_translation, int batch, int n, float focal_length, float img_wh,
                                           void* stream) {
+  B200_NVTX("b200smpl_perspective_project_backward");
   (void)img_wh;
   if (!points || !rotation || !translation || !grad_out || batch < 1 || n < 1)
     return fail(B200SMPL_ERR_INVALID, "bad argument");
@@ -374,6 +382,7 @@ int b200smpl_perspective_project_backward(const float* points, const float* rota
 int b200smpl_joints2d_loss(const float* joints, const float* cam, const int32_t* joint_map, const float* label,
                            const uint8_t* vis, int batch, int num_joints, int nmap, float proj_wh, float norm_wh,
                            float log_var, float* loss, float* grad_joints, float* grad_cam, void* stream) {
+  B200_NVTX("b200smpl_joints2d_loss");
   if (!joints || !cam || !joint_map || !label || !loss || batch < 1 || nmap < 1)
     return fail(B200SMPL_ERR_INVALID, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;

@@ -137,12 +137,21 @@ int fail(int code, const std::string& msg);
 void count_launch(int n = 1);
 
 // optional per-launch device timing (bench.py roofline); see b200smpl_timing_enable
+// NVTX range over a C-ABI entry point / a kernel launch (SURVEY.md section 5 "Tracing"; no-ops unless a tool such
+// as Nsight Systems has injected its NVTX library into the process)
+struct NvtxRange {
+  explicit NvtxRange(const char* name);
+  ~NvtxRange();
+};
+#define B200_NVTX(name) ::b200smpl::NvtxRange _nvtx_range(name)
+
 struct LaunchTimer {
   LaunchTimer(const char* name, cudaStream_t st);
   ~LaunchTimer();
   const char* name_;
   cudaStream_t st_;
   cudaEvent_t start_ = nullptr;
+  NvtxRange nvtx_;
 };
 
 #define B200_CUDA_TRY(expr)                                                                       \

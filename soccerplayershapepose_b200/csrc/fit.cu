@@ -181,6 +181,7 @@ int b200smpl_fit_loss(const float* joints, const float* cam, const int32_t* join
                       const uint8_t* vis, const float* betas, int batch, int num_joints, int nmap, int num_betas,
                       float proj_wh, float norm_wh, float log_var, float shape_weight, float* loss_per_body,
                       float* grad_joints, float* grad_cam, float* grad_betas, void* stream) {
+  B200_NVTX("b200smpl_fit_loss");
   if (!joints || !cam || !joint_map || !label || !betas || !loss_per_body || !grad_joints || !grad_cam || batch < 1 ||
       nmap < 1)
     return fail(B200SMPL_ERR_INVALID, "bad argument");
@@ -194,6 +195,7 @@ int b200smpl_fit_loss(const float* joints, const float* cam, const int32_t* join
 
 int b200smpl_fit_mark_best(const float* loss_per_body, float* best_loss, int32_t* best_iter, uint8_t* improved,
                            int32_t* step, int batch, void* stream) {
+  B200_NVTX("b200smpl_fit_mark_best");
   if (!loss_per_body || !best_loss || !best_iter || !improved || !step || batch < 1)
     return fail(B200SMPL_ERR_INVALID, "bad argument");
   fit_mark_kernel<<<(batch + 255) / 256, 256, 0, (cudaStream_t)stream>>>(loss_per_body, best_loss, best_iter, improved,
@@ -206,6 +208,7 @@ int b200smpl_fit_adam_step(float* params, const float* grad, const float* grad_e
                            float* best_params, const uint8_t* improved, const uint8_t* frozen_cols, int32_t* step,
                            int commit_step, int batch, int cols, float lr, float beta1, float beta2, float eps,
                            void* stream) {
+  B200_NVTX("b200smpl_fit_adam_step");
   if (!params || !grad || !exp_avg || !exp_avg_sq || !best_params || !improved || !step || batch < 1 || cols < 1)
     return fail(B200SMPL_ERR_INVALID, "bad argument");
   const long long n = (long long)batch * cols;
@@ -220,6 +223,7 @@ int b200smpl_fit_adam_step(float* params, const float* grad, const float* grad_e
 int b200smpl_fit_update(const b200smpl_fit_group* groups, int ngroups, const float* loss_per_body, float* best_loss,
                         int32_t* best_iter, float* first_loss, int32_t* step, int parity, int batch, float lr, float beta1,
                         float beta2, float eps, void* stream) {
+  B200_NVTX("b200smpl_fit_update");
   if (!groups || ngroups < 1 || ngroups > B200SMPL_FIT_MAX_GROUPS || !loss_per_body || !best_loss || !best_iter || !step ||
       batch < 1 || (parity != 0 && parity != 1))
     return fail(B200SMPL_ERR_INVALID, "bad argument");
