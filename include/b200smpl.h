@@ -260,6 +260,43 @@ B200SMPL_API int b200smpl_fit_update(const b200smpl_fit_group* groups, int ngrou
                                      float* best_loss, int32_t* best_iter, float* first_loss, int32_t* step, int parity,
                                      int batch, float lr, float beta1, float beta2, float eps, void* stream);
 
+/*
+ * Fused multi-task loss of the regressor training step -- replaces HomoscedasticUncertaintyWeightedMultiTaskLoss
+ * (losses/multi_task_loss.py:92-130, without its silhouette term) as called at PyTorch3DTest.py:1072-1106:
+ *   loss = sum over the present terms of  mean((pred - label)^2) * exp(-log_var_t) + log_var_t
+ * terms t = 0 vertices, 1 2D joints (orthographic_project_torch(joints, cam)[:, map2d] -> undo_keypoint_normalisation
+ * (proj_wh) -> both sides 2x/norm_wh - 1, optional vis mask over (body, joint) pairs), 2 3D joints (joints[:, map3d]),
+ * 3 shape parameters, 4 pose rotation matrices.  A term is present when its prediction pointer (map pointer for the
+ * joint terms) is non-NULL.  All pointers are DEVICE pointers; log_var [5] and the upstream gradient are read on the
+ * device, so forward and backward are CUDA-graph capturable.
+ *   forward : out[0] = loss, out[1..5] = weighted parts, out[6..10] = d loss / d log_var_t; fills scratch
+ *   backward: gradients of  grad_loss[0] * loss  (grad_loss NULL = 1) w.r.t. vertices / joints [B][NJ][3] (both joint
+ *             terms accumulated) / cam / shape / pose; any output may be NULL.  Needs the scratch of the forward.
+ */
+typedef struct b200smpl_multitask_loss_args {
+  int32_t batch, num_verts, num_joints, nmap2d, nmap3d, num_betas, pose_cols, reserved0;
+  float proj_wh, norm_wh;         /* 512, 256 in the reference (player_recon.py:1220, config.REGRESSOR_IMG_WH) */
+  const float* verts;             /* [B][V][3] or NULL */
+  const float* verts_label;
+  const float* joints;            /* [B][NJ][3] */
+  const float* cam;               /* [B][3] */
+  const int32_t* map2d;           /* [nmap2d] or NULL */
+  const float* label2d;           /* [B][nmap2d][2] pixels */
+  const uint8_t* vis;             /* [B][nmap2d] or NULL */
+  const int32_t* map3d;           /* [nmap3d] or NULL */
+  const float* label3d;           /* [B][nmap3d][3] */
+  const float* shape;             /* [B][num_betas] or NULL */
+  const float* shape_label;
+  const float* pose;              /* [B][pose_cols] or NULL */
+  const float* pose_label;
+  const float* log_var;           /* [5] */
+  float* scratch;                 /* [16] floats, written by the forward, read by the backward */
+} b200smpl_multitask_loss_args;
+B200SMPL_API int b200smpl_multitask_loss(const b200smpl_multitask_loss_args* args, float* out, void* stream);
+B200SMPL_API int b200smpl_multitask_loss_backward(const b200smpl_multitask_loss_args* args, const float* grad_loss,
+                                                  float* grad_verts, float* grad_joints, float* grad_cam,
+                                                  float* grad_shape, float* grad_pose, void* stream);
+
 /* Test hook (host arithmetic only, no device): the cluster work list of the forward blend GEMM for `body_tiles`
  * 128-body tiles x `row_tiles` 128-row tiles on a device with `num_sms` SMs.  Writes (body-tile pair, first row-tile
  * pair, end row-tile pair) per cluster into out[3 * capacity]; returns the number of clusters or -1. */

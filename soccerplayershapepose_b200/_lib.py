@@ -67,6 +67,18 @@ class FitGroup(Structure):
     ]
 
 
+class MultiTaskLossArgs(Structure):
+    _fields_ = [
+        ("batch", c_int32), ("num_verts", c_int32), ("num_joints", c_int32), ("nmap2d", c_int32), ("nmap3d", c_int32),
+        ("num_betas", c_int32), ("pose_cols", c_int32), ("reserved0", c_int32),
+        ("proj_wh", c_float), ("norm_wh", c_float),
+        ("verts", c_void_p), ("verts_label", c_void_p), ("joints", c_void_p), ("cam", c_void_p),
+        ("map2d", c_void_p), ("label2d", c_void_p), ("vis", c_void_p), ("map3d", c_void_p), ("label3d", c_void_p),
+        ("shape", c_void_p), ("shape_label", c_void_p), ("pose", c_void_p), ("pose_label", c_void_p),
+        ("log_var", c_void_p), ("scratch", c_void_p),
+    ]
+
+
 # every symbol include/b200smpl.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "b200smpl_model_create": (c_int, [POINTER(ModelDesc), c_int, POINTER(c_void_p)]),
@@ -98,6 +110,9 @@ SYMBOLS = {
                                        c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_void_p]),
     "b200smpl_fit_update": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                     c_float, c_float, c_float, c_void_p]),
+    "b200smpl_multitask_loss": (c_int, [POINTER(MultiTaskLossArgs), c_void_p, c_void_p]),
+    "b200smpl_multitask_loss_backward": (c_int, [POINTER(MultiTaskLossArgs), c_void_p, c_void_p, c_void_p, c_void_p,
+                                                 c_void_p, c_void_p, c_void_p]),
     "b200smpl_debug_fwd_gemm_worklist": (c_int, [c_int, c_int, c_int, c_void_p, c_int]),
     "b200smpl_last_error": (c_char_p, []),
     "b200smpl_abi_version": (c_int, []),

@@ -210,3 +210,100 @@ def joints2d_loss(joints: torch.Tensor, cam: torch.Tensor, joint_map: torch.Tens
     (losses/multi_task_loss.py:97-113) with a fixed log-variance.  joint_map: integer CUDA tensor with entries in
     [0, NJ) (converted to int32; a repeated joint accumulates its gradient)."""
     return _J2dLoss.apply(joints, cam, joint_map, label_pixels, vis, proj_wh, norm_wh, log_var)
+
+
+class _MultiTaskLoss(torch.autograd.Function):
+    """loss, parts = f(log_var[5], verts, joints, cam, shape, pose | labels, maps): two launches forward (one
+    reduction pass + finalise), one launch backward; the upstream gradient and the log-variances are read on the
+    device, so the whole thing sits inside a CUDA graph."""
+
+    @staticmethod
+    def forward(ctx, log_var, verts, joints, cam, shape, pose, verts_label, map2d, label2d, vis, map3d, label3d,
+                shape_label, pose_label, proj_wh, norm_wh):
+        dev = log_var.device
+        f = lambda t, n: None if t is None else _req(t, n)   # noqa: E731
+        log_var = _req(log_var, "log_var")
+        verts, joints, cam = f(verts, "verts"), f(joints, "joints"), f(cam, "cam")
+        shape, pose = f(shape, "shape"), f(pose, "pose")
+        verts_label, label2d, label3d = f(verts_label, "verts_label"), f(label2d, "label2d"), f(label3d, "label3d")
+        shape_label, pose_label = f(shape_label, "shape_label"), f(pose_label, "pose_label")
+        ref = joints if joints is not None else (verts if verts is not None else (shape if shape is not None else pose))
+        if ref is None:
+            raise ValueError("multitask_loss needs at least one term")
+        B = ref.shape[0]
+        NJ = 0 if joints is None else joints.shape[1]
+        if map2d is not None:
+            map2d = _checked_joint_map(map2d, dev, NJ)
+        if map3d is not None:
+            map3d = _checked_joint_map(map3d, dev, NJ)
+        n2 = 0 if map2d is None else map2d.numel()
+        n3 = 0 if map3d is None else map3d.numel()
+
+        def chk(t, shp, name):
+            if t is not None and tuple(t.shape) != tuple(shp):
+                raise ValueError("{} has shape {}, expected {}".format(name, tuple(t.shape), tuple(shp)))
+        if log_var.numel() != 5:
+            raise ValueError("log_var must hold 5 values (verts, joints2D, joints3D, shape, pose)")
+        V = 0 if verts is None else verts.shape[1]
+        chk(verts, (B, V, 3), "verts"); chk(verts_label, (B, V, 3), "verts_label")
+        chk(cam, (B, 3), "cam"); chk(label2d, (B, n2, 2), "label2d"); chk(label3d, (B, n3, 3), "label3d")
+        if (verts is None) != (verts_label is None) or (shape is None) != (shape_label is None) or \
+                (pose is None) != (pose_label is None):
+            raise ValueError("a prediction and its label must be given together")
+        pose2 = None if pose is None else pose.reshape(B, -1)
+        pose_label2 = None if pose_label is None else pose_label.reshape(B, -1)
+        if shape is not None:
+            chk(shape_label, tuple(shape.shape), "shape_label")
+        if pose2 is not None:
+            chk(pose_label2, tuple(pose2.shape), "pose_label")
+        visu8 = None
+        if vis is not None:
+            chk(vis, (B, n2), "vis")
+            visu8 = vis.to(torch.uint8).contiguous()
+        p = lambda t: None if t is None else t.data_ptr()   # noqa: E731
+        scratch = torch.empty(16, dtype=torch.float32, device=dev)
+        out = torch.empty(11, dtype=torch.float32, device=dev)
+        args = _lib.MultiTaskLossArgs(
+            batch=B, num_verts=V, num_joints=NJ, nmap2d=n2, nmap3d=n3, num_betas=0 if shape is None else shape.shape[1],
+            pose_cols=0 if pose2 is None else pose2.shape[1], reserved0=0, proj_wh=float(proj_wh), norm_wh=float(norm_wh),
+            verts=p(verts), verts_label=p(verts_label), joints=p(joints), cam=p(cam), map2d=p(map2d), label2d=p(label2d),
+            vis=p(visu8), map3d=p(map3d), label3d=p(label3d), shape=p(shape), shape_label=p(shape_label), pose=p(pose2),
+            pose_label=p(pose_label2), log_var=p(log_var), scratch=p(scratch))
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().b200smpl_multitask_loss(ctypes.byref(args), out.data_ptr(), _stream(log_var)),
+                       "multitask_loss")
+        ctx.args = args
+        ctx.keep = (log_var, verts, joints, cam, shape, pose2, verts_label, map2d, label2d, visu8, map3d, label3d,
+                    shape_label, pose_label2, scratch, out)          # the raw pointers in `args` stay valid
+        ctx.pose_shape = None if pose is None else pose.shape
+        parts = out[1:6]
+        ctx.mark_non_differentiable(parts)
+        return out[0], parts
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_parts):
+        (log_var, verts, joints, cam, shape, pose2, _vl, _m2, _l2, _vis, _m3, _l3, _sl, _pl, _scratch, out) = ctx.keep
+        need = ctx.needs_input_grad
+        g = g_loss.contiguous().float()
+        mk = lambda t, on: torch.empty_like(t) if (t is not None and on) else None   # noqa: E731
+        gv, gj, gc = mk(verts, need[1]), mk(joints, need[2]), mk(cam, need[3])
+        gs, gp = mk(shape, need[4]), mk(pose2, need[5])
+        p = lambda t: None if t is None else t.data_ptr()   # noqa: E731
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.load().b200smpl_multitask_loss_backward(
+                ctypes.byref(ctx.args), g.data_ptr(), p(gv), p(gj), p(gc), p(gs), p(gp), _stream(g)),
+                "multitask_loss_backward")
+        glv = out[6:11] * g if need[0] else None
+        if gp is not None:
+            gp = gp.reshape(ctx.pose_shape)
+        return (glv, gv, gj, gc, gs, gp) + (None,) * 10
+
+
+def multitask_loss(log_var: torch.Tensor, *, verts=None, verts_label=None, joints=None, cam=None, map2d=None,
+                   label2d=None, vis=None, map3d=None, label3d=None, shape=None, shape_label=None, pose=None,
+                   pose_label=None, proj_wh: float = 512.0, norm_wh: float = 256.0):
+    """Fused HomoscedasticUncertaintyWeightedMultiTaskLoss (losses/multi_task_loss.py:92-130 without the silhouette
+    term): `log_var` (5,) = log-variances of (verts, joints2D, joints3D, shape_params, pose_params); a term is
+    evaluated when its prediction (its joint map for the joint terms) is given.  Returns (loss, parts (5,))."""
+    return _MultiTaskLoss.apply(log_var, verts, joints, cam, shape, pose, verts_label, map2d, label2d, vis, map3d,
+                                label3d, shape_label, pose_label, proj_wh, norm_wh)

@@ -178,3 +178,92 @@ def test_graphed_step_matches_eager_steps(synthetic_model):
     np.testing.assert_allclose(graphed, eager[warm:], rtol=2e-4)
     for pa, pb in zip(head_a.parameters(), head_b.parameters()):
         assert (pa - pb).abs().max().item() < 5e-3 * lr + 1e-6 + 2e-3 * pa.abs().max().item() * 0 + 2e-5
+
+
+def test_single_input_regressor_matches_the_reference_layout():
+    """models/regressor.py:7-46 with resnet_layers=18: ResNet-18 encoder (11.2 M parameters) + IEFModule([512, 512],
+    512, 157); 11.9 M parameters = the 47.6 MB gradient all-reduce of SURVEY.md section 8e."""
+    net = regressor.SingleInputRegressor(resnet_in_channels=18)
+    n = sum(p.numel() for p in net.parameters())
+    assert n == 11_909_789
+    keys = set(net.state_dict())
+    for k in ("image_encoder.conv1.weight", "image_encoder.layer1.0.conv1.weight", "image_encoder.layer2.0.downsample.0.weight",
+              "image_encoder.layer4.1.bn2.running_var", "ief_module.fc1.weight", "ief_module.ief_layers.4.bias"):
+        assert k in keys, k
+    assert not any(k.endswith("initial_params_estimate") or ".fc." in k for k in keys)
+    assert net.image_encoder.conv1.weight.shape == (64, 18, 7, 7)
+    cam, pose6d, shape = net(torch.zeros(2, 18, 64, 64))
+    assert cam.shape == (2, 3) and pose6d.shape == (2, 144) and shape.shape == (2, 10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_vis", [False, True])
+@pytest.mark.parametrize("losses", [LOSSES, ("joints2D", "shape_params"), ("verts",)])
+def test_fused_multitask_loss_matches_eager(synthetic_model, with_vis, losses):
+    """csrc/loss.cu against the module's eager arithmetic (= losses/multi_task_loss.py:92-130, pinned to the reference
+    file in tests/test_oracle.py): value, parts and every gradient (outputs and log-variances), float64 eager reference."""
+    from soccerplayershapepose_b200.smpl import SMPL
+    dev = torch.device("cuda", 0)
+    B = 7
+    feats, labels = _batch(synthetic_model, B, 11)
+    if with_vis:
+        labels["vis"] = torch.rand(B, 17, generator=torch.Generator().manual_seed(3)) > 0.3
+    smpl = SMPL(model_data=synthetic_model, mode="fp32").to(dev)
+    g6, gproj = regressor.gpu_ops()
+    head, _ = _make()
+    head = head.to(dev)
+    crit = regressor.MultiTaskLoss(losses, WEIGHTS).to(dev)
+    lab = {k: v.to(dev) for k, v in labels.items()}
+    out = regressor.predict(head, smpl, feats.to(dev), g6, gproj)
+    leaves = {k: out[k].detach().clone().requires_grad_(True) for k in ("verts", "joints", "cam", "shape_params",
+                                                                        "pose_params_rot_matrices")}
+    loss, parts = crit.forward_fused(lab, leaves)
+    (2.5 * loss).backward()
+    # eager reference in float64 on the same leaves
+    crit64 = regressor.MultiTaskLoss(losses, WEIGHTS).double().to(dev)
+    l64 = {k: v.detach().double().requires_grad_(True) for k, v in leaves.items()}
+    o64 = dict(l64)
+    o64["joints2D"] = O.undo_keypoint_normalisation(O.orthographic_project(l64["joints"], l64["cam"]), 512)[
+        :, config.SMPL_TO_KPRCNN_MAP, :]
+    o64["joints3D"] = l64["joints"][:, config.ALL_JOINTS_TO_COCO_MAP, :]
+    lab64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in lab.items()}
+    ref, parts64 = crit64(lab64, o64)
+    (2.5 * ref).backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    for name in losses:
+        assert abs(parts[name].item() - parts64[name].item()) < 1e-5 * max(1e-3, abs(parts64[name].item()))
+        g, g64 = getattr(crit, name + "_log_var").grad, getattr(crit64, name + "_log_var").grad
+        assert abs(g.item() - g64.item()) < 1e-5 * max(1.0, abs(g64.item()))
+    for k in leaves:
+        g64 = l64[k].grad
+        if g64 is None:
+            assert leaves[k].grad is None or leaves[k].grad.abs().max().item() == 0.0, k
+            continue
+        err = (leaves[k].grad.double() - g64).abs().max().item()
+        assert err < 2e-5 * g64.abs().max().item() + 1e-12, (k, err)
+
+
+@pytest.mark.gpu
+def test_graphed_step_with_fused_loss_and_encoder(synthetic_model):
+    """The captured step with the fused loss kernels and the ResNet-18 encoder in front follows the eager step with
+    the eager loss (same initial weights, same batches)."""
+    from soccerplayershapepose_b200.smpl import SMPL
+    dev = torch.device("cuda", 0)
+    B = 4
+    _, labels = _batch(synthetic_model, B, 13)
+    labels = {k: v.to(dev) for k, v in labels.items()}
+    crops = torch.randn(B, 18, 64, 64, generator=torch.Generator().manual_seed(1)).to(dev)
+    smpl = SMPL(model_data=synthetic_model, mode="fp32").to(dev)
+    g6, gproj = regressor.gpu_ops()
+    torch.manual_seed(0)
+    net_a = regressor.SingleInputRegressor(18).to(dev)
+    net_b = regressor.SingleInputRegressor(18).to(dev)
+    net_b.load_state_dict(net_a.state_dict())
+    crit_a = regressor.MultiTaskLoss(LOSSES, WEIGHTS).to(dev)
+    crit_b = regressor.MultiTaskLoss(LOSSES, WEIGHTS).to(dev)
+    lr, warm, n = 1e-4, 2, 3
+    opt = torch.optim.Adam(list(net_a.parameters()) + list(crit_a.parameters()), lr=lr)
+    eager = [regressor.train_step(net_a, crit_a, opt, smpl, crops, labels, g6, gproj).item() for _ in range(warm + n)]
+    gs = regressor.GraphedTrainStep(net_b, crit_b, smpl, crops, labels, g6, None, lr=lr, warmup=warm, fused_loss=True)
+    graphed = [gs(crops, labels).item() for _ in range(n)]
+    np.testing.assert_allclose(graphed, eager[warm:], rtol=2e-3)
