@@ -207,16 +207,19 @@ class MultiViewFitter:
 
     def __init__(self, smpl: SMPL, lr: float = 1e-3, rounds: int = 3, shape_weight: float = 0.0,
                  joints2d_log_var: float = 0.0, proj_wh: float = 512.0, norm_wh: float = float(config.REGRESSOR_IMG_WH),
-                 betas: tuple = (0.9, 0.999), eps: float = 1e-8, mode: Optional[str] = None):
+                 betas: tuple = (0.9, 0.999), eps: float = 1e-8, mode: Optional[str] = None,
+                 use_cuda_graph: bool = True):
         self.base = BatchedFitter(smpl, lr=lr, shape_weight=shape_weight, joints2d_log_var=joints2d_log_var,
                                   proj_wh=proj_wh, norm_wh=norm_wh, betas=betas, eps=eps, use_cuda_graph=False, mode=mode)
         self.rounds = int(rounds)
+        self.use_graph = bool(use_cuda_graph)
         dev = self.base.dev
         frozen = torch.zeros(23, 9, dtype=torch.uint8)
         for j in (6, 7, 21, 22):                     # body_pose[:, 6:8] and body_pose[:, 21:]
             frozen[j] = 1
         self.frozen_bp = frozen.reshape(-1).to(dev)
         self._inc = torch.tensor([0, 1], dtype=torch.int32, device=dev)
+        self._cache = {}
 
     # one Adam step of `p` (rows, cols) through the C-ABI; `step` holds [committed, current]
     def _adam(self, p, g, extra, m, v, step, frozen, never):
@@ -228,10 +231,17 @@ class MultiViewFitter:
             ctypes.c_void_p(torch.cuda.current_stream(b.dev).cuda_stream)), "fit_adam_step")
 
     def _loss(self, st, v, need_grad):
-        """Forward of view v with the current parameters; fills st['loss'] (and the gradients)."""
+        """Forward of view v with the current parameters; fills st['loss'] (and the gradients).  The training pass
+        keeps the forward's transforms and joint rows for its backward (no pose stage / blend GEMM recomputation)."""
         b = self.base
         st["rot"][:, :9] = st["go"][v]
-        _, joints, _ = b.eng.forward(st["betas"], st["rot"], None, None, axis_angle=False, mode=b.mode, want_vertices=False)
+        if need_grad:
+            _, joints, _, saved = b.eng.forward(st["betas"], st["rot"], None, None, axis_angle=False, mode=b.mode,
+                                                want_vertices=False, save=True, saved_buffer=st.get("saved"))
+            st["saved"] = saved
+        else:
+            _, joints, _ = b.eng.forward(st["betas"], st["rot"], None, None, axis_angle=False, mode=b.mode,
+                                         want_vertices=False)
         vis = st.get("vis")
         stream = ctypes.c_void_p(torch.cuda.current_stream(b.dev).cuda_stream)
         P = st["rot"].shape[0]
@@ -243,40 +253,129 @@ class MultiViewFitter:
         if not need_grad:
             return None
         gb, gp, _, _ = b.eng.backward(st["betas"], st["rot"], None, None, None, None, st["gj"], None,
-                                      axis_angle=False, mode=b.mode, need_transl=False, need_cam=False)
+                                      axis_angle=False, mode=b.mode, need_transl=False, need_cam=False, saved=st["saved"])
         return gb, gp
+
+    # ---- static state + the two kinds of work units (one optimiser step on one view; one validation pass) --------
+    def _state(self, P, V, nb, has_vis):
+        key = (P, V, nb, has_vis)
+        c = self._cache.get(key)
+        if c is not None:
+            return c
+        b = self.base
+        dev = b.dev
+        f32 = dict(dtype=torch.float32, device=dev)
+        st = {"go": torch.empty((V, P, 9), **f32), "cam": torch.empty((V, P, 3), **f32),
+              "label": torch.empty((V, P, b.jmap.numel(), 2), **f32), "bp": torch.empty((P, 207), **f32),
+              "betas": torch.empty((P, nb), **f32), "rot": torch.empty((P, 216), **f32), "loss": torch.zeros(P, **f32),
+              "gj": torch.zeros((P, b.eng.num_joints_out, 3), **f32), "gcam": torch.zeros((P, 3), **f32),
+              "gbetas_prior": torch.zeros((P, nb), **f32)}
+        if has_vis:
+            st["vis"] = torch.empty((V, P, b.jmap.numel()), dtype=torch.uint8, device=dev)
+        c = {"st": st,
+             # dense per-view gradients: all zero except the slice of the view being stepped (written before the
+             # Adam launch, cleared after it) -- the other views move by their momentum only, as under
+             # optim.Adam([cam_wp_mult, global_orient_mult]) in the reference
+             "g_go": torch.zeros((V, P, 9), **f32), "g_cam": torch.zeros((V, P, 3), **f32), "g_bp": torch.zeros((P, 207), **f32),
+             "mom": {k: (torch.zeros_like(st[k]), torch.zeros_like(st[k])) for k in ("go", "cam", "bp", "betas")},
+             "step": torch.zeros(2, dtype=torch.int32, device=dev),
+             "never": torch.zeros(V * P, dtype=torch.uint8, device=dev),
+             "val": torch.zeros(P, **f32), "best_metric": torch.empty(P, **f32),
+             "best": {k: torch.empty_like(st[k]) for k in ("go", "cam", "bp", "betas")},
+             "final": {k: torch.empty_like(st[k]) for k in ("go", "cam", "bp", "betas")},
+             "graphs": {}, "warm": set()}
+        self._cache[key] = c
+        return c
+
+    def _view_step(self, c, phase, v):
+        st, step, mom, never = c["st"], c["step"], c["mom"], c["never"]
+        V, P = st["go"].shape[0], st["go"].shape[1]
+        gb, gp = self._loss(st, v, need_grad=True)
+        step += self._inc
+        if phase == "A":                                        # per-view camera and global orientation
+            g_go, g_cam = c["g_go"], c["g_cam"]
+            g_go[v] = gp[:, :9]
+            g_cam[v] = st["gcam"]
+            self._adam(st["go"].view(V * P, 9), g_go.view(V * P, 9), None, mom["go"][0].view(V * P, 9),
+                       mom["go"][1].view(V * P, 9), step, None, never)
+            self._adam(st["cam"].view(V * P, 3), g_cam.view(V * P, 3), None, mom["cam"][0].view(V * P, 3),
+                       mom["cam"][1].view(V * P, 3), step, None, never)
+            g_go[v].zero_()
+            g_cam[v].zero_()
+        else:                                                   # shared body pose (hands / feet frozen) and betas
+            c["g_bp"].copy_(gp[:, 9:])
+            self._adam(st["bp"], c["g_bp"], None, mom["bp"][0], mom["bp"][1], step, self.frozen_bp, never)
+            self._adam(st["betas"], gb, st["gbetas_prior"], mom["betas"][0], mom["betas"][1], step, None, never)
+            st["rot"][:, 9:] = st["bp"]
+
+    def _validate(self, c, phase):
+        st, val, best_metric = c["st"], c["val"], c["best_metric"]
+        V, P = st["go"].shape[0], st["go"].shape[1]
+        val.zero_()
+        for v in range(V):
+            self._loss(st, v, need_grad=False)
+            val += st["loss"]
+        improved = val < best_metric
+        best_metric.copy_(torch.where(improved, val, best_metric))
+        phase_keys = ("go", "cam") if phase == "A" else ("bp", "betas")
+        for k in ("go", "cam", "bp", "betas"):
+            mask = improved.view(1, P, 1) if k in ("go", "cam") else improved.view(P, 1)
+            c["final"][k].copy_(torch.where(mask, st[k], c["final"][k]))
+            if k in phase_keys:
+                c["best"][k].copy_(torch.where(mask, st[k], c["best"][k]))
+
+    def _run(self, c, name, fn):
+        """One work unit: eager the first time (allocations, attribute set-up), then captured once and replayed."""
+        if not self.use_graph:
+            fn()
+            return
+        g = c["graphs"].get(name)
+        if g is not None:
+            g.replay()
+            return
+        dev = self.base.dev
+        if name not in c["warm"]:
+            c["warm"].add(name)
+            fn()
+            return
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(g):
+            fn()
+        c["graphs"][name] = g
+        g.replay()                                              # the capture itself does not execute
 
     def fit(self, body_pose: torch.Tensor, betas: torch.Tensor, global_orient: torch.Tensor, cam: torch.Tensor,
             keypoints2d: torch.Tensor, vis: Optional[torch.Tensor] = None, iterations: int = 10,
             view_orders=None, seed: int = 0) -> Dict[str, torch.Tensor]:
         """body_pose (P,23,3,3) and betas (P,10) shared by the views; global_orient (P,V,3,3), cam (P,V,3),
         keypoints2d (P,V,17,2) [, vis (P,V,17)] per view.  `iterations` epochs per phase.  `view_orders`: optional
-        list (one per epoch, in execution order: round 0 phase A, round 0 phase B, ...) of view permutations."""
+        list (one per epoch, in execution order: round 0 phase A, round 0 phase B, ...) of view permutations.
+
+        With `use_cuda_graph` the work units -- (phase, view) optimiser steps and the two validation passes -- are
+        captured once per problem shape over static state buffers and replayed: an epoch is V + 1 graph launches
+        whatever its view order, instead of ~12 V eager C-ABI / torch calls."""
         b = self.base
         dev = b.dev
         f32 = dict(dtype=torch.float32, device=dev)
         P, V = global_orient.shape[0], global_orient.shape[1]
-        st = {"go": global_orient.to(**f32).reshape(P, V, 9).transpose(0, 1).contiguous(),          # (V,P,9)
-              "cam": cam.to(**f32).transpose(0, 1).contiguous(),                                    # (V,P,3)
-              "label": keypoints2d.to(**f32).transpose(0, 1).contiguous(),                          # (V,P,17,2)
-              "bp": body_pose.to(**f32).reshape(P, 207).clone().contiguous(),
-              "betas": betas.to(**f32).clone().contiguous()}
+        c = self._state(P, V, int(betas.shape[1]), vis is not None)
+        st = c["st"]
+        st["go"].copy_(global_orient.to(**f32).reshape(P, V, 9).transpose(0, 1))
+        st["cam"].copy_(cam.to(**f32).transpose(0, 1))
+        st["label"].copy_(keypoints2d.to(**f32).transpose(0, 1))
+        st["bp"].copy_(body_pose.to(**f32).reshape(P, 207))
+        st["betas"].copy_(betas.to(**f32))
         if vis is not None:
-            st["vis"] = vis.to(device=dev, dtype=torch.uint8).transpose(0, 1).contiguous()
-        st["rot"] = torch.empty((P, 216), **f32)
+            st["vis"].copy_(vis.to(device=dev, dtype=torch.uint8).transpose(0, 1))
         st["rot"][:, 9:] = st["bp"]
-        st["loss"] = torch.zeros(P, **f32)
-        st["gj"] = torch.zeros((P, b.eng.num_joints_out, 3), **f32)
-        st["gcam"] = torch.zeros((P, 3), **f32)
-        st["gbetas_prior"] = torch.zeros((P, st["betas"].shape[1]), **f32)
-        g_go, g_cam = torch.zeros_like(st["go"]), torch.zeros_like(st["cam"])
-        g_bp = torch.zeros_like(st["bp"])
-        mom = {k: (torch.zeros_like(st[k]), torch.zeros_like(st[k])) for k in ("go", "cam", "bp", "betas")}
-        step = torch.zeros(2, dtype=torch.int32, device=dev)
-        never_vp = torch.zeros(V * P, dtype=torch.uint8, device=dev)
-        best_metric = torch.full((P,), float("inf"), **f32)
-        best = {k: st[k].clone() for k in ("go", "cam", "bp", "betas")}          # per-phase restore points
-        final = {k: st[k].clone() for k in ("go", "cam", "bp", "betas")}         # everything at the best epoch
+        for k in ("g_go", "g_cam", "g_bp"):
+            c[k].zero_()
+        c["best_metric"].fill_(float("inf"))
+        for k in ("go", "cam", "bp", "betas"):
+            c["best"][k].copy_(st[k])                           # per-phase restore points
+            c["final"][k].copy_(st[k])                          # everything at the best epoch
+        mom, step, best, final = c["mom"], c["step"], c["best"], c["final"]
         gen = torch.Generator().manual_seed(seed)
         first_val = None
         epoch_no = 0
@@ -287,62 +386,28 @@ class MultiViewFitter:
             epoch_no += 1
             return o
 
-        def validate(phase_keys):
-            nonlocal best_metric, first_val
-            val = torch.zeros(P, **f32)
-            for v in range(V):
-                self._loss(st, v, need_grad=False)
-                val += st["loss"]
-            if first_val is None:
-                first_val = val.clone()
-            improved = val < best_metric
-            best_metric = torch.where(improved, val, best_metric)
-            for k in ("go", "cam", "bp", "betas"):
-                mask = improved.view(1, P, 1) if k in ("go", "cam") else improved.view(P, 1)
-                final[k] = torch.where(mask, st[k], final[k])
-                if k in phase_keys:
-                    best[k] = torch.where(mask, st[k], best[k])
-
         for _ in range(self.rounds):
-            # ---- phase A: per-view camera and global orientation ----
-            for k in ("go", "cam"):
-                mom[k][0].zero_(); mom[k][1].zero_()
-            step.zero_()
-            for _e in range(iterations):
-                for v in order():
-                    _, gp = self._loss(st, v, need_grad=True)
-                    g_go.zero_(); g_cam.zero_()
-                    g_go[v] = gp[:, :9]
-                    g_cam[v] = st["gcam"]
-                    step += self._inc
-                    self._adam(st["go"].view(V * P, 9), g_go.view(V * P, 9), None, mom["go"][0].view(V * P, 9),
-                               mom["go"][1].view(V * P, 9), step, None, never_vp)
-                    self._adam(st["cam"].view(V * P, 3), g_cam.view(V * P, 3), None, mom["cam"][0].view(V * P, 3),
-                               mom["cam"][1].view(V * P, 3), step, None, never_vp)
-                validate(("go", "cam"))
-            st["go"].copy_(best["go"]); st["cam"].copy_(best["cam"])
-            # ---- phase B: shared body pose (hands / feet frozen) and betas ----
-            for k in ("bp", "betas"):
-                mom[k][0].zero_(); mom[k][1].zero_()
-            step.zero_()
-            for _e in range(iterations):
-                for v in order():
-                    gb, gp = self._loss(st, v, need_grad=True)
-                    g_bp.copy_(gp[:, 9:])
-                    step += self._inc
-                    self._adam(st["bp"], g_bp, None, mom["bp"][0], mom["bp"][1], step, self.frozen_bp, never_vp)
-                    self._adam(st["betas"], gb, st["gbetas_prior"], mom["betas"][0], mom["betas"][1], step, None, never_vp)
-                    st["rot"][:, 9:] = st["bp"]
-                validate(("bp", "betas"))
-            st["bp"].copy_(best["bp"]); st["betas"].copy_(best["betas"])
-            st["rot"][:, 9:] = st["bp"]
+            for phase, keys in (("A", ("go", "cam")), ("B", ("bp", "betas"))):
+                for k in keys:                                  # a fresh Adam per phase (:1734-1740, :1863-1869)
+                    mom[k][0].zero_(); mom[k][1].zero_()
+                step.zero_()
+                for _e in range(iterations):
+                    for v in order():
+                        self._run(c, (phase, v), lambda: self._view_step(c, phase, v))
+                    self._run(c, ("val", phase), lambda: self._validate(c, phase))
+                    if first_val is None:
+                        first_val = c["val"].clone()
+                for k in keys:                                  # the phase ends at its best epoch (:1846-1847, :1961-1962)
+                    st[k].copy_(best[k])
+                st["rot"][:, 9:] = st["bp"]
 
         go = final["go"].transpose(0, 1).reshape(P, V, 3, 3).contiguous()
         cam_out = final["cam"].transpose(0, 1).contiguous()
-        return {"body_pose": final["bp"].reshape(P, 23, 3, 3), "betas": final["betas"], "global_orient": go,
+        return {"body_pose": final["bp"].reshape(P, 23, 3, 3).clone(), "betas": final["betas"].clone(), "global_orient": go,
                 "cam": cam_out,
                 "translation": convert_weak_perspective_to_camera_translation_torch(
                     cam_out.reshape(P * V, 3), config.FOCAL_LENGTH, b.proj_wh).reshape(P, V, 3),
-                "best_loss": best_metric, "initial_loss": first_val,
-                "last": {"body_pose": st["bp"].reshape(P, 23, 3, 3), "betas": st["betas"],
-                         "global_orient": st["go"].transpose(0, 1).reshape(P, V, 3, 3), "cam": st["cam"].transpose(0, 1)}}
+                "best_loss": c["best_metric"].clone(), "initial_loss": first_val,
+                "last": {"body_pose": st["bp"].reshape(P, 23, 3, 3).clone(), "betas": st["betas"].clone(),
+                         "global_orient": st["go"].transpose(0, 1).reshape(P, V, 3, 3).clone(),
+                         "cam": st["cam"].transpose(0, 1).clone()}}

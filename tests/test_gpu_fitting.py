@@ -191,7 +191,10 @@ def _ref_multiview(model, bp0, betas0, go0, cam0, label, iters, lr, rounds, orde
             "last": {"go": go, "cam": cam, "bp": bp, "betas": betas}}
 
 
-def test_multi_view_fit_matches_reference_loop(setup):
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_multi_view_fit_matches_reference_loop(setup, use_graph):
+    """use_graph: every (phase, view) step and both validation passes run eagerly once, are captured on their second
+    use and replayed from then on -- all three paths inside one fit; a second fit on the cached graphs must agree."""
     from soccerplayershapepose_b200.fitting import MultiViewFitter
     model, smpl, dev = setup
     P, V, iters, rounds, lr = 4, 3, 3, 2, 2e-3
@@ -216,9 +219,16 @@ def test_multi_view_fit_matches_reference_loop(setup):
     rng = np.random.default_rng(0)
     orders = [rng.permutation(V).tolist() for _ in range(rounds * 2 * iters)]
     ref = _ref_multiview(model, bp0, betas0, go0, cam0, label, iters, lr, rounds, orders)
-    res = MultiViewFitter(smpl, lr=lr, rounds=rounds).fit(bp0.to(dev), betas0.to(dev), go0.to(dev), cam0.to(dev),
-                                                          label.to(dev), iterations=iters, view_orders=orders)
+    fitter = MultiViewFitter(smpl, lr=lr, rounds=rounds, use_cuda_graph=use_graph)
+    res = fitter.fit(bp0.to(dev), betas0.to(dev), go0.to(dev), cam0.to(dev), label.to(dev), iterations=iters,
+                     view_orders=orders)
     torch.cuda.synchronize()
+    if use_graph:                                           # replays only, from re-initialised state buffers
+        assert len(fitter._cache[(P, V, 10, False)]["graphs"]) == 2 * V + 2
+        again = fitter.fit(bp0.to(dev), betas0.to(dev), go0.to(dev), cam0.to(dev), label.to(dev), iterations=iters,
+                           view_orders=orders)
+        for k in ("body_pose", "betas", "global_orient", "cam", "best_loss"):
+            assert (again[k] - res[k]).abs().max().item() < 1e-5, k
     np.testing.assert_allclose(res["initial_loss"].cpu().double().numpy(), ref["first_val"].numpy(), rtol=2e-3)
     np.testing.assert_allclose(res["best_loss"].cpu().double().numpy(), ref["best_metric"].numpy(), rtol=5e-3)
     nsteps = rounds * iters * V
