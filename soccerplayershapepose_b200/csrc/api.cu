@@ -11,6 +11,11 @@
 
 namespace b200smpl {
 
+bool pdl_enabled() {
+  static const bool on = getenv("B200_PDL") == nullptr || atoi(getenv("B200_PDL")) != 0;
+  return on;
+}
+
 NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
 NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
@@ -325,7 +330,7 @@ int b200smpl_forward(const b200smpl_model* m, const b200smpl_forward_args* a, vo
     if (rc) return rc;
     if (a->vertices)
       if ((rc = launch_lbs_fwd(d, vpT, S, A_T, b0, nb, a->transl, a->vertices, m->num_sms, st))) return rc;
-    if ((rc = launch_joints_fwd(d, vpT, S, A_T, b0, nb, a->transl, a->joints, st))) return rc;
+    if ((rc = launch_joints_fwd(d, vpT, S, A_T, b0, nb, a->transl, a->joints, a->vertices != nullptr, st))) return rc;
   }
   if (a->joints2d)   // reprojection of all joints: utils/cam_utils.py:5-26
     if ((rc = b200smpl_orthographic_project(a->joints, a->cam, a->joints2d, B, d.njout, 0.f, stream))) return rc;
@@ -418,7 +423,7 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
                                m->num_sms, st)))
         return rc;
     if (have_j)
-      if ((rc = launch_joints_bwd(d, vpT, S, Sw, A_T, b0, nb, dJ, dvp_hi, dvp_lo, dA_part, dtr_part, st))) return rc;
+      if ((rc = launch_joints_bwd(d, vpT, S, Sw, A_T, b0, nb, dJ, dvp_hi, dvp_lo, dA_part, dtr_part, have_v, st))) return rc;
     if (a->mode == B200SMPL_MODE_FP32_SIMT)
       rc = launch_blend_bwd_simt(d, dvp_hi, dvp_lo, S, Sw, dfeat_part, row_begin, row_end, st);
     else

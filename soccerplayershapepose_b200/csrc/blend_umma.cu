@@ -407,6 +407,9 @@ umma_gemm2_kernel(const __grid_constant__ GemmOps ops, int split3, int nc8, int 
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // launched with the PDL attribute behind the kernels that write dvp: everything above overlapped their tail
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_trigger();
   // stage layout: [A_hi | B_hi | A_lo | B_lo]
   const int off_bhi = A_BYTES, off_alo = A_BYTES + B_BYTES, off_blo = 2 * A_BYTES + B_BYTES;
 
@@ -952,6 +955,9 @@ blend_fwd_bs2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // launched with the PDL attribute behind pose_fwd (which writes the feature rows): everything above overlapped it
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): own body tile once, then own half of every model-row tile pair =====
@@ -1218,7 +1224,7 @@ static int launch_blend_fwd_umma_bs2(const DevModel& m, int mode, const __nv_bfl
   if ((rc = make_map(&map_f, feat, m.fl.pitch, Sw, m.fl.pitch, WS_BN))) return rc;   // rows >= Sw read as zero
   constexpr int smem = (WS_MAX_SLABS + WS_STAGES) * BM * BK * 2 + 1024 + 256;
   auto kern = blend_fwd_bs2_kernel<0>;
-  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  B200_SMEM_ATTR_ONCE(kern, smem);
   const int mtiles = (row_end - row_begin) / BM;
   const int wtp_total = (mtiles + 1) / 2;
   const int ntiles_n = Sw / WS_BN;
@@ -1232,13 +1238,15 @@ static int launch_blend_fwd_umma_bs2(const DevModel& m, int mode, const __nv_bfl
   cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   LaunchTimer _timer("blend_fwd_umma", st);
   B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map_w, map_f, pslabs, (m.fl.k_cs + UMMA_K - 1) / UMMA_K,
                                    (NPOSE + UMMA_K - 1) / UMMA_K, use_lo, row_begin, mtiles, ntiles_n, work,
@@ -1361,7 +1369,7 @@ static int launch_bwd_bn_2cta(GemmOps& ops, const DevModel& m, int nseg, int row
   for (int s = 0; s < nseg; ++s)
     if ((rc = make_map(&ops.b[s], bsrc[s], row_end, nf_pad, m.n_pad, BN / 2))) return rc;
   auto kern = umma_gemm2_kernel<BN>;
-  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  B200_SMEM_ATTR_ONCE(kern, smem);
   const int slabs = slab_end - slab_begin;
   const int sps = (slabs + nsplit - 1) / nsplit;
   cudaLaunchConfig_t cfg;
@@ -1370,13 +1378,15 @@ static int launch_bwd_bn_2cta(GemmOps& ops, const DevModel& m, int nseg, int row
   cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   LaunchTimer _timer("blend_bwd_umma", st);
   B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ops, nseg == 3 ? 1 : 0, m.n_pad / 8, slab_begin, slab_end, sps, dfeat_part,
                                    nf_pad, split_stride));

@@ -5,7 +5,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200smpl.h"
@@ -154,6 +156,49 @@ struct LaunchTimer {
   NvtxRange nvtx_;
 };
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------
+// Consecutive kernels of the forward / backward chains are launched with the programmatic-stream-serialization
+// attribute: a dependent grid may become resident while its predecessor drains, runs its prologue (barrier init,
+// TMEM allocation, descriptor prefetch) and blocks in pdl_wait() until the predecessor grid has completed and
+// flushed.  pdl_trigger() in the predecessor marks the point after which dependents may be scheduled.
+// B200_PDL=0 disables the attribute (the device instructions are then no-ops).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// kernel<<<grid, block, smem, st>>>(args...) with the PDL attribute when `pdl` (and B200_PDL != 0)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+#endif
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when the kernel needs more than it has been granted on this
+// device so far (the size can depend on the model), instead of on every launch
+#define B200_SMEM_ATTR_ONCE(kern, bytes)                                                          \
+  do {                                                                                            \
+    static int _granted[64] = {};                                                                 \
+    int _dev = 0;                                                                                 \
+    B200_CUDA_TRY(cudaGetDevice(&_dev));                                                          \
+    if (_dev < 0 || _dev >= 64 || (int)(bytes) > _granted[_dev]) {                                \
+      B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      if (_dev >= 0 && _dev < 64) _granted[_dev] = (int)(bytes);                                  \
+    }                                                                                             \
+  } while (0)
+
 #define B200_CUDA_TRY(expr)                                                                       \
   do {                                                                                            \
     cudaError_t _e = (expr);                                                                      \
@@ -202,10 +247,10 @@ int launch_lbs_bwd(const DevModel& m, const float* vpT, int S, int Sw, const flo
                    float* dtr_acc, int num_sms, cudaStream_t st);
 
 int launch_joints_fwd(const DevModel& m, const float* vpB, int S, const float* A_blk, int b0, int nb,
-                      const float* transl, float* joints, cudaStream_t st);
+                      const float* transl, float* joints, bool after_lbs, cudaStream_t st);
 int launch_joints_bwd(const DevModel& m, const float* vpB, int S, int Sw, const float* A_blk, int b0, int nb,
                       const float* dJ, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_part, float* dtr_part,
-                      cudaStream_t st);
+                      bool after_lbs, cudaStream_t st);
 int launch_joint_grad_total(const float* joints, const float* cam, const float* gj, const float* g2d, float* dJ,
                             float* gcam, int B, int nj, cudaStream_t st);
 

@@ -92,6 +92,9 @@ joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
     }
     __syncwarp();
   }
+  // launched behind lbs_fwd with the PDL attribute and no wait up front (nothing read here is written by it): the
+  // grid must not complete before its predecessor has
+  pdl_wait();
 }
 
 // backward over virtual tiles.  dJ: total joint gradient (B, NJout, 3).
@@ -194,6 +197,7 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
   red_add(dtr_g + lane, sx);
   red_add(dtr_g + 32 + lane, sy);
   red_add(dtr_g + 64 + lane, sz);
+  pdl_wait();                 // as in the forward: complete only after lbs_bwd (the gradient GEMM behind needs both)
 }
 
 // total joint gradient when a 2D reprojection gradient is present:
@@ -231,16 +235,18 @@ joint_grad_total_kernel(const float* __restrict__ joints, const float* __restric
 static int joints_split(int ntv) { return std::max(1, (ntv + JW - 1) / JW); }
 static size_t joints_smem(int pitch) { return (size_t)(AG_WORDS + JW * 32 * pitch + 1) * 4 + 16; }
 
+// after_lbs: the previous kernel in the stream is the skinning kernel of the same slab -> PDL launch (overlaps its tail)
 int launch_joints_fwd(const DevModel& m, const float* vpB, int S, const float* A_blk, int b0, int nb,
-                      const float* transl, float* joints, cudaStream_t st) {
+                      const float* transl, float* joints, bool after_lbs, cudaStream_t st) {
   if (nb <= 0 || m.ntv == 0) return 0;
   const int groups = (nb + 31) / 32;
   const int pitch = m.vt_maxcols | 1;
   const size_t smem = joints_smem(pitch);
-  B200_CUDA_TRY(cudaFuncSetAttribute(joints_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B200_SMEM_ATTR_ONCE(joints_fwd_kernel, smem);
   LaunchTimer _timer("joints_fwd", st);
-  joints_fwd_kernel<<<dim3(groups, joints_split(m.ntv)), JT, smem, st>>>(m, reinterpret_cast<const float4*>(vpB), m.n_pad / 4,
-                                             reinterpret_cast<const float4*>(A_blk), b0, nb, pitch, transl, joints);
+  B200_CUDA_TRY(launch_k(joints_fwd_kernel, dim3(groups, joints_split(m.ntv)), dim3(JT), smem, st, after_lbs, m,
+                         reinterpret_cast<const float4*>(vpB), m.n_pad / 4, reinterpret_cast<const float4*>(A_blk), b0, nb, pitch,
+                         transl, joints));
   B200_LAUNCH_CHECK("joints_fwd");
   return 0;
 }
@@ -248,16 +254,16 @@ int launch_joints_fwd(const DevModel& m, const float* vpB, int S, const float* A
 // Sw: active slab width (multiple of 32); absent bodies get zero dvp rows.
 int launch_joints_bwd(const DevModel& m, const float* vpB, int S, int Sw, const float* A_blk, int b0, int nb,
                       const float* dJ, __nv_bfloat16* dvp_hi, __nv_bfloat16* dvp_lo, float* dA_acc, float* dtr_acc,
-                      cudaStream_t st) {
+                      bool after_lbs, cudaStream_t st) {
   if (m.ntv == 0) return 0;
   const int groups = Sw / 32;
   const int pitch = m.vt_maxcols | 1;
   const size_t smem = joints_smem(pitch);
-  B200_CUDA_TRY(cudaFuncSetAttribute(joints_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B200_SMEM_ATTR_ONCE(joints_bwd_kernel, smem);
   LaunchTimer _timer("joints_bwd", st);
-  joints_bwd_kernel<<<dim3(groups, joints_split(m.ntv)), JT, smem, st>>>(m, reinterpret_cast<const float4*>(vpB), m.n_pad / 4,
-                                             reinterpret_cast<const float4*>(A_blk), b0, nb, pitch, dJ, dvp_hi, dvp_lo,
-                                             dA_acc, dtr_acc);
+  B200_CUDA_TRY(launch_k(joints_bwd_kernel, dim3(groups, joints_split(m.ntv)), dim3(JT), smem, st, after_lbs, m,
+                         reinterpret_cast<const float4*>(vpB), m.n_pad / 4, reinterpret_cast<const float4*>(A_blk), b0, nb, pitch,
+                         dJ, dvp_hi, dvp_lo, dA_acc, dtr_acc));
   B200_LAUNCH_CHECK("joints_bwd");
   return 0;
 }

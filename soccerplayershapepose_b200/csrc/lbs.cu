@@ -326,6 +326,8 @@ lbs_fwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();                 // launched behind the blend GEMM with the PDL attribute: v_posed is complete from here on
+  if (threadIdx.x == 0) pdl_trigger();     // the joint kernel behind reads nothing this grid writes: it may fill SMs as CTAs exit
   uint32_t a_phase = 0, n_used = 0;                                // n_used: items this warp has pulled so far
   const CtaRange cta = make_cta_range(ngroups, nitems);
   for (int seg0 = cta.begin; seg0 < cta.end;) {
@@ -542,6 +544,7 @@ lbs_bwd_kernel(const float4* __restrict__ vpB, int nc4, const float4* __restrict
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (threadIdx.x == 0) pdl_trigger();     // the joint kernel behind touches disjoint dvp rows (dA by REDs): it may overlap the tail
   uint32_t a_phase = 0, n_used = 0;
   const size_t row_stride = (size_t)V * 3;
   const CtaRange cta = make_cta_range(ngroups, nitems);
@@ -666,11 +669,11 @@ int launch_lbs_fwd(const DevModel& m, const float* vpB, int S, const float* A_bl
   const int groups = (nb + 31) / 32;
   const int nitems = m.ntiles * (TILE_V / FWD_HV);
   const int vec_ok = ((m.V & 1) == 0 && (reinterpret_cast<uintptr_t>(verts) & 7) == 0) ? 1 : 0;
-  B200_CUDA_TRY(cudaFuncSetAttribute(lbs_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
+  B200_SMEM_ATTR_ONCE(lbs_fwd_kernel, FWD_SMEM);
   LaunchTimer _timer("lbs_fwd", st);
-  lbs_fwd_kernel<<<run_grid(groups, nitems, FWD_WARPS, num_sms), FWD_THREADS, FWD_SMEM, st>>>(
-      reinterpret_cast<const float4*>(vpB), m.n_pad / 4, reinterpret_cast<const float4*>(A_blk), b0, nb, groups, transl, verts,
-      m.V, nitems, vec_ok, m.vplan);
+  B200_CUDA_TRY(launch_k(lbs_fwd_kernel, dim3(run_grid(groups, nitems, FWD_WARPS, num_sms)), dim3(FWD_THREADS), FWD_SMEM, st, true,
+                         reinterpret_cast<const float4*>(vpB), m.n_pad / 4, reinterpret_cast<const float4*>(A_blk), b0, nb, groups,
+                         transl, verts, m.V, nitems, vec_ok, m.vplan));
   B200_LAUNCH_CHECK("lbs_fwd");
   return 0;
 }
@@ -683,7 +686,7 @@ int launch_lbs_bwd(const DevModel& m, const float* vpB, int S, int Sw, const flo
   const int groups = Sw / 32;
   const int nitems = m.ntiles * (TILE_V / BWD_HV);
   const int vec_ok = ((m.V & 1) == 0 && (reinterpret_cast<uintptr_t>(grad_verts) & 7) == 0) ? 1 : 0;
-  B200_CUDA_TRY(cudaFuncSetAttribute(lbs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+  B200_SMEM_ATTR_ONCE(lbs_bwd_kernel, BWD_SMEM);
   LaunchTimer _timer("lbs_bwd", st);
   lbs_bwd_kernel<<<run_grid(groups, nitems, BWD_WARPS, num_sms), BWD_THREADS, BWD_SMEM, st>>>(
       reinterpret_cast<const float4*>(vpB), m.n_pad / 4, reinterpret_cast<const float4*>(A_blk), b0, nb, groups, grad_verts, m.V,

@@ -403,6 +403,7 @@ pose_fwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __r
   const int nbeta = fl.nb;
   const size_t body0 = (size_t)b0 + (size_t)g * 32;
   (void)S;
+  if (tid == 0) pdl_trigger();          // the blend GEMM behind may set itself up; it waits for this grid's completion
   // ---------------- P1 ----------------
   {
     constexpr int PWc = AA ? NJ * 3 : NJ * 9;
@@ -617,6 +618,7 @@ pose_bwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __r
   const FeatLayout fl = m.fl;
   const int nbeta = fl.nb, nf = fl.nf_pad, NG = S / 32;
   const size_t body0 = (size_t)b0 + (size_t)g * 32;
+  pdl_wait();                           // launched behind the gradient GEMM with the PDL attribute
   // ---------------- P1: stage ----------------
   {
     // (a) straight copies, 16 bytes per cp.async: the group's transforms and dL/dA
@@ -873,11 +875,11 @@ int launch_pose_fwd(const DevModel& m, const float* betas, const float* pose, bo
   const int grid = Sw / 32;
   if ((pose_use_lb() & 1) && m.fl.nb * 32 <= LBF_THREADS) {
     if (axis_angle) {
-      B200_CUDA_TRY(cudaFuncSetAttribute(pose_fwd_lb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB_FWD_SMEM));
+      B200_SMEM_ATTR_ONCE(pose_fwd_lb_kernel<true>, LB_FWD_SMEM);
       LaunchTimer _timer("pose_fwd", st);
       pose_fwd_lb_kernel<true><<<grid, LBF_THREADS, LB_FWD_SMEM, st>>>(m, betas, pose, b0, nb, S, feat, featf, A_T, transl, joints);
     } else {
-      B200_CUDA_TRY(cudaFuncSetAttribute(pose_fwd_lb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB_FWD_SMEM));
+      B200_SMEM_ATTR_ONCE(pose_fwd_lb_kernel<false>, LB_FWD_SMEM);
       LaunchTimer _timer("pose_fwd", st);
       pose_fwd_lb_kernel<false><<<grid, LBF_THREADS, LB_FWD_SMEM, st>>>(m, betas, pose, b0, nb, S, feat, featf, A_T, transl, joints);
     }
@@ -906,15 +908,17 @@ int launch_pose_bwd(const DevModel& m, const float* betas, const float* pose, bo
   const int grid = (nb + 31) / 32;
   if ((pose_use_lb() & 2) && A_blk != nullptr && m.fl.nf_pad <= 224 && m.fl.nb * 32 <= LBB_THREADS) {
     if (axis_angle) {
-      B200_CUDA_TRY(cudaFuncSetAttribute(pose_bwd_lb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB_BWD_SMEM));
+      B200_SMEM_ATTR_ONCE(pose_bwd_lb_kernel<true>, LB_BWD_SMEM);
       LaunchTimer _timer("pose_bwd", st);
-      pose_bwd_lb_kernel<true><<<grid, LBB_THREADS, LB_BWD_SMEM, st>>>(m, betas, pose, b0, nb, S, A_blk, dA_part, n_dA_parts, dtr_part,
-                                                             dfeat_part, n_dfeat_parts, dJ, grad_betas, grad_pose, grad_transl);
+      B200_CUDA_TRY(launch_k(pose_bwd_lb_kernel<true>, dim3(grid), dim3(LBB_THREADS), LB_BWD_SMEM, st, true, m, betas, pose, b0, nb,
+                             S, A_blk, dA_part, n_dA_parts, dtr_part, dfeat_part, n_dfeat_parts, dJ, grad_betas, grad_pose,
+                             grad_transl));
     } else {
-      B200_CUDA_TRY(cudaFuncSetAttribute(pose_bwd_lb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LB_BWD_SMEM));
+      B200_SMEM_ATTR_ONCE(pose_bwd_lb_kernel<false>, LB_BWD_SMEM);
       LaunchTimer _timer("pose_bwd", st);
-      pose_bwd_lb_kernel<false><<<grid, LBB_THREADS, LB_BWD_SMEM, st>>>(m, betas, pose, b0, nb, S, A_blk, dA_part, n_dA_parts, dtr_part,
-                                                              dfeat_part, n_dfeat_parts, dJ, grad_betas, grad_pose, grad_transl);
+      B200_CUDA_TRY(launch_k(pose_bwd_lb_kernel<false>, dim3(grid), dim3(LBB_THREADS), LB_BWD_SMEM, st, true, m, betas, pose, b0, nb,
+                             S, A_blk, dA_part, n_dA_parts, dtr_part, dfeat_part, n_dfeat_parts, dJ, grad_betas, grad_pose,
+                             grad_transl));
     }
     B200_LAUNCH_CHECK("pose_bwd");
     return 0;
