@@ -1,13 +1,17 @@
 #!/usr/bin/env python
 """Turn one `ncu --set full` report of scripts/profile_step.py into the files committed under profiles/:
    <prefix>.txt (one summary line + stall mix per kernel), <prefix>_raw.csv (selected raw metrics per launch) and
-   r01_ncu_traffic.json (DRAM bytes per launch of each kernel, read by bench.py for roofline.traffic).
-   usage: ncu_to_profiles.py report.ncu-rep profiles/r01_ncu_step_b4096_fp32 [batch]"""
+   r02_ncu_traffic.json (DRAM bytes per launch of each kernel, read by bench.py for roofline.traffic; stamped with the
+   hash of the CUDA sources so that bench.py stops quoting it once the kernels change).
+   usage: ncu_to_profiles.py report.ncu-rep profiles/r02_ncu_step_b4096_fp32 [batch]"""
 import csv
 import json
 import os
 import subprocess
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import kernel_source_hash                                          # noqa: E402
 
 rep, prefix = sys.argv[1], sys.argv[2]
 batch = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
@@ -53,5 +57,6 @@ for r in rows[2:]:                                  # the last launch of every k
             break
 traffic["source"] = os.path.basename(prefix) + "_raw.csv (ncu --set full --clock-control none, B=%d fp32, dram__bytes_read.sum + dram__bytes_write.sum per launch)" % batch
 traffic["batch"] = batch
-json.dump(traffic, open(os.path.join(os.path.dirname(prefix), "r01_ncu_traffic.json"), "w"), indent=1)
+traffic["kernel_source_hash"] = kernel_source_hash()
+json.dump(traffic, open(os.path.join(os.path.dirname(prefix), "r02_ncu_traffic.json"), "w"), indent=1)
 print(json.dumps(traffic, indent=1))

@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200smpl.so")
+# B200SMPL_LIB: an alternative build of the same library (kernel-variant experiments); never a different implementation
+LIB_PATH = os.environ.get("B200SMPL_LIB") or os.path.join(HERE, "libb200smpl.so")
 
 MODE_FP32 = 0
 MODE_BF16 = 1
