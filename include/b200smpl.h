@@ -199,6 +199,17 @@ B200SMPL_API int b200smpl_perspective_project_backward(const float* points, cons
                                           float* grad_translation, int batch, int n, float focal_length,
                                           float img_wh, void* stream);
 
+/* the same with an explicit intrinsics matrix (the cam_K argument of utils/cam_utils.py:54-85): cam_K [B][3][3]
+ * (cam_K_batched != 0) or one [3][3] shared by the batch; out = rows 0 and 1 of K . (X'/z).  No gradient for cam_K. */
+B200SMPL_API int b200smpl_perspective_project_camk(const float* points, const float* rotation, const float* translation,
+                                                   const float* cam_K, int cam_K_batched, float* out, int batch, int n,
+                                                   void* stream);
+B200SMPL_API int b200smpl_perspective_project_camk_backward(const float* points, const float* rotation,
+                                                            const float* translation, const float* cam_K,
+                                                            int cam_K_batched, const float* grad_out, float* grad_points,
+                                                            float* grad_rotation, float* grad_translation, int batch,
+                                                            int n, void* stream);
+
 /*
  * Fused joints2D loss term (losses/multi_task_loss.py:97-113 on top of player_recon.py:1217-1221):
  *   j2d = undo_keypoint_normalisation(orthographic(joints, cam)[:, map], proj_wh)

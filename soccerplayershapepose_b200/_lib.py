@@ -102,6 +102,10 @@ SYMBOLS = {
                                              c_float, c_void_p]),
     "b200smpl_perspective_project_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                       c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
+    "b200smpl_perspective_project_camk": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                                                  c_void_p]),
+    "b200smpl_perspective_project_camk_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                                           c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b200smpl_joints2d_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200smpl_fit_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

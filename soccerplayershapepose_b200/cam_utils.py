@@ -28,12 +28,8 @@ def get_intrinsics_matrix(img_width, img_height, focal_length):
 
 
 def perspective_project_torch(points, rotation, translation, cam_K=None, focal_length=None, img_wh=None):
-    """X' = R X + t, divide by depth, apply K.  The fused kernel covers the (focal_length, img_wh)
-    form the reference calls (player_recon.py:685-688); an explicit cam_K must have that structure."""
+    """X' = R X + t, divide by depth, apply K (reference lines 54-85): either an explicit `cam_K` (bs,3,3) -- any
+    intrinsics matrix -- or the (focal_length, img_wh) form the reference calls (player_recon.py:685-688)."""
     if cam_K is not None:
-        K = cam_K[0] if cam_K.dim() == 3 else cam_K
-        if not (cam_K.dim() == 2 or bool((cam_K == cam_K[:1]).all())) or float(K[0, 1]) != 0.0 \
-                or float(K[0, 0]) != float(K[1, 1]) or float(K[0, 2]) != float(K[1, 2]):
-            raise NotImplementedError("perspective_project_torch: only K = [[f,0,c],[0,f,c],[0,0,1]] is fused")
-        focal_length, img_wh = float(K[0, 0]), 2.0 * float(K[0, 2])
+        return ops.perspective_project_camk(points, rotation, translation, cam_K.to(points.device, torch.float32))
     return ops.perspective_project(points, rotation, translation, focal_length, img_wh)

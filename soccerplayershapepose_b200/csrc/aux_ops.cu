@@ -161,9 +161,24 @@ __global__ void ortho_bwd_kernel(const float* __restrict__ pts, const float* __r
 }
 
 // ---- perspective ------------------------------------------------------------------------------
+// intrinsics rows 0 and 1 of the body: from cam_K ([B][3][3], k_stride = 9, or one shared [3][3], k_stride = 0) or
+// K = [[f,0,c],[0,f,c],[0,0,1]]
+__device__ __forceinline__ void load_intrinsics(float (&K)[6], const float* __restrict__ camK, int k_stride, int b, float f,
+                                                float c) {
+  if (camK != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) K[i] = camK[(size_t)b * k_stride + i];
+  } else {
+    K[0] = f; K[1] = 0.f; K[2] = c; K[3] = 0.f; K[4] = f; K[5] = c;
+  }
+}
+
 __global__ void persp_fwd_kernel(const float* __restrict__ pts, const float* __restrict__ rot,
-                                 const float* __restrict__ trans, float* __restrict__ out, int n, float f, float c) {
+                                 const float* __restrict__ trans, float* __restrict__ out, int n, float f, float c,
+                                 const float* __restrict__ camK, int k_stride) {
   const int b = blockIdx.x;
+  float K[6];
+  load_intrinsics(K, camK, k_stride, b, f, c);
   float R[9], t[3];
 #pragma unroll
   for (int i = 0; i < 9; ++i) R[i] = rot[b * 9 + i];
@@ -174,18 +189,21 @@ __global__ void persp_fwd_kernel(const float* __restrict__ pts, const float* __r
     const float x = R[0] * p[0] + R[1] * p[1] + R[2] * p[2] + t[0];
     const float y = R[3] * p[0] + R[4] * p[1] + R[5] * p[2] + t[1];
     const float z = R[6] * p[0] + R[7] * p[1] + R[8] * p[2] + t[2];
-    // projected = X'/z ; K . projected with K = [[f,0,c],[0,f,c],[0,0,1]]
-    out[((size_t)b * n + i) * 2] = f * (x / z) + c * (z / z);
-    out[((size_t)b * n + i) * 2 + 1] = f * (y / z) + c * (z / z);
+    // projected = X'/z ; rows 0 and 1 of K . projected (utils/cam_utils.py:79-85)
+    const float u = x / z, v = y / z, w = z / z;
+    out[((size_t)b * n + i) * 2] = K[0] * u + K[1] * v + K[2] * w;
+    out[((size_t)b * n + i) * 2 + 1] = K[3] * u + K[4] * v + K[5] * w;
   }
 }
 
 __global__ void persp_bwd_kernel(const float* __restrict__ pts, const float* __restrict__ rot,
                                  const float* __restrict__ trans, const float* __restrict__ gout,
                                  float* __restrict__ gpts, float* __restrict__ grot, float* __restrict__ gtrans, int n,
-                                 float f) {
+                                 float f, const float* __restrict__ camK, int k_stride) {
   __shared__ float sh[32];
   const int b = blockIdx.x;
+  float K[6];
+  load_intrinsics(K, camK, k_stride, b, f, 0.f);
   float R[9], t[3];
 #pragma unroll
   for (int i = 0; i < 9; ++i) R[i] = rot[b * 9 + i];
@@ -200,9 +218,10 @@ __global__ void persp_bwd_kernel(const float* __restrict__ pts, const float* __r
     const float x = R[0] * p[0] + R[1] * p[1] + R[2] * p[2] + t[0];
     const float y = R[3] * p[0] + R[4] * p[1] + R[5] * p[2] + t[1];
     const float z = R[6] * p[0] + R[7] * p[1] + R[8] * p[2] + t[2];
-    const float gu = gout[((size_t)b * n + i) * 2], gv = gout[((size_t)b * n + i) * 2 + 1];
+    const float go0 = gout[((size_t)b * n + i) * 2], go1 = gout[((size_t)b * n + i) * 2 + 1];
+    const float gu = K[0] * go0 + K[3] * go1, gv = K[1] * go0 + K[4] * go1;     // d / d (x/z), d / d (y/z)
     const float iz = 1.f / z;
-    const float g3[3] = {f * gu * iz, f * gv * iz, -f * (gu * x + gv * y) * iz * iz};
+    const float g3[3] = {gu * iz, gv * iz, -(gu * x + gv * y) * iz * iz};
     if (gpts != nullptr) {
       float* g = gpts + ((size_t)b * n + i) * 3;
 #pragma unroll
@@ -360,8 +379,33 @@ int b200smpl_perspective_project(const float* points, const float* rotation, con
   if (!points || !rotation || !translation || !out || batch < 1 || n < 1)
     return fail(B200SMPL_ERR_INVALID, "bad argument");
   persp_fwd_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(points, rotation, translation, out, n, focal_length,
-                                                           img_wh / 2.0f);
+                                                           img_wh / 2.0f, nullptr, 0);
   B200_LAUNCH_CHECK("persp_fwd");
+  return 0;
+}
+
+int b200smpl_perspective_project_camk(const float* points, const float* rotation, const float* translation,
+                                      const float* cam_K, int cam_K_batched, float* out, int batch, int n, void* stream) {
+  B200_NVTX("b200smpl_perspective_project_camk");
+  if (!points || !rotation || !translation || !cam_K || !out || batch < 1 || n < 1)
+    return fail(B200SMPL_ERR_INVALID, "bad argument");
+  persp_fwd_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(points, rotation, translation, out, n, 0.f, 0.f, cam_K,
+                                                           cam_K_batched ? 9 : 0);
+  B200_LAUNCH_CHECK("persp_fwd");
+  return 0;
+}
+
+int b200smpl_perspective_project_camk_backward(const float* points, const float* rotation, const float* translation,
+                                               const float* cam_K, int cam_K_batched, const float* grad_out,
+                                               float* grad_points, float* grad_rotation, float* grad_translation,
+                                               int batch, int n, void* stream) {
+  B200_NVTX("b200smpl_perspective_project_camk_backward");
+  if (!points || !rotation || !translation || !cam_K || !grad_out || batch < 1 || n < 1)
+    return fail(B200SMPL_ERR_INVALID, "bad argument");
+  persp_bwd_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(points, rotation, translation, grad_out, grad_points,
+                                                           grad_rotation, grad_translation, n, 0.f, cam_K,
+                                                           cam_K_batched ? 9 : 0);
+  B200_LAUNCH_CHECK("persp_bwd");
   return 0;
 }
 
@@ -374,7 +418,7 @@ int b200smpl_perspective_project_backward(const float* points, const float* rota
   if (!points || !rotation || !translation || !grad_out || batch < 1 || n < 1)
     return fail(B200SMPL_ERR_INVALID, "bad argument");
   persp_bwd_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(points, rotation, translation, grad_out, grad_points,
-                                                           grad_rotation, grad_translation, n, focal_length);
+                                                           grad_rotation, grad_translation, n, focal_length, nullptr, 0);
   B200_LAUNCH_CHECK("persp_bwd");
   return 0;
 }

@@ -210,6 +210,34 @@ def _to_np(x):
     return np.asarray(x)
 
 
+class _ChumpyStub:
+    """Stands in for `chumpy.ch.Ch` when chumpy is not installed: the official SMPL .pkl stores v_template,
+    shapedirs, posedirs, weights, J as chumpy arrays, and unpickling them only needs their state -- the value of
+    a plain `Ch` leaf is the ndarray in its `x` attribute, which is what `.r` returns."""
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {"x": state})
+
+    @property
+    def r(self):
+        if "x" not in self.__dict__:
+            raise ValueError("chumpy object without a stored value: install chumpy to load this file")
+        return np.asarray(self.__dict__["x"])
+
+
+class _TolerantUnpickler(pickle.Unpickler):
+    """pickle.load(f, encoding='latin1') as smplx does, except that classes of a missing `chumpy` package resolve to
+    `_ChumpyStub` instead of raising ModuleNotFoundError."""
+
+    def find_class(self, module, name):
+        try:
+            return super().find_class(module, name)
+        except (ImportError, AttributeError):
+            if module.split(".")[0] == "chumpy":
+                return _ChumpyStub
+            raise
+
+
 def load_smpl_file(path: str) -> Dict[str, np.ndarray]:
     """Load an official SMPL file (`.pkl` as read by smplx, latin1, or its `.npz` conversion).
 
@@ -221,7 +249,7 @@ def load_smpl_file(path: str) -> Dict[str, np.ndarray]:
         raw = dict(np.load(path, allow_pickle=True))
     else:
         with open(path, "rb") as f:
-            raw = pickle.load(f, encoding="latin1")
+            raw = _TolerantUnpickler(f, encoding="latin1").load()
     shapedirs = _to_np(raw["shapedirs"])[:, :, :NUM_BETAS]
     posedirs = _to_np(raw["posedirs"])
     if posedirs.ndim == 3:                       # (6890,3,207) -> (207, 20670)

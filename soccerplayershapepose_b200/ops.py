@@ -139,6 +139,41 @@ class _Persp(torch.autograd.Function):
         return gp, gr, gt, None, None
 
 
+class _PerspK(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pts, rot, trans, cam_K):
+        pts, rot, trans, cam_K = _req(pts, "points"), _req(rot, "rotation"), _req(trans, "translation"), _req(cam_K, "cam_K")
+        B, N = pts.shape[0], pts.shape[1]
+        batched = cam_K.dim() == 3
+        if tuple(cam_K.shape) not in ((3, 3), (B, 3, 3)):
+            raise ValueError("cam_K has shape {}, expected (3, 3) or ({}, 3, 3)".format(tuple(cam_K.shape), B))
+        out = torch.empty((B, N, 2), dtype=torch.float32, device=pts.device)
+        with torch.cuda.device(pts.device):
+            _lib.check(_lib.load().b200smpl_perspective_project_camk(
+                pts.data_ptr(), rot.data_ptr(), trans.data_ptr(), cam_K.data_ptr(), int(batched), out.data_ptr(), B, N,
+                _stream(pts)), "persp_camk")
+        ctx.save_for_backward(pts, rot, trans, cam_K)
+        ctx.batched = batched
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pts, rot, trans, cam_K = ctx.saved_tensors
+        g = g.contiguous()
+        B, N = pts.shape[0], pts.shape[1]
+        gp, gr, gt = torch.empty_like(pts), torch.empty_like(rot), torch.empty_like(trans)
+        with torch.cuda.device(pts.device):
+            _lib.check(_lib.load().b200smpl_perspective_project_camk_backward(
+                pts.data_ptr(), rot.data_ptr(), trans.data_ptr(), cam_K.data_ptr(), int(ctx.batched), g.data_ptr(),
+                gp.data_ptr(), gr.data_ptr(), gt.data_ptr(), B, N, _stream(pts)), "persp_camk_bwd")
+        return gp, gr, gt, None
+
+
+def perspective_project_camk(points, rotation, translation, cam_K) -> torch.Tensor:
+    """utils/cam_utils.py:54-85 with an explicit intrinsics matrix cam_K (B,3,3) or (3,3); cam_K gets no gradient."""
+    return _PerspK.apply(points, rotation, translation, cam_K)
+
+
 def perspective_project(points, rotation, translation, focal_length: float, img_wh: float) -> torch.Tensor:
     """utils/cam_utils.py:54-85 with the (focal_length, img_wh) intrinsics form used at
     player_recon.py:685-688."""

@@ -123,6 +123,38 @@ def main():
     G["loss2_out"] = total2.detach().numpy()
     G["loss2_log_vars"] = np.array([crit2.joints2D_log_var.item(), crit2.shape_params_log_var.item()], np.float32)
 
+    # --- round 2 additions (own generator: the arrays above stay bit-identical) --------------------------------
+    g2 = torch.Generator().manual_seed(20262)
+    # explicit intrinsics: batched, unequal focal lengths, skew, off-centre principal point, non-trivial third row
+    camK = torch.zeros(B, 3, 3)
+    camK[:, 0, 0] = 800 + 4200 * torch.rand(B, generator=g2)
+    camK[:, 1, 1] = 800 + 4200 * torch.rand(B, generator=g2)
+    camK[:, 0, 1] = 5 * torch.randn(B, generator=g2)
+    camK[:, 1, 0] = 0.5 * torch.randn(B, generator=g2)
+    camK[:, 0, 2] = 256 + 20 * torch.randn(B, generator=g2)
+    camK[:, 1, 2] = 256 + 20 * torch.randn(B, generator=g2)
+    camK[:, 2] = torch.tensor([0.01, -0.02, 1.1])
+    G["persp_camK"] = camK.numpy()
+    G["persp_camK_out"] = ref_cam.perspective_project_torch(pts, rot, trans, cam_K=camK).numpy()
+    # all five MSE terms of the multi-task loss (verts, joints2D with vis, joints3D, shape, pose), unequal weights
+    names = ["verts", "joints2D", "joints3D", "shape_params", "pose_params"]
+    w5 = {"verts": 2.0, "joints2D": 0.3, "joints3D": 1.5, "shape_params": 0.05, "pose_params": 0.7}
+    crit5 = RefLoss(losses_on=names, init_loss_weights=w5)
+    o5 = {"verts": torch.randn(B, 50, 3, generator=g2), "joints2D": torch.rand(B, 17, 2, generator=g2) * 256,
+          "joints3D": torch.randn(B, 17, 3, generator=g2), "shape_params": torch.randn(B, 10, generator=g2),
+          "pose_params_rot_matrices": torch.randn(B, 24, 3, 3, generator=g2)}
+    l5 = {k: v + 0.3 * torch.randn(v.shape, generator=g2) for k, v in o5.items()}
+    l5["joints2D"] = torch.rand(B, 17, 2, generator=g2) * 256
+    l5["vis"] = torch.rand(B, 17, generator=g2) > 0.25
+    total5, parts5 = crit5(l5, o5)
+    for k, v in o5.items():
+        G["loss5_pred_" + k] = v.numpy()
+    for k, v in l5.items():
+        G["loss5_label_" + k] = v.numpy()
+    G["loss5_out"] = total5.detach().numpy()
+    G["loss5_parts"] = np.array([parts5[k].item() for k in names], np.float32)
+    G["loss5_log_vars"] = np.array([getattr(crit5, k + "_log_var").item() for k in names], np.float32)
+
     G.update(literal_inputs())
     np.savez_compressed(OUT, **G)
     print("wrote", OUT, "with", len(G), "arrays")

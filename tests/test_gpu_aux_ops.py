@@ -144,3 +144,50 @@ def test_batch_rodrigues_matches_smplx_arithmetic(dev):
     # (B, 72) poses: same layout the reference reshapes from
     pose = torch.randn(4, 72, generator=g).to(dev)
     assert batch_rodrigues(pose.view(-1, 3)).view(4, 24, 3, 3).shape == (4, 24, 3, 3)
+
+
+def test_perspective_with_explicit_intrinsics_golden_and_grad(intree_golden, dev):
+    """General cam_K (utils/cam_utils.py:54-85 called with an intrinsics matrix): golden from the reference file,
+    gradients against the fp64 oracle; a shared (3,3) matrix equals the batched call."""
+    g = intree_golden
+    pts = torch.from_numpy(g["ortho_points"]).to(dev).requires_grad_(True)
+    rot = torch.from_numpy(g["persp_rot"]).to(dev).requires_grad_(True)
+    tr = torch.from_numpy(g["persp_trans"]).to(dev).requires_grad_(True)
+    K = torch.from_numpy(g["persp_camK"])
+    out = cam_utils.perspective_project_torch(pts, rot, tr, cam_K=K.to(dev))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["persp_camK_out"], rtol=2e-6, atol=1e-3)
+    w = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+    (out * w.to(dev)).sum().backward()
+    p64, r64, t64 = (torch.from_numpy(g[k]).double().requires_grad_(True)
+                     for k in ("ortho_points", "persp_rot", "persp_trans"))
+    (O.perspective_project(p64, r64, t64, cam_K=K.double()) * w.double()).sum().backward()
+    assert _rel(pts.grad.cpu().double(), p64.grad) < 1e-5
+    assert _rel(rot.grad.cpu().double(), r64.grad) < 1e-5
+    assert _rel(tr.grad.cpu().double(), t64.grad) < 1e-5
+    one = cam_utils.perspective_project_torch(pts.detach(), rot.detach(), tr.detach(), cam_K=K[0].to(dev))
+    rep = cam_utils.perspective_project_torch(pts.detach(), rot.detach(), tr.detach(), cam_K=K[:1].expand(K.shape[0], 3, 3).contiguous().to(dev))
+    assert torch.equal(one, rep)
+    with pytest.raises(ValueError):
+        ops.perspective_project_camk(pts, rot, tr, K[:2].to(dev))
+
+
+def test_fused_multitask_loss_against_the_reference_golden(intree_golden, dev):
+    """csrc/loss.cu directly against HomoscedasticUncertaintyWeightedMultiTaskLoss executed from the reference file
+    (tests/golden/make_golden_from_reference.py): the predicted pixels of the golden are fed as joints whose
+    orthographic projection with cam = [1, 0, 0] lands exactly there (pix = (x + 1) * 256)."""
+    g = intree_golden
+    B = g["loss5_pred_verts"].shape[0]
+    joints = torch.zeros(B, 34, 3)
+    joints[:, :17, :2] = torch.from_numpy(g["loss5_pred_joints2D"]) / 256.0 - 1.0
+    joints[:, 17:] = torch.from_numpy(g["loss5_pred_joints3D"])
+    cam = torch.tensor([1.0, 0.0, 0.0]).repeat(B, 1)
+    d = lambda k: torch.from_numpy(g[k]).to(dev)   # noqa: E731
+    loss, parts = ops.multitask_loss(
+        torch.from_numpy(g["loss5_log_vars"]).to(dev), verts=d("loss5_pred_verts"), verts_label=d("loss5_label_verts"),
+        joints=joints.to(dev), cam=cam.to(dev), map2d=torch.arange(17, dtype=torch.int32, device=dev),
+        label2d=d("loss5_label_joints2D"), vis=d("loss5_label_vis"), map3d=torch.arange(17, 34, dtype=torch.int32, device=dev),
+        label3d=d("loss5_label_joints3D"), shape=d("loss5_pred_shape_params"), shape_label=d("loss5_label_shape_params"),
+        pose=d("loss5_pred_pose_params_rot_matrices"), pose_label=d("loss5_label_pose_params_rot_matrices"),
+        proj_wh=512.0, norm_wh=256.0)
+    np.testing.assert_allclose(loss.item(), g["loss5_out"], rtol=2e-5)
+    np.testing.assert_allclose(parts.cpu().numpy(), g["loss5_parts"], rtol=2e-5)

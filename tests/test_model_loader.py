@@ -109,3 +109,38 @@ def test_file_constructed_module_computes_the_same(synthetic_model, tmp_path, mo
     ob = b(betas=betas, body_pose=pose[:, 3:], global_orient=pose[:, :3])
     assert torch.equal(oa.vertices, ob.vertices) and torch.equal(oa.joints, ob.joints)
     assert oa.joints.shape == (3, 90, 3)
+
+
+def test_official_pickle_loads_without_chumpy(synthetic_model, tmp_path, monkeypatch):
+    """The official file pickles its arrays as `chumpy.ch.Ch` objects.  With chumpy absent (as in this image) the
+    loader substitutes a stub that recovers the stored ndarray instead of failing in `pickle.load`."""
+    import sys
+    import types
+    assert "chumpy" not in sys.modules
+    mod, sub = types.ModuleType("chumpy"), types.ModuleType("chumpy.ch")
+
+    class Ch:                                   # what the writer's chumpy would have pickled: state dict with `x`
+        def __init__(self, x):
+            self.x = np.asarray(x)
+            self.dterms = ("x",)
+
+    Ch.__module__, Ch.__qualname__ = "chumpy.ch", "Ch"
+    sub.Ch, mod.ch = Ch, sub
+    monkeypatch.setitem(sys.modules, "chumpy", mod)
+    monkeypatch.setitem(sys.modules, "chumpy.ch", sub)
+    write_official_layout(synthetic_model, str(tmp_path))
+    path = os.path.join(str(tmp_path), "PlayerReconstruction", "additional", "smpl", "SMPL_NEUTRAL.pkl")
+    raw = pickle.load(open(path, "rb"), encoding="latin1")
+    raw["shapedirs"] = Ch(raw["shapedirs"].r)
+    raw["v_template"] = Ch(raw["v_template"])
+    raw["weights"] = Ch(raw["weights"])
+    with open(path, "wb") as f:
+        pickle.dump(raw, f, protocol=2)
+    monkeypatch.delitem(sys.modules, "chumpy")          # ... and the reader has no chumpy
+    monkeypatch.delitem(sys.modules, "chumpy.ch")
+    with pytest.raises(ModuleNotFoundError):
+        pickle.load(open(path, "rb"), encoding="latin1")
+    monkeypatch.chdir(tmp_path)
+    loaded = load_smpl_model(config.SMPL_MODEL_DIR)
+    for k in KEYS:
+        assert np.array_equal(np.asarray(loaded[k]), np.asarray(synthetic_model[k])), k

@@ -222,3 +222,31 @@ def test_vertices2joints_helper_matches_oracle():
     v = torch.randn(3, 50, 3, generator=g, dtype=torch.float64)
     J = torch.rand(7, 50, generator=g, dtype=torch.float64)
     assert torch.allclose(vertices2joints(J, v), O.vertices2joints(J, v), rtol=0, atol=1e-12)
+
+
+def test_perspective_projection_with_explicit_intrinsics(intree_golden):
+    """cam_K argument of utils/cam_utils.py:54-85: batched matrices with skew, unequal focal lengths, off-centre
+    principal point and a non-trivial third row (which the reference computes and drops)."""
+    g = intree_golden
+    out = O.perspective_project(torch.from_numpy(g["ortho_points"]), torch.from_numpy(g["persp_rot"]),
+                                torch.from_numpy(g["persp_trans"]), cam_K=torch.from_numpy(g["persp_camK"]))
+    np.testing.assert_allclose(out.numpy(), g["persp_camK_out"], rtol=0, atol=0)
+
+
+def test_five_term_multitask_loss_matches_the_reference_class(intree_golden):
+    """regressor.MultiTaskLoss (the eager restatement the fused kernels are tested against) reproduces
+    HomoscedasticUncertaintyWeightedMultiTaskLoss executed from the reference file: all five MSE terms, a vis mask,
+    unequal initial weights."""
+    from soccerplayershapepose_b200 import regressor
+    g = intree_golden
+    names = ["verts", "joints2D", "joints3D", "shape_params", "pose_params"]
+    w5 = {"verts": 2.0, "joints2D": 0.3, "joints3D": 1.5, "shape_params": 0.05, "pose_params": 0.7}
+    crit = regressor.MultiTaskLoss(names, w5)
+    np.testing.assert_allclose([getattr(crit, k + "_log_var").item() for k in names], g["loss5_log_vars"], rtol=1e-6)
+    keys = ("verts", "joints2D", "joints3D", "shape_params", "pose_params_rot_matrices")
+    outputs = {k: torch.from_numpy(g["loss5_pred_" + k]) for k in keys}
+    labels = {k: torch.from_numpy(g["loss5_label_" + k]) for k in keys}
+    labels["vis"] = torch.from_numpy(g["loss5_label_vis"])
+    total, parts = crit(labels, outputs)
+    np.testing.assert_allclose(total.item(), g["loss5_out"], rtol=1e-6)
+    np.testing.assert_allclose([parts[k].item() for k in names], g["loss5_parts"], rtol=1e-6)
