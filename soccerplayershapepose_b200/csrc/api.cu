@@ -323,14 +323,25 @@ int b200smpl_forward(const b200smpl_model* m, const b200smpl_forward_args* a, vo
     }
     if ((rc = launch_pose_fwd(d, a->betas, a->pose, aa, b0, nb, S, Sw, feat, featf, A_T, a->transl, a->joints, st)))
       return rc;
-    if (a->mode == B200SMPL_MODE_FP32_SIMT)
+    // forward-only calls that want vertices (no products kept for a backward): the blend GEMM skins in its epilogue
+    // and v_posed never touches HBM (188 us against 108 + 136 us at B = 4096).  When the products are kept the
+    // fused kernel would write v_posed AND the vertices (658 MB of pure writes, 242 us): no faster than the two
+    // kernels, so that case stays on them (B200_FUSED_FWD=2 forces the fused kernel, 0 disables it).
+    const bool fused = a->vertices != nullptr && a->mode != B200SMPL_MODE_FP32_SIMT && d.n_virt0 == d.ntiles * 96 &&
+                       (saved == nullptr ? fused_fwd_mode() >= 1 : fused_fwd_mode() >= 2);
+    if (fused) {
+      rc = launch_blend_lbs_fwd(d, fwd_gemm_mode(a->mode), feat, S, Sw, vpT, A_T, b0, nb, a->transl,
+                                a->vertices, saved != nullptr, m->num_sms, st);
+    } else if (a->mode == B200SMPL_MODE_FP32_SIMT) {
       rc = launch_blend_fwd_simt(d, featf, S, Sw, vpT, row_begin, d.n_pad, st);
-    else
+    } else {
       rc = launch_blend_fwd_umma(d, fwd_gemm_mode(a->mode), feat, S, Sw, vpT, row_begin, d.n_pad, st);
+    }
     if (rc) return rc;
-    if (a->vertices)
+    if (a->vertices && !fused)
       if ((rc = launch_lbs_fwd(d, vpT, S, A_T, b0, nb, a->transl, a->vertices, m->num_sms, st))) return rc;
-    if ((rc = launch_joints_fwd(d, vpT, S, A_T, b0, nb, a->transl, a->joints, a->vertices != nullptr, st))) return rc;
+    // behind the fused kernel the joint kernel reads rows its predecessor writes: plain stream order
+    if ((rc = launch_joints_fwd(d, vpT, S, A_T, b0, nb, a->transl, a->joints, a->vertices != nullptr && !fused, st))) return rc;
   }
   if (a->joints2d)   // reprojection of all joints: utils/cam_utils.py:5-26
     if ((rc = b200smpl_orthographic_project(a->joints, a->cam, a->joints2d, B, d.njout, 0.f, stream))) return rc;

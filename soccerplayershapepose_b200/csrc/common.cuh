@@ -239,6 +239,12 @@ int launch_blend_bwd_umma(const DevModel& m, int mode, const __nv_bfloat16* dvp_
                           int S, int Sw, float* dfeat_part, int nsplit, int row_begin, int row_end,
                           cudaStream_t st);
 int blend_bwd_umma_splits(const DevModel& m, int mode, int S, int num_sms);
+// blend GEMM with the skinning in its epilogue (fused_fwd.cu).  B200_FUSED_FWD: 0 never, 1 (default) forward-only
+// calls, 2 also when the forward products are kept
+int fused_fwd_mode();
+int launch_blend_lbs_fwd(const DevModel& m, int mode, const __nv_bfloat16* feat, int S, int Sw, float* vpT,
+                         const float* A_blk, int b0, int nb, const float* transl, float* verts, int write_vp,
+                         int num_sms, cudaStream_t st);
 
 int launch_lbs_fwd(const DevModel& m, const float* vpT, int S, const float* A_T, int b0, int nb,
                    const float* transl, float* verts, int num_sms, cudaStream_t st);

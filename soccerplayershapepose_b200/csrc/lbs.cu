@@ -17,23 +17,10 @@
 // instructions), every byte read or written exactly once with streaming accesses.  The backward writes
 // dv_posed as bf16 hi/lo 16-byte chunks [S/128][n/8][128][8] (512 contiguous bytes per warp store, the operand
 // layout of the gradient GEMM) and adds dA / dtransl into the slab accumulators with fp32 REDs.
-#include "skin_common.cuh"
+#include "lbs_tiles.cuh"
 
 namespace b200smpl {
 
-template <int HV>
-struct ItemShape {
-  static constexpr int ROWS = HV * 3;             // blend rows (floats per body) of one item
-  static constexpr int HROW = ROWS + 4;           // staging row pitch: 16-byte aligned, HROW / 4 odd -> a quarter-warp
-  static constexpr int TILE_WORDS = 32 * HROW;    // of 128-bit row accesses (lane = row) covers all banks
-  static constexpr int NCH4 = ROWS / 4;           // float4 chunks of v_posed per body
-  static constexpr int NCH8 = ROWS / 8;           // 8-row chunks of dvp per body
-  static constexpr int PAIRS = ROWS / 2;          // 8-byte pieces per body row
-  static constexpr int VP_WORDS = NCH4 * 128;     // dense v_posed block [NCH4][32] float4
-  static constexpr int PLAN_WORDS = (HV / 8) * 40;  // plan records of one item
-  static constexpr uint32_t TX_BYTES = (VP_WORDS + PLAN_WORDS) * 4;
-  static_assert((HROW / 4) % 2 == 1 && ROWS % 8 == 0 && HV % 8 == 0, "item shape");
-};
 
 // contiguous range of the flat (group, item) list owned by this CTA; it is walked one group at a time
 struct CtaRange {
@@ -55,60 +42,6 @@ __device__ __forceinline__ void issue_item(float4* vbuf, uint32_t* stash, uint64
   mbar_expect_tx(bar, SH::TX_BYTES);
   bulk_g2s(vbuf, vp_group + (size_t)t * (SH::NCH4 * 32), SH::VP_WORDS * 4, bar);
   bulk_g2s(stash, vplan + (size_t)t * SH::PLAN_WORDS, SH::PLAN_WORDS * 4, bar);
-}
-// plan words of vertices [4u, 4u+4) of the item inside the stash (records of 8 vertices: 8 float4 + 8 words)
-__device__ __forceinline__ const float4* plan_wts(const uint32_t* stash, int u) {
-  return reinterpret_cast<const float4*>(stash + (u >> 1) * 40 + (u & 1) * 16);
-}
-__device__ __forceinline__ const uint32_t* plan_meta(const uint32_t* stash, int u) {
-  return stash + (u >> 1) * 40 + 32 + (u & 1) * 4;
-}
-
-// ---- rows of the staging tile <-> row segments of a (B, V, 3) tensor, in 8-byte pieces.  The 32 * PAIRS pieces
-// are taken 32 per warp instruction: piece = k * 32 + lane -> row = piece / PAIRS, column pair = piece % PAIRS.
-// Since 96 = RPP * PAIRS the (row offset, column) of a lane repeats every 3 instructions, RPP rows further down,
-// so a lane keeps 3 global pointers and adds a constant stride.
-template <int HV>
-__device__ __forceinline__ void tile_to_global_full(const float* tile, float* dst0, size_t row_stride, int lane) {
-  using SH = ItemShape<HV>;
-  constexpr int RPP = 96 / SH::PAIRS, J = 32 / RPP;
-  float* gp[3];
-  const float* sp[3];
-#pragma unroll
-  for (int kk = 0; kk < 3; ++kk) {
-    const int piece = kk * 32 + lane, rr = piece / SH::PAIRS, c = (piece - rr * SH::PAIRS) * 2;
-    gp[kk] = dst0 + (size_t)rr * row_stride + c;
-    sp[kk] = tile + rr * SH::HROW + c;
-  }
-  const size_t step = (size_t)RPP * row_stride;
-#pragma unroll
-  for (int j = 0; j < J; ++j)
-#pragma unroll
-    for (int kk = 0; kk < 3; ++kk) {
-      st_stream2(gp[kk], *reinterpret_cast<const float2*>(sp[kk] + j * RPP * SH::HROW));
-      gp[kk] += step;
-    }
-}
-template <int HV>
-__device__ __forceinline__ void tile_to_global(const float* tile, float* dst0, size_t row_stride, int nrows,
-                                               int ncols, int lane) {
-  using SH = ItemShape<HV>;
-  if (nrows == 32 && ncols == SH::ROWS) {
-    tile_to_global_full<HV>(tile, dst0, row_stride, lane);
-    return;
-  }
-#pragma unroll 1
-  for (int k = 0; k < SH::PAIRS; ++k) {
-    const int piece = k * 32 + lane;
-    const int r = piece / SH::PAIRS;
-    const int c = (piece - r * SH::PAIRS) * 2;
-    const float2 v = *reinterpret_cast<const float2*>(tile + r * SH::HROW + c);
-    float* dst = dst0 + (size_t)r * row_stride + c;
-    if (r < nrows) {
-      if (c + 1 < ncols) st_stream2(dst, v);
-      else if (c < ncols) st_stream(dst, v.x);
-    }
-  }
 }
 // gradient rows: global -> registers (issued one item ahead) -> staging tile
 template <int HV>
@@ -204,13 +137,6 @@ __device__ __forceinline__ void issue_rows(float* tile, const float* __restrict_
     cp_async8_zfill(tile + r * SH::HROW + c, ok ? src0 + (size_t)r * row_stride + c : src0, bytes);
   }
 }
-// element-wise fallbacks (odd V or a base pointer that is not 8-byte aligned)
-template <int HV>
-__device__ __forceinline__ void tile_to_global_scalar(const float* tile, float* dst0, size_t row_stride, int nrows,
-                                                      int ncols, int lane) {
-  for (int r = 0; r < nrows; ++r)
-    for (int c = lane; c < ncols; c += 32) dst0[(size_t)r * row_stride + c] = tile[r * ItemShape<HV>::HROW + c];
-}
 template <int HV>
 __device__ __forceinline__ void global_to_tile_scalar(float* tile, const float* src0, size_t row_stride, int nrows,
                                                       int ncols, int lane) {
@@ -239,19 +165,6 @@ constexpr int FWD_THREADS = FWD_WARPS * 32;
 constexpr int FWD_WARP_WORDS = ItemShape<FWD_HV>::TILE_WORDS + 2 * (ItemShape<FWD_HV>::VP_WORDS + ItemShape<FWD_HV>::PLAN_WORDS) + 4;
 constexpr size_t FWD_SMEM = (size_t)(AG_WORDS + FWD_WARPS * FWD_WARP_WORDS) * 4 + 16;
 
-// The four cached transforms ("slots") as packed pairs: x/y rows of a slot are (r0c, r1c) pairs, the z rows of
-// two slots share pairs (lo = slots 0 / 2, hi = slots 1 / 3), so a vertex costs 25 FFMA2-class instructions
-// instead of 48 scalar FFMA.
-struct SlotXY {
-  f2 c0, c1, c2, t;          // (r00 r10) (r01 r11) (r02 r12) (t0 t1)
-};
-struct SlotZ2 {
-  f2 r20, r21, r22, t2;      // z row of two slots
-};
-struct Slots {
-  SlotXY s0, s1, s2, s3;
-  SlotZ2 zA, zB;
-};
 template <bool HI>
 __device__ __forceinline__ void load_slot2(SlotXY& s, SlotZ2& z, const float* A_s, int joint, int lane) {
   const float4* p = reinterpret_cast<const float4*>(A_s) + joint * 96 + lane;

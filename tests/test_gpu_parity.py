@@ -476,11 +476,28 @@ def test_no_write_outside_caller_buffers(engine, dev, monkeypatch, B):
         assert bool((raw[hi:] == 0xA5).all()), "write above a caller buffer"
 
 
-@pytest.mark.parametrize("env", [{"B200_POSE_LB": "0"}, {"B200_FWD_2CTA": "1"}, {"B200_FWD_2CTA": "0", "B200_BWD_2CTA": "0"}])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("B", [3, 130, 700])
+def test_fused_forward_equals_two_kernel_forward(engine, dev, mode, B):
+    """Forward-only calls run the blend GEMM with the skinning in its epilogue (csrc/fused_fwd.cu); calls that keep the
+    forward products run blend GEMM + skinning kernel.  Same MMAs in the same K order, same skinning arithmetic: the
+    vertices and joints must agree bit for bit (ragged batches and a batch wider than one CTA pair included)."""
+    betas, pose, trans, _ = make_inputs(B, 900 + B)
+    rot = rotmats_of(pose)
+    b, r, t = betas.to(dev), rot.to(dev), trans.to(dev)
+    v0, j0, _ = engine.forward(b, r, t, None, mode=_lib.MODES[mode])[:3]                  # fused
+    v1, j1, _, _ = engine.forward(b, r, t, None, mode=_lib.MODES[mode], save=True)         # two kernels
+    torch.cuda.synchronize()
+    assert torch.equal(v0, v1) and torch.equal(j0, j1)
+
+
+@pytest.mark.parametrize("env", [{"B200_POSE_LB": "0"}, {"B200_FWD_2CTA": "1"}, {"B200_FWD_2CTA": "0", "B200_BWD_2CTA": "0"},
+                                 {"B200_FUSED_FWD": "0"}, {"B200_FUSED_FWD": "2"}])
 def test_comparison_kernels_stay_correct(env):
     """The kernels kept for comparison behind environment switches (lane = joint pose kernels, row-stationary
-    CTA-pair and single-CTA GEMMs) are selected once per process: run the forward / backward parity tests in a
-    child process with the switch set."""
+    CTA-pair and single-CTA GEMMs, the fused forward switched off / forced on for calls that keep the forward
+    products) are selected once per process: run the forward / backward parity tests in a child process with the
+    switch set."""
     import os
     import subprocess
     import sys
