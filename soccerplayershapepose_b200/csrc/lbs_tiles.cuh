@@ -54,48 +54,12 @@ __device__ __forceinline__ void tile_to_global_full(const float* tile, float* ds
       gp[kk] += step;
     }
 }
-// The same flush with every store address in its own register pair (batches of NB stores): a store holds its
-// address registers until the memory pipeline has accepted it, so the pointer increment of the loop above waits for
-// the store in front of it and the stores of one pointer leave one acceptance latency apart (~1500 cycles per
-// 12-store flush measured in the fused forward kernel); independent addresses let them queue back to back.
-template <int HV, int NB>
-__device__ __forceinline__ void tile_to_global_full_batched(const float* tile, float* dst0, size_t row_stride, int lane) {
-  using SH = ItemShape<HV>;
-  constexpr int RPP = 96 / SH::PAIRS, J = 32 / RPP, N = 3 * J;
-  static_assert(N % NB == 0, "batch size");
-  uint32_t off[3];
-  const float* sp[3];
-#pragma unroll
-  for (int kk = 0; kk < 3; ++kk) {
-    const int piece = kk * 32 + lane, rr = piece / SH::PAIRS, c = (piece - rr * SH::PAIRS) * 2;
-    off[kk] = (uint32_t)rr * (uint32_t)row_stride + (uint32_t)c;
-    sp[kk] = tile + rr * SH::HROW + c;
-  }
-  const uint32_t step = (uint32_t)RPP * (uint32_t)row_stride;
-#pragma unroll
-  for (int b0 = 0; b0 < N; b0 += NB) {
-    float2 val[NB];
-    float* ptr[NB];
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-      const int j = (b0 + i) / 3, kk = (b0 + i) % 3;
-      val[i] = *reinterpret_cast<const float2*>(sp[kk] + j * RPP * SH::HROW);
-      ptr[i] = dst0 + (size_t)(off[kk] + (uint32_t)j * step);
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) st_stream2(ptr[i], val[i]);
-  }
-}
 template <int HV>
 __device__ __forceinline__ void tile_to_global(const float* tile, float* dst0, size_t row_stride, int nrows,
                                                int ncols, int lane) {
   using SH = ItemShape<HV>;
   if (nrows == 32 && ncols == SH::ROWS) {
-#ifdef B200_FLUSH_BATCH
-    tile_to_global_full_batched<HV, B200_FLUSH_BATCH>(tile, dst0, row_stride, lane);
-#else
     tile_to_global_full<HV>(tile, dst0, row_stride, lane);
-#endif
     return;
   }
 #pragma unroll 1
