@@ -100,7 +100,12 @@ static Plan make_plan(const b200smpl_model* m, int batch, int mode, int slab_bod
     p.off_dA = take((size_t)(NJ * AELEMS + 3) * S_ * 4);
     p.off_dtr = p.off_dA + (size_t)NJ * AELEMS * S_ * 4;
     p.off_dJtot = take((size_t)std::max(batch, 1) * d.njout * 3 * 4);
-    p.off_dfeat = take((size_t)p.k_splits * S_ * d.fl.nf_pad * 4);
+    // split-K partials of the gradient GEMM; the fused backward (fused_bwd.cu) writes one partial per piece of a body
+    // pair's item range and the virtual (joint) rows keep their own GEMM behind it
+    int parts = p.k_splits;
+    if (bmode != B200SMPL_MODE_FP32_SIMT && d.fl.nf_pad == 224)
+      parts = std::max(parts, std::max(0, fused_bwd_parts(d, p.S, m->num_sms)) + p.k_splits);
+    p.off_dfeat = take((size_t)parts * S_ * d.fl.nf_pad * 4);
   }
   p.total = off + 1024;   // slack for aligning the caller's base pointer
   return p;
@@ -210,6 +215,8 @@ int b200smpl_model_create(const b200smpl_model_desc* desc, int device, b200smpl_
   UP(Wf, h.Wf);
   UP(Wb_hi, h.Wb_hi);
   UP(Wb_lo, h.Wb_lo);
+  UP(Wbi_hi, h.Wbi_hi);
+  UP(Wbi_lo, h.Wbi_lo);
   UP(W32, h.W32);
   UP(vmeta, h.vmeta);
   UP(vwts, h.vwts);
@@ -429,18 +436,40 @@ int b200smpl_backward(const b200smpl_model* m, const b200smpl_backward_args* a, 
         if (dvp_lo) B200_CUDA_TRY(cudaMemset2DAsync(dvp_lo + c0 * 1024, pitch, 0, width, (size_t)Sw / 128, st));
       }
     }
-    if (have_v)
-      if ((rc = launch_lbs_bwd(d, vpT, S, Sw, A_T, b0, nb, a->grad_vertices, dvp_hi, dvp_lo, dA_part, dtr_part,
-                               m->num_sms, st)))
+    int n_parts = k_splits;
+    if (have_v && fused_bwd_usable(d, a->mode, a->grad_vertices)) {
+      // vertex rows: skinning backward + gradient GEMM in one kernel (dv_posed stays in tensor memory); the virtual
+      // (joint) rows go through joints_bwd and their own small GEMM into the partials behind
+      const int nfp = fused_bwd_parts(d, Sw, m->num_sms);
+      if (nfp < 0) return fail(B200SMPL_ERR_INVALID, "slab too wide for the fused backward work list");
+      B200_CUDA_TRY(cudaMemsetAsync(dfeat_part, 0, (size_t)nfp * S * d.fl.nf_pad * 4, st));
+      if ((rc = launch_lbs_bwd_gemm(d, bmode, vpT, S, Sw, A_T, b0, nb, a->grad_vertices, dA_part, dtr_part, dfeat_part,
+                                    m->num_sms, st)))
         return rc;
-    if (have_j)
-      if ((rc = launch_joints_bwd(d, vpT, S, Sw, A_T, b0, nb, dJ, dvp_hi, dvp_lo, dA_part, dtr_part, have_v, st))) return rc;
-    if (a->mode == B200SMPL_MODE_FP32_SIMT)
-      rc = launch_blend_bwd_simt(d, dvp_hi, dvp_lo, S, Sw, dfeat_part, row_begin, row_end, st);
-    else
-      rc = launch_blend_bwd_umma(d, bmode, dvp_hi, dvp_lo, S, Sw, dfeat_part, k_splits, row_begin, row_end, st);
-    if (rc) return rc;
-    if ((rc = launch_pose_bwd(d, a->betas, a->pose, aa, b0, nb, S, A_T, dA_part, 1, dtr_part, dfeat_part, k_splits,
+      n_parts = nfp;
+      if (have_j) {
+        if ((rc = launch_joints_bwd(d, vpT, S, Sw, A_T, b0, nb, dJ, dvp_hi, dvp_lo, dA_part, dtr_part, false, st))) return rc;
+        const int vslabs = (row_end + 63) / 64 - d.n_virt0 / 64;
+        const int ksv = std::max(1, std::min(p.k_splits, vslabs / 8));
+        if ((rc = launch_blend_bwd_umma(d, bmode, dvp_hi, dvp_lo, S, Sw, dfeat_part + (size_t)nfp * S * d.fl.nf_pad, ksv,
+                                        d.n_virt0, row_end, st)))
+          return rc;
+        n_parts += ksv;
+      }
+    } else {
+      if (have_v)
+        if ((rc = launch_lbs_bwd(d, vpT, S, Sw, A_T, b0, nb, a->grad_vertices, dvp_hi, dvp_lo, dA_part, dtr_part,
+                                 m->num_sms, st)))
+          return rc;
+      if (have_j)
+        if ((rc = launch_joints_bwd(d, vpT, S, Sw, A_T, b0, nb, dJ, dvp_hi, dvp_lo, dA_part, dtr_part, have_v, st))) return rc;
+      if (a->mode == B200SMPL_MODE_FP32_SIMT)
+        rc = launch_blend_bwd_simt(d, dvp_hi, dvp_lo, S, Sw, dfeat_part, row_begin, row_end, st);
+      else
+        rc = launch_blend_bwd_umma(d, bmode, dvp_hi, dvp_lo, S, Sw, dfeat_part, k_splits, row_begin, row_end, st);
+      if (rc) return rc;
+    }
+    if ((rc = launch_pose_bwd(d, a->betas, a->pose, aa, b0, nb, S, A_T, dA_part, 1, dtr_part, dfeat_part, n_parts,
                               have_j ? dJ : nullptr, a->grad_betas, a->grad_pose, a->grad_transl, st)))
       return rc;
   }

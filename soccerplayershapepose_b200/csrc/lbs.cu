@@ -95,48 +95,6 @@ __device__ __forceinline__ void rows_store(float* tile, const RowRegs<HV>& R, in
     for (int j = 0; j < J; ++j) *reinterpret_cast<float2*>(sp + j * RPP * SH::HROW) = R.v[j * 3 + kk];
   }
 }
-// gradient rows: global -> staging tile with 8-byte cp.async (fully asynchronous, no registers held)
-__device__ __forceinline__ void cp_async8_zfill(void* dst_smem, const void* src, int src_bytes) {
-  asm volatile("cp.async.ca.shared.global.L2::256B [%0], [%1], 8, %2;" ::"r"(smem_addr(dst_smem)), "l"(src), "r"(src_bytes)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-template <int HV>
-__device__ __forceinline__ void issue_rows(float* tile, const float* __restrict__ src0, size_t row_stride, int nrows,
-                                           int ncols, int lane) {
-  using SH = ItemShape<HV>;
-  constexpr int RPP = 96 / SH::PAIRS, J = 32 / RPP;
-  if (nrows == 32 && ncols == SH::ROWS) {
-    const float* gp[3];
-    float* sp[3];
-#pragma unroll
-    for (int kk = 0; kk < 3; ++kk) {
-      const int piece = kk * 32 + lane, rr = piece / SH::PAIRS, c = (piece - rr * SH::PAIRS) * 2;
-      gp[kk] = src0 + (size_t)rr * row_stride + c;
-      sp[kk] = tile + rr * SH::HROW + c;
-    }
-    const size_t step = (size_t)RPP * row_stride;
-#pragma unroll
-    for (int j = 0; j < J; ++j)
-#pragma unroll
-      for (int kk = 0; kk < 3; ++kk) {
-        cp_async8_zfill(sp[kk] + j * RPP * SH::HROW, gp[kk], 8);
-        gp[kk] += step;
-      }
-    return;
-  }
-#pragma unroll 1
-  for (int k = 0; k < SH::PAIRS; ++k) {
-    const int piece = k * 32 + lane;
-    const int r = piece / SH::PAIRS;
-    const int c = (piece - r * SH::PAIRS) * 2;
-    const bool ok = r < nrows && c < ncols;
-    const int bytes = ok ? (c + 1 < ncols ? 8 : 4) : 0;
-    cp_async8_zfill(tile + r * SH::HROW + c, ok ? src0 + (size_t)r * row_stride + c : src0, bytes);
-  }
-}
 template <int HV>
 __device__ __forceinline__ void global_to_tile_scalar(float* tile, const float* src0, size_t row_stride, int nrows,
                                                       int ncols, int lane) {
@@ -330,27 +288,6 @@ constexpr int BWD_NTILE = B200_BWD_ASYNC_ROWS ? 2 : 1;
 constexpr int BWD_WARP_WORDS = BWD_NTILE * ItemShape<BWD_HV>::TILE_WORDS + 2 * (ItemShape<BWD_HV>::VP_WORDS + ItemShape<BWD_HV>::PLAN_WORDS) + 4;
 constexpr size_t BWD_SMEM = (size_t)(AG_WORDS + BWD_WARPS * BWD_WARP_WORDS) * 4 + 16;
 
-// Slot pairs (lo = slots 0 / 2, hi = slots 1 / 3): rotation entries and gradient accumulators as packed pairs, so
-// the per-vertex arithmetic is 54 FFMA2-class instructions instead of 111 scalar ones.
-struct SlotPair {
-  f2 R[9];                   // R[r * 3 + c]
-  f2 D[AELEMS];              // dL/dA accumulators, D[r * 4 + c]
-};
-struct BwdState {
-  SlotPair A, B;
-  uint32_t prev;             // plan word of the previous vertex (joint ids of the slots)
-  float sx, sy, sz;
-};
-// close one slot: its accumulator halves -> fp32 RED into the group's dA rows [joint * 12 + e][32]; clear them
-template <bool HI>
-__device__ __forceinline__ void flush_half(SlotPair& P, float* dA_g, int joint, int lane) {
-  float* p = dA_g + (size_t)joint * AELEMS * 32 + lane;
-#pragma unroll
-  for (int e = 0; e < AELEMS; ++e) {
-    red_add(p + e * 32, get_half<HI>(P.D[e]));
-    P.D[e] = set_half<HI>(P.D[e], 0.f);
-  }
-}
 template <bool HI>
 __device__ __forceinline__ void load_rot_half(SlotPair& P, const float* A_s, int joint, int lane) {
   const float4* p = reinterpret_cast<const float4*>(A_s) + joint * 96 + lane;
@@ -419,18 +356,6 @@ __device__ __forceinline__ void skin_bwd4(BwdState& s, const float* A_s, float* 
 #pragma unroll
   for (int i = 0; i < 3; ++i)
     *reinterpret_cast<float4*>(row_io + i * 4) = make_float4(G[i * 4], G[i * 4 + 1], G[i * 4 + 2], G[i * 4 + 3]);
-}
-
-// close the accumulators of the current group: 4 slots -> dA, translation sums -> dtransl
-__device__ __forceinline__ void bwd_close_group(BwdState& s, float* dA_g, float* dtr_g, int lane) {
-  flush_half<false>(s.A, dA_g, s.prev & 31, lane);
-  flush_half<true>(s.A, dA_g, (s.prev >> 5) & 31, lane);
-  flush_half<false>(s.B, dA_g, (s.prev >> 10) & 31, lane);
-  flush_half<true>(s.B, dA_g, (s.prev >> 15) & 31, lane);
-  red_add(dtr_g + lane, s.sx);
-  red_add(dtr_g + 32 + lane, s.sy);
-  red_add(dtr_g + 64 + lane, s.sz);
-  s.sx = s.sy = s.sz = 0.f;
 }
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)

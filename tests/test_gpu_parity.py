@@ -467,6 +467,7 @@ def test_no_write_outside_caller_buffers(engine, dev, monkeypatch, B):
         engine.backward(betas, pose_aa, trans, cam, out[1], dV, dJ, dJ2, axis_angle=True, mode=m, saved=out[3])
         engine.backward(betas, pose_aa, trans, cam, out[1], dV, dJ, dJ2, axis_angle=True, mode=m)
         engine.forward(betas, pose_aa, None, None, axis_angle=True, mode=m, want_vertices=False)
+        engine.forward(betas, pose_aa, trans, cam, axis_angle=True, mode=m)      # forward-only: the fused kernel
     torch.cuda.synchronize(dev)
     monkeypatch.setattr(torch, "empty", real_empty)
     engine._ws.clear()
@@ -492,11 +493,11 @@ def test_fused_forward_equals_two_kernel_forward(engine, dev, mode, B):
 
 
 @pytest.mark.parametrize("env", [{"B200_POSE_LB": "0"}, {"B200_FWD_2CTA": "1"}, {"B200_FWD_2CTA": "0", "B200_BWD_2CTA": "0"},
-                                 {"B200_FUSED_FWD": "0"}, {"B200_FUSED_FWD": "2"}])
+                                 {"B200_FUSED_FWD": "0"}, {"B200_FUSED_FWD": "2"}, {"B200_FUSED_BWD": "1"}])
 def test_comparison_kernels_stay_correct(env):
     """The kernels kept for comparison behind environment switches (lane = joint pose kernels, row-stationary
     CTA-pair and single-CTA GEMMs, the fused forward switched off / forced on for calls that keep the forward
-    products) are selected once per process: run the forward / backward parity tests in a child process with the
+    products, the opt-in fused skinning-backward + gradient GEMM) are selected once per process: run the forward / backward parity tests in a child process with the
     switch set."""
     import os
     import subprocess
@@ -504,6 +505,7 @@ def test_comparison_kernels_stay_correct(env):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     child_env = dict(os.environ, **env)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
-                        "-k", "test_backward_full or test_forward_rotmat_surface or test_forward_axis_angle"],
+                        "-k", "test_backward_full or test_forward_rotmat_surface or test_forward_axis_angle or "
+                              "test_backward_partial_gradients or test_backward_full_size_vs_oracle"],
                        cwd=root, env=child_env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
