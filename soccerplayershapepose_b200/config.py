@@ -3,7 +3,7 @@
 Only what the hot path needs (SURVEY.md section 2, row "config.py (joint-map part)"): the
 default data locations used by `load_smpl_model`, the two camera constants, and the integer
 joint-index tables.  The index tables are pure integer data and must stay bit-exact with the
-reference (`config.py:29-38`); `tests/test_index_tables.py` checks them against golden
+reference (`config.py:29-38`); `tests/test_oracle.py::test_index_tables_bit_exact` checks them against golden
 vectors generated from the reference file itself.
 """
 import os
