@@ -471,6 +471,34 @@ def main():
             extras["sustained"] = {"seconds": sus_ms / 1e3, "steps": n_sus, "ms_per_step": sus_ms / n_sus,
                                    "value": B * n_sus / (sus_ms / 1e3), "unit": UNIT, "clocks": samp.stop()}
 
+        # ---- forward only on the device (no products kept for a backward: the fused blend + skinning kernel) ----
+        def fwd_device():
+            eng.forward(betas, rot, trans, None, mode=mode, slab=args.slab)
+        for _ in range(3):
+            fwd_device()
+        torch.cuda.synchronize(dev)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            fwd_device()
+        f1.record()
+        torch.cuda.synchronize(dev)
+        fwd_ms = f0.elapsed_time(f1) / args.steps
+        lib.b200smpl_timing_enable(1)
+        for _ in range(args.steps):
+            fwd_device()
+        torch.cuda.synchronize(dev)
+        lib.b200smpl_timing_enable(0)
+        fkt = timing_report(lib)
+        fwd_bytes = 82680 + 90 * 12 + (10 + 216 + 3) * 4          # vertices + joints out, inputs in: the fused lower bound
+        extras["forward_only_device"] = {
+            "ms_per_step": fwd_ms, "value": B / (fwd_ms / 1e3), "unit": "meshes/s (forward only)",
+            "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(fkt.items())},
+            "roofline": {"bound": "hbm", "achieved": B * fwd_bytes / (fwd_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": B * fwd_bytes / (fwd_ms / 1e3) / 1e9 / peak, "bytes_per_mesh": fwd_bytes,
+                         "note": "algorithmic bytes of the fully fused forward (SURVEY.md section 8d); v_posed stays on "
+                                 "chip (csrc/fused_fwd.cu), joints still read their virtual rows from HBM"}}
+
         # ---- small batches (the reference's own regime: SMPL(batch_size=1), player_recon.py:147) ----
         def timed(fn, n=50):
             for _ in range(5):
