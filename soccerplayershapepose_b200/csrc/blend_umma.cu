@@ -316,184 +316,15 @@ umma_gemm2_kernel(const __grid_constant__ GemmOps ops, int split3, int nc8, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Forward blend GEMM, W-stationary.  A CTA keeps its 128-row slice of the model operand (all K: 9 x 16 KB)
-// resident in shared memory and streams only the feature tiles of its share of the bodies through a
-// 5-stage ring (the stream is latency-bound: bytes in flight decide the rate), accumulating in two
-// alternating TMEM buffers so the epilogue of body tile i overlaps the MMAs of tile i+1.  K schedule per
-// body tile (FeatLayout): slab 0 (constants + shape) against model slab 0; each pf_hi slab j against
-// P_hi slab j and (fp32 mode) P_lo slab j; each pf_lo slab j against P_hi slab j.  M = 128 bodies (A operand = streamed features), N = 128 model rows
-// (B operand = resident slice): the epilogue thread owns one body and writes float4s of the group-blocked vpB.
-// grid: (row tiles, body chunks); CTA = 6 warps (TMA, MMA, 4 epilogue).
+// Forward blend GEMMs.  K schedule per body tile (FeatLayout): slab 0 (constants + shape) against model slab 0; each
+// pf_hi slab j against P_hi slab j and (fp32 mode) P_lo slab j; each pf_lo slab j against P_hi slab j.  M = bodies
+// (A operand = features), N = model rows: the epilogue thread owns one body and writes float4s of the group-blocked
+// vpB.  (The single-CTA kernel these grew out of -- one resident 128-row model slice per CTA, bound by the shared-memory
+// operand reads of an N = 128 SS-mode MMA at 175 us -- is in the history: commit ee3a35b and before.)
 // ---------------------------------------------------------------------------------------------
 constexpr int WS_STAGES = 5;
-constexpr int WS_MAX_SLABS = 9;        // resident model slabs: constants+shape, 4 x P_hi, 4 x P_lo
+constexpr int WS_MAX_SLABS = 9;        // resident slabs: constants+shape, 4 x hi, 4 x lo
 constexpr int WS_BN = 128;
-#ifndef B200_WS_CLUSTER
-#define B200_WS_CLUSTER 1
-#endif
-constexpr int WS_CLUSTER = B200_WS_CLUSTER;    // CTAs (different model-row slices) that share one multicast feature stream
-
-// CL CTAs of a cluster own CL consecutive 128-row slices of the model operand and walk the same body tiles in
-// lockstep: every 16 KB feature tile is fetched from L2 once per cluster -- CTA r loads rows [r*128/CL, ...) of it
-// and multicasts them into the same shared-memory offsets of all CL CTAs -- which divides the L2->SM traffic of
-// the streamed operand (the bound of this GEMM) by CL.  A ring slot is free again when all CL consumers have
-// released it (tcgen05.commit multicast onto every CTA's empty barrier).
-template <int CL>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-blend_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_f, int pslabs,
-                    int ksteps_cs, int ksteps_p, int use_lo, int row0, int mtiles, int ntiles_n, int tiles_per_chunk,
-                    float4* __restrict__ vpB, int nc4) {
-  const int nslab_f = 1 + 2 * pslabs;               // streamed feature slabs per body tile
-  const int nslab_w = 1 + (use_lo ? 2 : 1) * pslabs;   // resident model slabs
-  constexpr int SLAB = BM * BK * 2;                 // 16 KB: 128 rows x 64 bf16 (both operands)
-  constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1);
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  unsigned char* w_s = smem;                                          // [nslab][16 KB]
-  unsigned char* f_s = smem + WS_MAX_SLABS * SLAB;                    // [WS_STAGES][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(f_s + WS_STAGES * SLAB);
-  uint64_t* w_full = bars;
-  uint64_t* full_bar = bars + 1;
-  uint64_t* empty_bar = full_bar + WS_STAGES;
-  uint64_t* tfull_bar = empty_bar + WS_STAGES;      // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool live = (int)blockIdx.x < mtiles;       // grid.x is padded to a multiple of CL: the extra CTAs only relay
-  const int m0 = row0 + min((int)blockIdx.x, mtiles - 1) * BM;
-  const int nt_begin = blockIdx.y * tiles_per_chunk;
-  const int nt_end = min(ntiles_n, nt_begin + tiles_per_chunk);
-  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&map_w);
-    prefetch_tmap(&map_f);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(w_full, 1);
-    for (int i = 0; i < WS_STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL);                 // one release per consumer CTA
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);                 // one arrival per epilogue warp
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    __syncwarp();
-    tmem_alloc(tmem_slot, 2 * WS_BN);
-  }
-  tc_fence_before();
-  if (CL > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers exist before anything is multicast
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===== TMA producer: the whole warp walks the loop, one elected lane issues =====
-    if (elect_one()) {
-      mbar_arrive_expect_tx(w_full, (uint32_t)nslab_w * SLAB);
-      for (int s = 0; s < nslab_w; ++s) tma_load_2d(w_s + s * SLAB, &map_w, w_full, s * BK, m0);
-    }
-    __syncwarp();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int nt = nt_begin; nt < nt_end; ++nt)
-      for (int s = 0; s < nslab_f; ++s) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);   // every CTA of the cluster has released this slot
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&full_bar[stage], SLAB);
-          if (CL > 1)
-            tma_load_2d_mc(f_s + stage * SLAB + rank * (SLAB / CL), &map_f, &full_bar[stage], s * BK,
-                           nt * WS_BN + (int)rank * (WS_BN / CL), MASK);
-          else
-            tma_load_2d(f_s + stage * SLAB, &map_f, &full_bar[stage], s * BK, nt * WS_BN);
-        }
-        __syncwarp();
-        if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
-      }
-  } else if (warp == 1) {
-    // ===== MMA issuer: warp-uniform loop (descriptors in uniform registers), one elected lane issues =====
-    constexpr uint32_t idesc = make_idesc(BM, WS_BN);
-    constexpr int KS = BK / UMMA_K;
-    mbar_wait(w_full, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t tphase[2] = {0u, 0u};
-    int acc = 0;
-    for (int nt = nt_begin; nt < nt_end; ++nt, acc ^= 1) {
-      mbar_wait(&tempty_bar[acc], tphase[acc] ^ 1);   // epilogue has drained this accumulator
-      tphase[acc] ^= 1;
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * WS_BN);
-      int j = 0;                                        // pose slab index of the current feature slab
-      for (int s = 0; s < nslab_f; ++s) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint64_t da = make_sw128_desc(smem_u32(f_s + stage * SLAB));   // A: 128 bodies x 64 features
-        // which model slabs this feature slab multiplies, and how many 16-wide K steps of it are non-zero
-        int ks = ksteps_cs, w0 = 0, w1 = -1;
-        if (s > 0) {
-          ks = min(KS, ksteps_p - j * KS);
-          w0 = 1 + j;                                                        // P_hi slab j
-          if (s <= pslabs && use_lo) w1 = 1 + pslabs + j;                    // pf_hi also meets P_lo slab j
-          if (++j == pslabs) j = 0;
-        }
-        const uint64_t db0 = make_sw128_desc(smem_u32(w_s + w0 * SLAB));     // B: 128 model rows x 64
-        const uint64_t db1 = make_sw128_desc(smem_u32(w_s + max(w1, 0) * SLAB));
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < KS; ++k)
-            if (k < ks) umma_bf16(d_tmem, da + 2 * k, db0 + 2 * k, idesc, (s | k) != 0);
-          if (w1 >= 0) {
-#pragma unroll
-            for (int k = 0; k < KS; ++k)
-              if (k < ks) umma_bf16(d_tmem, da + 2 * k, db1 + 2 * k, idesc, 1u);
-          }
-          if (CL > 1) umma_commit_mc(&empty_bar[stage], MASK); else umma_commit(&empty_bar[stage]);
-          if (s == nslab_f - 1) umma_commit(&tfull_bar[acc]);
-        }
-        __syncwarp();
-        if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    float4* colbase = vpB + ((size_t)q * nc4 + (m0 >> 2)) * 32 + lane;   // group q of the body tile, chunk m0/4
-    uint32_t tphase[2] = {0u, 0u};
-    int acc = 0;
-    for (int nt = nt_begin; nt < nt_end; ++nt, acc ^= 1) {
-      mbar_wait(&tfull_bar[acc], tphase[acc]);
-      tphase[acc] ^= 1;
-      tc_fence_after();
-      if (live) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < BM; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * WS_BN + c0), v);
-          float4* o = colbase + ((size_t)nt * 4 * nc4 + (c0 >> 2)) * 32;
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            o[i * 32] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                    __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[acc])) : "memory");
-      }
-    }
-  }
-  tc_fence_before();
-  if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA leaves while peers may still signal its barriers
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * WS_BN);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Forward blend GEMM on a CTA PAIR (cta_group::2): the pair owns 256 consecutive model rows -- each CTA keeps
@@ -1060,9 +891,8 @@ static int launch_blend_fwd_umma_bs2(const DevModel& m, int mode, const __nv_bfl
 
 int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat, int S, int Sw, float* vpT,
                           int row_begin, int row_end, cudaStream_t st) {
-  constexpr int CL = WS_CLUSTER;
-  // B200_FWD_2CTA: 2 (default) body-stationary CTA pairs, 1 model-row-stationary CTA pairs, 0 single-CTA kernel
-  // (the latter two are kept for comparison)
+  // B200_FWD_2CTA: 2 (default) body-stationary CTA pairs; 1 model-row-stationary CTA pairs (also the fall-back for
+  // slabs wider than the body-stationary work list)
   static const int sel = getenv("B200_FWD_2CTA") == nullptr ? 2 : atoi(getenv("B200_FWD_2CTA"));
   if (sel >= 2 && (Sw / WS_BN + 1) / 2 <= BS_MAX_WORK) {     // wider slabs than 160 body-tile pairs: row-stationary kernel
     int dev = 0, sms = 148;
@@ -1070,53 +900,8 @@ int launch_blend_fwd_umma(const DevModel& m, int mode, const __nv_bfloat16* feat
     B200_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     return launch_blend_fwd_umma_bs2(m, mode, feat, S, Sw, vpT, row_begin, row_end, sms, st);
   }
-  if (sel >= 1) return launch_blend_fwd_umma_2cta(m, mode, feat, S, Sw, vpT, row_begin, row_end, st);
-  const int pslabs = m.fl.pseg / BK;
-  const int use_lo = (mode == B200SMPL_MODE_BF16) ? 0 : 1;
-  if (1 + 2 * pslabs > WS_MAX_SLABS) return fail(B200SMPL_ERR_INVALID, "feature pitch too large for the resident operand");
-  CUtensorMap map_w, map_f;
-  int rc;
-  if ((rc = make_map(&map_w, m.Wf, m.fl.pitch, m.n_pad, m.fl.pitch, BM))) return rc;
-  if ((rc = make_map(&map_f, feat, m.fl.pitch, S, m.fl.pitch, WS_BN / CL))) return rc;   // each CTA of a cluster loads 128/CL bodies
-  constexpr int smem = (WS_MAX_SLABS + WS_STAGES) * BM * BK * 2 + 1024 + 256;
-  auto kern = blend_fwd_ws_kernel<CL>;
-  B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int mtiles = (row_end - row_begin) / BM;
-  const int gx = round_up(mtiles, CL);
-  const int ntiles_n = Sw / WS_BN;
-  // body chunks: enough CTAs for several waves, but at least 4 body tiles per CTA to amortise the W load
-  int chunks = 1;
-  {
-    double best = -1.0;
-    for (int c = 1; c <= ntiles_n; ++c) {
-      const int tpc = (ntiles_n + c - 1) / c;
-      if (tpc < 4 && c > 1) break;
-      const long long ctas = (long long)gx * ((ntiles_n + tpc - 1) / tpc);
-      const long long waves = (ctas + 147) / 148;
-      const double eff = (double)ctas / (double)(waves * 148);
-      if (eff > best + 1e-9) { best = eff; chunks = (ntiles_n + tpc - 1) / tpc; }
-    }
-  }
-  const int tpc = (ntiles_n + chunks - 1) / chunks;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(gx, (ntiles_n + tpc - 1) / tpc, 1);
-  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = CL > 1 ? 1 : 0;
-  LaunchTimer _timer("blend_fwd_umma", st);
-  B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map_w, map_f, pslabs, (m.fl.k_cs + UMMA_K - 1) / UMMA_K,
-                                   (NPOSE + UMMA_K - 1) / UMMA_K, use_lo, row_begin, mtiles, ntiles_n, tpc,
-                                   reinterpret_cast<float4*>(vpT), m.n_pad / 4));
-  B200_LAUNCH_CHECK("blend_fwd_umma");
-  return 0;
+  (void)sel;
+  return launch_blend_fwd_umma_2cta(m, mode, feat, S, Sw, vpT, row_begin, row_end, st);   // model-row-stationary pairs
 }
 
 }  // namespace b200smpl

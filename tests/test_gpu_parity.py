@@ -492,11 +492,11 @@ def test_fused_forward_equals_two_kernel_forward(engine, dev, mode, B):
     assert torch.equal(v0, v1) and torch.equal(j0, j1)
 
 
-@pytest.mark.parametrize("env", [{"B200_POSE_LB": "0"}, {"B200_FWD_2CTA": "1"}, {"B200_FWD_2CTA": "0", "B200_BWD_2CTA": "0"},
+@pytest.mark.parametrize("env", [{"B200_POSE_LB": "0"}, {"B200_FWD_2CTA": "1"}, {"B200_BWD_2CTA": "0"},
                                  {"B200_FUSED_FWD": "0"}, {"B200_FUSED_FWD": "2"}, {"B200_FUSED_BWD": "1"}])
 def test_comparison_kernels_stay_correct(env):
     """The kernels kept for comparison behind environment switches (lane = joint pose kernels, row-stationary
-    CTA-pair and single-CTA GEMMs, the fused forward switched off / forced on for calls that keep the forward
+    CTA-pair forward GEMM and single-CTA gradient GEMM, the fused forward switched off / forced on for calls that keep the forward
     products, the opt-in fused skinning-backward + gradient GEMM) are selected once per process: run the forward / backward parity tests in a child process with the
     switch set."""
     import os
