@@ -334,8 +334,10 @@ int b200smpl_forward(const b200smpl_model* m, const b200smpl_forward_args* a, vo
     // and v_posed never touches HBM (188 us against 108 + 136 us at B = 4096).  When the products are kept the
     // fused kernel would write v_posed AND the vertices (658 MB of pure writes, 242 us): no faster than the two
     // kernels, so that case stays on them (B200_FUSED_FWD=2 forces the fused kernel, 0 disables it).
+    // Below ~512 bodies a call is launch-latency bound and the two kernels (PDL-chained) are as fast or faster
+    // (scripts/fwd_only_sweep.py: 53 vs 47 us at B = 64, 57 vs 65 us at B = 512, 0.211 vs 0.263 ms at B = 4096).
     const bool fused = a->vertices != nullptr && a->mode != B200SMPL_MODE_FP32_SIMT && d.n_virt0 == d.ntiles * 96 &&
-                       (saved == nullptr ? fused_fwd_mode() >= 1 : fused_fwd_mode() >= 2);
+                       (saved == nullptr ? (fused_fwd_mode() >= 2 || (fused_fwd_mode() == 1 && nb >= 512)) : fused_fwd_mode() >= 2);
     if (fused) {
       rc = launch_blend_lbs_fwd(d, fwd_gemm_mode(a->mode), feat, S, Sw, vpT, A_T, b0, nb, a->transl,
                                 a->vertices, saved != nullptr, m->num_sms, st);
