@@ -74,6 +74,20 @@ static_assert(NJ % FF_NW == 0, "joints split evenly over the warps of a quadrant
 // timing experiments (kernel argument dbg): what is left out
 constexpr int FF_DBG_NO_MMA = 1, FF_DBG_NO_FLUSH = 2, FF_DBG_NO_SKIN = 4, FF_DBG_NO_RELOAD = 8, FF_DBG_NO_VP = 16;
 
+#ifndef B200_FF_TMA2SM
+#define B200_FF_TMA2SM 1
+#endif
+// TMA load of a CTA pair: the bytes land in THIS CTA's shared memory, the transaction count on the LEADER's
+// mbarrier (same offset, CTA rank bit of the shared::cluster address cleared), so the MMA issuer waits on one
+// barrier per stage and no warp has to relay the peer's "stage landed"
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
 // ---- tensor memory <-> registers (thread = lane of the warp's quadrant) --------------------------------------
 __device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const float4& v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
@@ -265,23 +279,33 @@ blend_lbs_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
   if (FF_NW == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FF_REGS_WG0));
   if (warp == 0) {
     // ===== TMA producer (both CTAs): own body tile once, then own half of every model slab of every row tile =====
+    const uint64_t pol_keep = l2_policy_evict_last();       // the model slabs are re-read by every body pair
     if (elect_one()) {
+#if B200_FF_TMA2SM
+      if (rank == 0) mbar_arrive_expect_tx(f_full, 2u * (uint32_t)nslab_f * FF_SLAB);   // both CTAs' bytes count here
+      for (int s = 0; s < nslab_f; ++s) tma_load_2d_pair(f_s + s * FF_SLAB, &map_f, f_full, s * BK, btile * BM, l2_policy_evict_first());
+#else
       mbar_arrive_expect_tx(f_full, (uint32_t)nslab_f * FF_SLAB);
       // rows beyond the slab (odd number of body tiles) are zero-filled by the TMA unit
       for (int s = 0; s < nslab_f; ++s) tma_load_2d(f_s + s * FF_SLAB, &map_f, f_full, s * BK, btile * BM);
+#endif
     }
     __syncwarp();
-    const uint64_t pol_keep = l2_policy_evict_last();       // the model slabs are re-read by every body pair
     int stage = 0;
     uint32_t phase = 0;
     for (int wt = wt_begin; wt < wt_end; ++wt)
       for (int s = 0; s < nslab_w; ++s) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
+#if B200_FF_TMA2SM
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * FF_STAGE_BYTES);
+          tma_load_2d_pair(w_s + stage * FF_STAGE_BYTES, &map_w, &full_bar[stage], s * BK, wt * FF_BN + (int)rank * FF_BNH, pol_keep);
+#else
           mbar_arrive_expect_tx(&full_bar[stage], FF_STAGE_BYTES);
           // rows beyond the model are zero-filled by the TMA unit
           tma_load_2d_hint(w_s + stage * FF_STAGE_BYTES, &map_w, &full_bar[stage], s * BK, wt * FF_BN + (int)rank * FF_BNH,
                            pol_keep);
+#endif
         }
         __syncwarp();
         if (++stage == FF_STAGES) { stage = 0; phase ^= 1; }
@@ -295,7 +319,7 @@ blend_lbs_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
       // division / descriptor rebuild; it was ~1000 cycles per slab with the schedule computed at run time) =====
       constexpr uint32_t idesc = make_idesc(2 * BM, FF_BN);
       mbar_wait(f_full, 0);
-      mbar_wait(peer_f_full, 0);
+      if (!B200_FF_TMA2SM) mbar_wait(peer_f_full, 0);
       const uint64_t da_base = make_sw128_desc(smem_u32(f_s));
       const uint64_t db_base = make_sw128_desc(smem_u32(w_s));
       uint32_t tph0 = 0, tph1 = 0;
@@ -303,7 +327,7 @@ blend_lbs_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
       // one model slab against one or two resident feature slabs; `first`: the tile's first MMA overwrites
       auto slab = [&](uint32_t d_tmem, int ks, int f0, int f1, bool first, uint64_t* tfull) {
         mbar_wait(&full_bar[stage], phase);
-        mbar_wait(&peer_full_bar[stage], phase);
+        if (!B200_FF_TMA2SM) mbar_wait(&peer_full_bar[stage], phase);
         tc_fence_after();
         const uint64_t db = db_base + (uint64_t)(stage * (FF_STAGE_BYTES >> 4));
         if (elect_one()) {
@@ -342,7 +366,7 @@ blend_lbs_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
             slab(d_tmem, min(KS, FF_KSP - j * KS), 1 + j, -1, false, j == PS - 1 ? &tfull_bar[acc] : nullptr);
         }
       }
-    } else {
+    } else if (!B200_FF_TMA2SM) {
       // ===== peer: relay "body tile landed" and every "stage landed" to the leader =====
       mbar_wait(f_full, 0);
       if (elect_one()) remote_arrive(peer_f_full, 0);
