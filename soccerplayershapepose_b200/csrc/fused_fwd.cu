@@ -18,10 +18,10 @@
 // lbs.cu and flushes them through a per-warp transposing tile as 96-byte row segments of the (B, V, 3) output.
 // Virtual (joint) row tiles are only stored.
 //
-// Compile-time variants kept for the experiments recorded in profiles/r02_experiments.md: B200_FF_NW=3 (three
-// epilogue warps per quadrant on registers the TMA / MMA warpgroup gives up with setmaxnreg), B200_FF_EARLY=1 (half
-// tile staged in 48 registers, accumulator released at once), B200_FF_HV=16 (192-byte row segments), and the
-// B200_FF_DBG bits that leave parts of the kernel out for timing.
+// The variants that lost (three epilogue warps per quadrant on setmaxnreg registers, the half tile staged in 48
+// registers with the accumulator released at once, 192-byte row segments) are in the history (commit cf06df6) and in
+// profiles/r02_experiments.md section 8; what remains of the experiments are the B200_FF_DBG bits that leave parts of
+// the kernel out for timing.
 #include <algorithm>
 
 #include "lbs_tiles.cuh"
@@ -31,15 +31,9 @@ namespace b200smpl {
 
 constexpr int FF_BN = 96;                           // model rows per tile = 32 vertices
 constexpr int FF_BNH = FF_BN / 2;                   // rows of a slab each CTA of the pair stages
-#ifndef B200_FF_NW
-#define B200_FF_NW 2                                // epilogue warps per TMEM lane quadrant (2 or 3)
-#endif
-#ifndef B200_FF_EARLY
-#define B200_FF_EARLY 0                             // 1: the half tile is staged in 48 registers and the accumulator released at once
-#endif
-constexpr int FF_NW = B200_FF_NW;
+constexpr int FF_NW = 2;                            // epilogue warps per TMEM lane quadrant
 #ifndef B200_FF_STAGES
-#define B200_FF_STAGES (B200_FF_NW == 2 ? 7 : 5)
+#define B200_FF_STAGES 7
 #endif
 constexpr int FF_STAGES = B200_FF_STAGES;
 constexpr int FF_STAGE_BYTES = FF_BNH * BK * 2;     // 6 KB
@@ -48,16 +42,9 @@ constexpr int FF_KSP = (NPOSE + UMMA_K - 1) / UMMA_K;   // K steps of one pose s
 constexpr int FF_MAX_SLABS = 1 + 2 * FF_PS;         // resident feature slabs: constants+shape, 4 x pf_hi, 4 x pf_lo
 constexpr int FF_SLAB = BM * BK * 2;                // 16 KB
 constexpr int FF_EPI_WARPS = 4 * FF_NW;
-// NW = 2: warps 0 / 1 = TMA / MMA, warps 2.. epilogue.  NW = 3: warpgroup 0 = TMA, MMA and two idle warps and gives
-// registers up (setmaxnreg) for the three epilogue warpgroups
-constexpr int FF_EPI_WARP0 = FF_NW == 2 ? 2 : 4;
+constexpr int FF_EPI_WARP0 = 2;                     // warps 0 / 1 = TMA / MMA, warps 2.. epilogue
 constexpr int FF_THREADS = (FF_EPI_WARP0 + FF_EPI_WARPS) * 32;
-constexpr int FF_REGS_WG0 = 32;
-constexpr int FF_REGS_EPI = 160;
-#ifndef B200_FF_HV
-#define B200_FF_HV 8
-#endif
-constexpr int FF_HV = B200_FF_HV;                   // vertices per flush of the staging tile (8 or 16)
+constexpr int FF_HV = 8;                            // vertices per flush of the staging tile
 constexpr int FF_TR_COL = 2 * FF_BN;                // first TMEM column of the transforms (12 per joint)
 constexpr int FF_WV = TILE_V / 2;                   // vertices of a half tile (one epilogue warp's unit of work)
 constexpr int FF_PLAN_WORDS = (FF_WV / 8) * 40;     // plan records of a half tile
@@ -68,7 +55,6 @@ constexpr size_t FF_SMEM = (size_t)FF_MAX_SLABS * FF_SLAB + (size_t)FF_STAGES * 
                            1024 /*alignment slack*/;
 static_assert(FF_SMEM <= 232448, "fused forward: shared memory budget");
 static_assert(FF_TR_COL + NJ * AELEMS <= 512, "fused forward: tensor memory budget");
-static_assert(FF_NW == 2 || FF_NW == 3, "fused forward: 2 or 3 epilogue warps per quadrant");
 static_assert(NJ % FF_NW == 0, "joints split evenly over the warps of a quadrant");
 
 // timing experiments (kernel argument dbg): what is left out
@@ -120,29 +106,6 @@ __device__ __forceinline__ void tmem_ld_24(uint32_t taddr, uint32_t (&r)[24]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
       : "r"(taddr), "r"(taddr + 8), "r"(taddr + 16)
       : "memory");
-}
-
-// 48 accumulator columns (a half tile: 16 vertices of this body) -> registers, complete on return
-__device__ __forceinline__ void tmem_ld_48(uint32_t taddr, uint32_t (&r)[48]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%48];\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%49];\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47}, [%50];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
-        "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
-        "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47])
-      : "r"(taddr), "r"(taddr + 16), "r"(taddr + 32)
-      : "memory");
-}
-
-template <int N>
-__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
-  if constexpr (N == 24) tmem_ld_24(taddr, r);
-  else tmem_ld_48(taddr, r);
 }
 
 // slot (re)load from tensor memory: columns of joint `joint` hold (r00 r10 r01 r11) (r02 r12 t0 t1) (r20 r21 r22 t2)
@@ -276,7 +239,6 @@ blend_lbs_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
   if (threadIdx.x == 0) pdl_trigger();
 
   if (warp < FF_EPI_WARP0) {
-  if (FF_NW == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FF_REGS_WG0));
   if (warp == 0) {
     // ===== TMA producer (both CTAs): own body tile once, then own half of every model slab of every row tile =====
     const uint64_t pol_keep = l2_policy_evict_last();       // the model slabs are re-read by every body pair
@@ -381,11 +343,9 @@ blend_lbs_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     }
   }
   } else {
-    if (FF_NW == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FF_REGS_EPI));
-    // ===== epilogue (both CTAs): three warps per TMEM lane quadrant walk the sequence of HALF tiles (16 vertices =
-    // 48 accumulator columns) of the cluster's range, warp r taking every third one: two warps share each tile, so the
-    // epilogue of tile t overlaps the MMAs of tile t + 1 in the other accumulator, and three warps per scheduler hide
-    // the dependent-issue latency of the skinning arithmetic better than two =====
+    // ===== epilogue (both CTAs): the two warps of a TMEM lane quadrant walk the sequence of HALF tiles (16 vertices =
+    // 48 accumulator columns) of the cluster's range, warp r3 taking half r3 of every tile: both warps share each
+    // tile, so the epilogue of tile t overlaps the MMAs of tile t + 1 in the other accumulator =====
     const int e = warp - FF_EPI_WARP0, q = warp & 3, r3 = e >> 2;
     float* tile = tiles + e * FF_TILE_WORDS;
     float* my_row = tile + lane * SH::HROW;
@@ -396,7 +356,7 @@ blend_lbs_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t tr_base = lane_base + FF_TR_COL;
     const bool skin = verts != nullptr;
-    // ---- the group's transforms -> tensor memory (the three warps of the quadrant take 8 joints each) ----
+    // ---- the group's transforms -> tensor memory (the two warps of the quadrant take 12 joints each) ----
     if (live && skin) {
       const float4* ap = A_blk + (size_t)g * (NJ * 3 * 32) + lane;
 #pragma unroll 1
@@ -455,33 +415,18 @@ blend_lbs_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
       if (skin && wt < n_vtiles) {
         const uint32_t b = n_plan & 1;
         if (is_vhalf(h + FF_NW) && lane == 0) issue_plan(b ^ 1, h + FF_NW);
-        constexpr bool WHOLE = B200_FF_EARLY || FF_HV == 16;          // the half tile's 48 columns in one load
-        constexpr int NV = WHOLE ? 48 : 24;
-        uint32_t v[NV];
-        if (WHOLE) {
-          // EARLY: the accumulator is handed back at once, the MMAs run up to two tiles ahead of the skinning
-          tmem_ld_n<NV>(acc_base, v);
-          release(acc);
-          if (write_vp && !(dbg & FF_DBG_NO_VP)) {
-#pragma unroll
-            for (int i = 0; i < NV / 4; ++i)
-              colbase[(size_t)i * 32] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                    __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-          }
-        }
         mbar_wait(&wbar[b], (n_plan >> 1) & 1);
         const uint32_t* st = stash + b * FF_PLAN_WORDS;
 #pragma unroll 1
         for (int sub = 0; sub < FF_WV / FF_HV; ++sub) {
-          if (!WHOLE) {
-            tmem_ld_n<NV>(acc_base + (uint32_t)(sub * 24), v);
-            if (sub == FF_WV / FF_HV - 1) release(acc);                // the MMAs of the tile after next may start
-            if (write_vp && !(dbg & FF_DBG_NO_VP)) {
+          uint32_t v[24];
+          tmem_ld_24(acc_base + (uint32_t)(sub * 24), v);
+          if (sub == FF_WV / FF_HV - 1) release(acc);                  // the MMAs of the tile after next may start
+          if (write_vp && !(dbg & FF_DBG_NO_VP)) {
 #pragma unroll
-              for (int i = 0; i < 6; ++i)
-                colbase[(size_t)(sub * 6 + i) * 32] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                                  __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-            }
+            for (int i = 0; i < 6; ++i)
+              colbase[(size_t)(sub * 6 + i) * 32] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                                __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
           }
           if (!(dbg & FF_DBG_NO_SKIN)) {
 #pragma unroll
@@ -489,7 +434,7 @@ blend_lbs_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
               float P[12];
 #pragma unroll
               for (int i = 0; i < 12; ++i)
-                P[i] = __uint_as_float((WHOLE && FF_HV == 8 && sub) ? v[(NV - 24) + u * 12 + i] : v[u * 12 + i]);
+                P[i] = __uint_as_float(v[u * 12 + i]);
               skin_fwd4_tm(sl, tr_base, plan_meta(st, sub * (FF_HV / 4) + u), plan_wts(st, sub * (FF_HV / 4) + u),
                            ((sub == 0 && u == 0) ? (0xFu << 20) : 0u) | ((dbg & FF_DBG_NO_RELOAD) ? (1u << 31) : 0u), tx, ty, tz,
                            P, my_row + u * 12);
