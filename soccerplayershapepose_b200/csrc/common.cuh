@@ -34,6 +34,8 @@ struct ChainTables {
   int8_t nchild[NJ];
   int8_t child[NJ][MAX_CHILD];
   int8_t maxchild_at[NJ];   // [d]: max number of children a joint of depth d-1 has (bounds the gather of round d)
+  int8_t order[NJ];         // joints sorted by depth (stable): the joints of one level are independent of each other
+  int8_t level_ptr[NJ + 1]; // order[level_ptr[d] .. level_ptr[d + 1]) = joints of depth d
   int32_t maxdepth;
 };
 

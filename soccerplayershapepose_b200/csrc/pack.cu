@@ -56,6 +56,16 @@ int pack_model(const b200smpl_model_desc* d, HostArrays& h, DevModel& dm, std::s
   for (int j = 0; j < NJ; ++j)
     if (ch.depth[j] + 1 < NJ) ch.maxchild_at[ch.depth[j] + 1] = std::max(ch.maxchild_at[ch.depth[j] + 1], ch.nchild[j]);
 
+  {  // joints by level (the lane = body pose kernels walk the tree one level at a time, one warp per joint of the level)
+    int n = 0;
+    for (int dpt = 0; dpt <= ch.maxdepth; ++dpt) {
+      ch.level_ptr[dpt] = (int8_t)n;
+      for (int j = 0; j < NJ; ++j)
+        if (ch.depth[j] == dpt) ch.order[n++] = (int8_t)j;
+    }
+    for (int dpt = ch.maxdepth + 1; dpt <= NJ; ++dpt) ch.level_ptr[dpt] = (int8_t)n;
+  }
+
   // ---- skinning influences per vertex (<= 4 non-zeros) ----
   struct Infl { int n; int j[4]; float w[4]; };
   std::vector<Infl> infl(V);

@@ -465,10 +465,12 @@ pose_fwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __r
     }
   }
   __syncthreads();
-  // ---------------- P3 ----------------
-  if (warp == 0) {
+  // ---------------- P3: one tree level at a time, one warp per joint of the level (9 levels on the SMPL tree
+  // instead of 24 dependent steps on one warp) ----------------
 #pragma unroll 1
-    for (int j = 0; j < NJ; ++j) {
+  for (int dpt = 0; dpt <= m.chain.maxdepth; ++dpt) {
+    for (int i = m.chain.level_ptr[dpt] + warp; i < m.chain.level_ptr[dpt + 1]; i += NW) {
+      const int j = m.chain.order[i];
       const int p = m.chain.parent[j];
       float G[12];
 #pragma unroll
@@ -488,8 +490,8 @@ pose_fwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __r
 #pragma unroll
       for (int e = 0; e < 12; ++e) sm.G[(j * 12 + e) * 32 + lane] = G[e];
     }
+    __syncthreads();
   }
-  __syncthreads();
   // ---------------- P4 ----------------
   {
     float4* A4 = reinterpret_cast<float4*>(A_T) + (size_t)g * (NJ * 3 * 32) + lane;
@@ -596,8 +598,9 @@ struct LbBwdSmem {
   float J[NJ * 3 * 32];          // rest joints
   float B[LB_MAXB * 32];         // betas
   float DA[NJ * 12 * 32];        // dL/dA (sum of the partials)
-  float D[NJ * 12 * 32];         // dL/dG handed up by the children
-  float DJ[NJ * 3 * 32];         // dL/dJr: handed up by the children, then final
+  float D[NJ * 12 * 32];         // [j]: dL/dG of j's PARENT as far as it comes through j (gathered by the parent)
+  float DJ[NJ * 3 * 32];         // dL/dJr, final
+  float DJc[NJ * 3 * 32];        // what a joint hands up to its parent's dL/dJr
   float DF[224 * LB_P];          // dL/d[betas | pose feature] (sum of the split-K partials), [k][body]
   float DJo[NJ * 3 * LB_P];      // dL/d(posed chain joints) from the caller
   float Jsd[NJ * 3 * LB_MAXB];
@@ -732,8 +735,6 @@ pose_bwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __r
     if (tid < 32 * nbeta) sm.B[(tid % nbeta) * 32 + tid / nbeta] = bv;
     for (int i = tid; i < NJ * 3 * nbeta; i += LBB_THREADS) sm.Jsd[i] = m.Jsd[i];
     if (tid < NJ * 3) sm.Jt[tid] = m.Jt[tid];
-    for (int i = tid; i < NJ * 12 * 8; i += LBB_THREADS) reinterpret_cast<float4*>(sm.D)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = tid; i < NJ * 3 * 32; i += LBB_THREADS) sm.DJ[i] = 0.f;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
@@ -753,11 +754,25 @@ pose_bwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __r
     }
   }
   __syncthreads();
-  // ---------------- P3: reverse walk (warp 0) ----------------
-  if (warp == 0) {
+  // ---------------- P3: reverse walk, one tree level at a time (deepest first), one warp per joint of the level.
+  // A joint leaves what it hands up in ITS OWN slots (sm.D[j]: dL/dG of its parent, sm.DJc[j]: the rest-joint term);
+  // the parent gathers its children's slots one level later, so the joints of a level never write the same word ----
 #pragma unroll 1
-    for (int j = NJ - 1; j >= 0; --j) {
-      float R[9], GR[9], Jr[3], dAr[12], dGR[9], dGt[3], dJr[3];
+  for (int dpt = m.chain.maxdepth; dpt >= 0; --dpt) {
+    for (int i = m.chain.level_ptr[dpt] + warp; i < m.chain.level_ptr[dpt + 1]; i += LBB_THREADS / 32) {
+      const int j = m.chain.order[i];
+      float R[9], GR[9], Jr[3], dAr[12], dGR[9], dGt[3], dJr[3], Dj[12], DJj[3];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) Dj[e] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) DJj[c] = 0.f;
+      for (int k = 0; k < m.chain.nchild[j]; ++k) {               // what the children handed up
+        const int ch = m.chain.child[j][k];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) Dj[e] += sm.D[(ch * 12 + e) * 32 + lane];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) DJj[c] -= sm.DJc[(ch * 3 + c) * 32 + lane];
+      }
 #pragma unroll
       for (int e = 0; e < 9; ++e) R[e] = sm.R[(j * 9 + e) * LB_P + lane];
       lb_rot_of(reinterpret_cast<const float4*>(sm.G) + (j * 3) * 32 + lane, GR);
@@ -768,13 +783,13 @@ pose_bwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __r
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const float dat = dAr[r * 4 + 3];
-        dGt[r] = sm.D[(j * 12 + r * 4 + 3) * 32 + lane] + dat + sm.DJo[(j * 3 + r) * LB_P + lane];
+        dGt[r] = Dj[r * 4 + 3] + dat + sm.DJo[(j * 3 + r) * LB_P + lane];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) dGR[r * 3 + c] = sm.D[(j * 12 + r * 4 + c) * 32 + lane] + dAr[r * 4 + c] - dat * Jr[c];
+        for (int c = 0; c < 3; ++c) dGR[r * 3 + c] = Dj[r * 4 + c] + dAr[r * 4 + c] - dat * Jr[c];
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c)
-        dJr[c] = sm.DJ[(j * 3 + c) * 32 + lane] - (GR[c] * dAr[3] + GR[3 + c] * dAr[7] + GR[6 + c] * dAr[11]);
+        dJr[c] = DJj[c] - (GR[c] * dAr[3] + GR[3 + c] * dAr[7] + GR[6 + c] * dAr[11]);
       const int p = m.chain.parent[j];
       float dRl[9];
       if (p >= 0) {
@@ -782,14 +797,14 @@ pose_bwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __r
         lb_rot_of(reinterpret_cast<const float4*>(sm.G) + (p * 3) * 32 + lane, PR);
 #pragma unroll
         for (int r = 0; r < 3; ++r) rel[r] = Jr[r] - sm.J[(p * 3 + r) * 32 + lane];
-        // G_j = G_p . [R_j | rel_j]: hand dL/dG_p up, keep dL/dR_j and dL/drel_j
+        // G_j = G_p . [R_j | rel_j]: hand dL/dG_p up (own slot), keep dL/dR_j and dL/drel_j
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            sm.D[(p * 12 + r * 4 + c) * 32 + lane] += dGR[r * 3] * R[c * 3] + dGR[r * 3 + 1] * R[c * 3 + 1] +
-                                                      dGR[r * 3 + 2] * R[c * 3 + 2] + dGt[r] * rel[c];
-          sm.D[(p * 12 + r * 4 + 3) * 32 + lane] += dGt[r];
+            sm.D[(j * 12 + r * 4 + c) * 32 + lane] = dGR[r * 3] * R[c * 3] + dGR[r * 3 + 1] * R[c * 3 + 1] +
+                                                     dGR[r * 3 + 2] * R[c * 3 + 2] + dGt[r] * rel[c];
+          sm.D[(j * 12 + r * 4 + 3) * 32 + lane] = dGt[r];
         }
 #pragma unroll
         for (int r = 0; r < 3; ++r)
@@ -799,7 +814,7 @@ pose_bwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __r
         for (int c = 0; c < 3; ++c) {
           const float drel = PR[c] * dGt[0] + PR[3 + c] * dGt[1] + PR[6 + c] * dGt[2];
           dJr[c] += drel;
-          sm.DJ[(p * 3 + c) * 32 + lane] -= drel;
+          sm.DJc[(j * 3 + c) * 32 + lane] = drel;
         }
       } else {
 #pragma unroll
@@ -812,8 +827,8 @@ pose_bwd_lb_kernel(DevModel m, const float* __restrict__ betas, const float* __r
 #pragma unroll
       for (int e = 0; e < 9; ++e) sm.R[(j * 9 + e) * LB_P + lane] = dRl[e];        // chain part of dL/dR_j
     }
+    __syncthreads();
   }
-  __syncthreads();
   // ---------------- P4: blend part, outputs ----------------
   for (int j = warp; j < NJ; j += LBB_THREADS / 32) {
     float dRl[9];
