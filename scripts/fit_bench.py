@@ -48,9 +48,22 @@ for use_graph in (True, False):
     res["graph" if use_graph else "eager"] = dt
     if use_graph:
         l0, l1 = r["initial_loss"].mean().item(), r["best_loss"].mean().item()
+kernels = None
+if os.environ.get("B200_FIT_KERNELS", "0") == "1":           # per-kernel device times of the eager iteration (library timers)
+    import ctypes
+    from soccerplayershapepose_b200 import _lib
+    lib = _lib.load()
+    lib.b200smpl_timing_enable(1)
+    fitter.fit(rot0, betas0, cam0, label, iterations=10)
+    torch.cuda.synchronize()
+    lib.b200smpl_timing_enable(0)
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.b200smpl_timing_report(buf, 1 << 16)
+    kernels = {r[0]: round(float(r[2]) / int(r[1]) * 1e3, 1) for r in (l.split() for l in buf.value.decode().splitlines())}
 print(json.dumps({"workload": "BASELINE.json configs[2]: fit %d players x %d Adam iterations (lr %g), joints2D loss + shape "
                               "prior, %s mode, joints-only SMPL path" % (B, iters, lr, mode),
                   "clocks": clocks_graph,
                   "seconds_cuda_graph": res["graph"], "seconds_eager": res["eager"],
                   "player_iterations_per_s": B * iters / res["graph"], "ms_per_iteration": res["graph"] / iters * 1e3,
-                  "mean_loss_initial": l0, "mean_loss_best": l1}))
+                  "mean_loss_initial": l0, "mean_loss_best": l1,
+                  **({"kernel_us_eager_timed": kernels} if kernels else {})}))

@@ -117,23 +117,79 @@ __global__ void fit_adam_kernel(float* __restrict__ p, const float* __restrict__
   if (commit_step && blockIdx.x == 0 && threadIdx.x == 0) step[0] = t;
 }
 
-// mark_best + the Adam step of every parameter tensor in ONE launch.  A CTA owns FIT_BPC whole bodies: it decides
-// "improved" for them from the old best loss (shared memory), then updates their rows of every tensor.  The step
-// counter is double-buffered (read step[parity], write step[1 - parity]) so that no CTA can read a counter another
-// CTA has already advanced.
-constexpr int FIT_BPC = 8;
+// mark_best + the Adam step of every parameter tensor in ONE launch.  A CTA owns `bpc` whole bodies (as many as
+// give every thread at most one element of the concatenated parameter row when that fits): it decides "improved"
+// for them from the old best loss (shared memory), then updates their rows of every tensor.  The kernel is a chain
+// of dependent memory round trips, not bandwidth: a thread issues the loads of its element (parameter, gradient,
+// moments) BEFORE the barrier, next to the loss loads, so the chain is one round trip instead of one per tensor.
+// The step counter is double-buffered (read step[parity], write step[1 - parity]) so that no CTA can read a
+// counter another CTA has already advanced.
+constexpr int FIT_THREADS = 256;
+constexpr int FIT_MAX_BPC = 32;
 struct FitGroups {
   b200smpl_fit_group g[B200SMPL_FIT_MAX_GROUPS];
   int n;
+  int ptot;                   // columns of all groups together
 };
-__global__ void __launch_bounds__(256)
-fit_update_kernel(FitGroups G, const float* __restrict__ loss, float* __restrict__ best_loss,
+struct FitElem {              // one element of one tensor and what the update needs of it
+  int k, bl;
+  long long i;
+  float x, gr, m, v;
+  bool live, frozen;
+};
+__device__ __forceinline__ void fit_elem_load(FitElem& e, const FitGroups& G, int idx, int b0, int batch) {
+  e.bl = idx / G.ptot;
+  int c = idx - e.bl * G.ptot;
+  e.k = 0;
+#pragma unroll
+  for (int k = 0; k < B200SMPL_FIT_MAX_GROUPS - 1; ++k)      // unrolled: the groups stay in the parameter bank
+    if (k + 1 < G.n && e.k == k && c >= G.g[k].cols) { c -= G.g[k].cols; e.k = k + 1; }
+  e.live = b0 + e.bl < batch;
+  e.frozen = true;
+  e.x = e.gr = e.m = e.v = 0.f;
+#pragma unroll
+  for (int k = 0; k < B200SMPL_FIT_MAX_GROUPS; ++k) {
+    if (k != e.k || !e.live) continue;
+    const b200smpl_fit_group& q = G.g[k];
+    e.i = (long long)(b0 + e.bl) * q.cols + c;
+    e.x = q.params[e.i];
+    e.frozen = q.frozen_cols != nullptr && q.frozen_cols[c];
+    if (!e.frozen) {
+      e.gr = q.grad[e.i];
+      if (q.grad_extra != nullptr) e.gr += q.grad_extra[e.i];
+      e.m = q.exp_avg[e.i];
+      e.v = q.exp_avg_sq[e.i];
+    }
+  }
+}
+__device__ __forceinline__ void fit_elem_store(const FitElem& e, const FitGroups& G, const uint8_t* imp, float beta1,
+                                               float beta2, float step_size, float inv_sqrt_bc2, float eps) {
+#pragma unroll
+  for (int k = 0; k < B200SMPL_FIT_MAX_GROUPS; ++k) {
+    if (k != e.k || !e.live) continue;
+    const b200smpl_fit_group& q = G.g[k];
+    if (imp[e.bl]) q.best_params[e.i] = e.x;
+    if (e.frozen) continue;
+    const float mi = beta1 * e.m + (1.f - beta1) * e.gr;
+    const float vi = beta2 * e.v + (1.f - beta2) * e.gr * e.gr;
+    q.exp_avg[e.i] = mi;
+    q.exp_avg_sq[e.i] = vi;
+    q.params[e.i] = e.x - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+}
+__global__ void __launch_bounds__(FIT_THREADS)
+fit_update_kernel(FitGroups G, int bpc, const float* __restrict__ loss, float* __restrict__ best_loss,
                   int32_t* __restrict__ best_iter, float* __restrict__ first_loss, int32_t* __restrict__ step, int parity,
                   int batch, float lr, float beta1, float beta2, float eps) {
-  __shared__ uint8_t imp[FIT_BPC];
+  __shared__ uint8_t imp[FIT_MAX_BPC];
+  const int b0 = blockIdx.x * bpc;
+  const int nel = bpc * G.ptot;
+  FitElem e0;
+  e0.live = false;
+  e0.k = -1;
+  if ((int)threadIdx.x < nel) fit_elem_load(e0, G, threadIdx.x, b0, batch);
   const int t = step[parity] + 1;
-  const int b0 = blockIdx.x * FIT_BPC;
-  if (threadIdx.x < FIT_BPC) {
+  if ((int)threadIdx.x < bpc) {
     const int b = b0 + threadIdx.x;
     bool im = false;
     if (b < batch) {
@@ -147,26 +203,11 @@ fit_update_kernel(FitGroups G, const float* __restrict__ loss, float* __restrict
   __syncthreads();
   const float bc1 = 1.f - powf(beta1, (float)t), bc2 = 1.f - powf(beta2, (float)t);
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
-#pragma unroll
-  for (int k = 0; k < B200SMPL_FIT_MAX_GROUPS; ++k) {          // unrolled: the groups stay in the parameter bank
-    if (k >= G.n) break;
-    const b200smpl_fit_group& q = G.g[k];
-    const int P = q.cols;
-    for (int idx = threadIdx.x; idx < FIT_BPC * P; idx += blockDim.x) {
-      const int bl = idx / P, c = idx - bl * P, b = b0 + bl;
-      if (b >= batch) break;
-      const long long i = (long long)b * P + c;
-      const float x = q.params[i];
-      if (imp[bl]) q.best_params[i] = x;
-      if (q.frozen_cols != nullptr && q.frozen_cols[c]) continue;
-      float gr = q.grad[i];
-      if (q.grad_extra != nullptr) gr += q.grad_extra[i];
-      const float mi = beta1 * q.exp_avg[i] + (1.f - beta1) * gr;
-      const float vi = beta2 * q.exp_avg_sq[i] + (1.f - beta2) * gr * gr;
-      q.exp_avg[i] = mi;
-      q.exp_avg_sq[i] = vi;
-      q.params[i] = x - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
-    }
+  if ((int)threadIdx.x < nel) fit_elem_store(e0, G, imp, beta1, beta2, step_size, inv_sqrt_bc2, eps);
+  for (int idx = threadIdx.x + FIT_THREADS; idx < nel; idx += FIT_THREADS) {   // rows longer than the CTA
+    FitElem e;
+    fit_elem_load(e, G, idx, b0, batch);
+    fit_elem_store(e, G, imp, beta1, beta2, step_size, inv_sqrt_bc2, eps);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) step[1 - parity] = t;
 }
@@ -185,6 +226,7 @@ int b200smpl_fit_loss(const float* joints, const float* cam, const int32_t* join
   if (!joints || !cam || !joint_map || !label || !betas || !loss_per_body || !grad_joints || !grad_cam || batch < 1 ||
       nmap < 1)
     return fail(B200SMPL_ERR_INVALID, "bad argument");
+  LaunchTimer _timer("fit_loss", (cudaStream_t)stream);
   fit_loss_kernel<<<(batch + 3) / 4, 128, 0, (cudaStream_t)stream>>>(joints, cam, joint_map, label, vis, betas, batch,
                                                                      num_joints, nmap, num_betas, proj_wh, norm_wh, log_var,
                                                                      shape_weight, loss_per_body, grad_joints, grad_cam,
@@ -235,9 +277,13 @@ int b200smpl_fit_update(const b200smpl_fit_group* groups, int ngroups, const flo
     if (!q.params || !q.grad || !q.exp_avg || !q.exp_avg_sq || !q.best_params || q.cols < 1)
       return fail(B200SMPL_ERR_INVALID, "bad parameter group");
     G.g[k] = q;
+    G.ptot += q.cols;
   }
-  fit_update_kernel<<<(batch + FIT_BPC - 1) / FIT_BPC, 256, 0, (cudaStream_t)stream>>>(G, loss_per_body, best_loss, best_iter, first_loss,
-                                                                                      step, parity, batch, lr, beta1, beta2, eps);
+  const int bpc = std::max(1, std::min(FIT_MAX_BPC, FIT_THREADS / G.ptot));
+  LaunchTimer _timer("fit_update", (cudaStream_t)stream);
+  fit_update_kernel<<<(batch + bpc - 1) / bpc, FIT_THREADS, 0, (cudaStream_t)stream>>>(G, bpc, loss_per_body, best_loss, best_iter,
+                                                                                      first_loss, step, parity, batch, lr, beta1,
+                                                                                      beta2, eps);
   B200_LAUNCH_CHECK("fit_update");
   return 0;
 }
