@@ -247,3 +247,62 @@ def test_multi_view_fit_matches_reference_loop(setup, use_graph):
     assert torch.equal(res["last"]["body_pose"][:, fz].cpu(), bp0[:, fz])
     assert res["translation"].shape == (P, V, 3) and res["global_orient"].shape == (P, V, 3, 3)
     assert (res["best_loss"] < res["initial_loss"]).all()
+
+
+@pytest.mark.parametrize("cols,batch", [((216, 10, 3), 37), ((72, 10, 3), 50), ((3,), 100), ((300, 7), 9), ((1, 1, 1, 1), 65)])
+def test_fit_update_matches_torch_adam(cols, batch):
+    """b200smpl_fit_update alone (best-iterate copy + Adam of up to four tensors in one launch) against
+    torch.optim.Adam over three steps: several bodies per CTA (short rows), rows longer than a CTA, a ragged last
+    CTA, frozen columns and an extra gradient term."""
+    import ctypes
+    from soccerplayershapepose_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(len(cols) * 1000 + batch)
+    n = len(cols)
+    p = [torch.randn(batch, c, generator=g).to(dev) for c in cols]
+    frozen = [None if k % 2 else (torch.rand(c, generator=g) < 0.3).to(torch.uint8).to(dev) for k, c in enumerate(cols)]
+    ref = [x.double().cpu().clone().requires_grad_(True) for x in p]
+    opt = torch.optim.Adam(ref, lr=1e-2)
+    m = [torch.zeros_like(x) for x in p]
+    v = [torch.zeros_like(x) for x in p]
+    best = [torch.zeros_like(x) for x in p]
+    best_loss = torch.full((batch,), float("inf"), device=dev)
+    best_iter = torch.zeros(batch, dtype=torch.int32, device=dev)
+    first_loss = torch.zeros(batch, device=dev)
+    step = torch.zeros(2, dtype=torch.int32, device=dev)
+    want_best = [x.double().cpu().clone() for x in p]
+    want_best_loss = torch.full((batch,), float("inf"), dtype=torch.float64)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    for it in range(3):
+        grads = [torch.randn(batch, c, generator=g) for c in cols]
+        extra = [torch.randn(batch, c, generator=g) if k == 1 else None for k, c in enumerate(cols)]
+        loss = torch.rand(batch, generator=g) + (0.0 if it != 1 else 0.5)     # some bodies improve, some do not
+        gd = [x.to(dev) for x in grads]
+        ed = [None if x is None else x.to(dev) for x in extra]
+        groups = (_lib.FitGroup * n)()
+        for k in range(n):
+            groups[k] = _lib.FitGroup(p[k].data_ptr(), gd[k].data_ptr(), None if ed[k] is None else ed[k].data_ptr(),
+                                      m[k].data_ptr(), v[k].data_ptr(), best[k].data_ptr(),
+                                      None if frozen[k] is None else frozen[k].data_ptr(), cols[k])
+        _lib.check(lib.b200smpl_fit_update(ctypes.cast(groups, ctypes.c_void_p), n, loss.to(dev).data_ptr(),
+                                           best_loss.data_ptr(), best_iter.data_ptr(), first_loss.data_ptr(),
+                                           step.data_ptr(), it & 1, batch, 1e-2, 0.9, 0.999, 1e-8, stream), "fit_update")
+        torch.cuda.synchronize()
+        # reference: keep the parameters that produced this loss where it improved, then one Adam step
+        imp = loss.double() < want_best_loss
+        want_best_loss = torch.where(imp, loss.double(), want_best_loss)
+        for k in range(n):
+            want_best[k][imp] = ref[k].detach()[imp]
+            gr = grads[k].double() + (0.0 if extra[k] is None else extra[k].double())
+            if frozen[k] is not None:
+                gr[:, frozen[k].cpu().bool()] = 0.0
+            ref[k].grad = gr
+        opt.step()
+        if it == 0:
+            assert torch.equal(first_loss.cpu(), loss)
+    assert int(step[1].item()) == 3                       # written to step[1 - parity] of the last call (parity 0)
+    assert torch.allclose(best_loss.cpu().double(), want_best_loss, atol=1e-7)
+    for k in range(n):
+        assert torch.allclose(p[k].cpu().double(), ref[k].detach(), atol=2e-6), (k, (p[k].cpu().double() - ref[k].detach()).abs().max())
+        assert torch.allclose(best[k].cpu().double(), want_best[k], atol=2e-6), k
