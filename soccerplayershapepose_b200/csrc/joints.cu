@@ -41,10 +41,7 @@ __device__ __forceinline__ void load_slot_s(float (&a)[AELEMS], const float* A_s
 __device__ __forceinline__ void quartet_sync(int tl) { asm volatile("bar.sync %0, 128;" ::"r"(1 + tl) : "memory"); }
 
 // A virtual tile (32 q-groups) is shared by four warps, eight q-groups each: the per-warp instruction chain is what
-// bounds these kernels (they move ~10 KB per body), so four short chains instead of one long one.  A CTA takes the
-// tile pairs blockIdx.y, blockIdx.y + gridDim.y, ... of its body group: one pair per CTA while that still fits one
-// wave, otherwise as many CTAs as are resident at once, so that a large batch does not re-fetch the group's
-// transforms for every tile pair.
+// bounds these kernels (they move ~10 KB per body), so four short chains instead of one long one.
 // dynamic shared memory: A_s [24][3][32] float4 | JW partial tiles [32][pitch] | mbarrier
 __global__ void __launch_bounds__(JT, 1024 / JT)
 joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const float4* __restrict__ A_blk, int b0, int nb,
@@ -57,23 +54,28 @@ joints_fwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + AG_WORDS + JW * 32 * pitch + ((JW * 32 * pitch) & 1));
   const int g = blockIdx.x;
   if (threadIdx.x == 0) fetch_group_transforms(A_s, reinterpret_cast<const float*>(A_blk), g, bar);
-  float tx = 0.f, ty = 0.f, tz = 0.f;
-  if (qt == 0 && transl != nullptr && g * 32 + lane < nb) {
-    const float* t = transl + (size_t)(b0 + g * 32 + lane) * 3;
-    tx = t[0]; ty = t[1]; tz = t[2];
+  const int tv = blockIdx.y * JTL + tl;
+  const bool on = tv < m.ntv;                                // uniform over the tile's four warps
+  float q[24];
+  uint32_t mt_l = 0;
+  float c_l = 0.f;
+  int ncols = 0;
+  if (on) {
+    load_q24(q, vpB + ((size_t)g * nc4 + (m.ntiles + tv) * 24 + qt * 6) * 32 + lane);
+    mt_l = __ldg(m.qmeta + tv * 32 + qt * 8 + (lane & 7));   // lane i holds the plan of q-group qt * 8 + (i & 7)
+    c_l = __ldg(m.qcoef + tv * 32 + qt * 8 + (lane & 7));
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    if (qt == 0 && transl != nullptr && g * 32 + lane < nb) {
+      const float* t = transl + (size_t)(b0 + g * 32 + lane) * 3;
+      tx = t[0]; ty = t[1]; tz = t[2];
+    }
+    // every output joint of the tile starts at the translation (first warp) and accumulates its terms in the lane's row
+    ncols = m.vt_nj[tv] * 3;
+    for (int c = 0; c < ncols; c += 3) { my_row[c] = tx; my_row[c + 1] = ty; my_row[c + 2] = tz; }
   }
   __syncthreads();                                           // barrier init visible to every waiter
-  bool first = true;
-  for (int tv = blockIdx.y * JTL + tl; tv < m.ntv; tv += gridDim.y * JTL) {   // uniform over the tile's four warps
-    float q[24];
-    load_q24(q, vpB + ((size_t)g * nc4 + (m.ntiles + tv) * 24 + qt * 6) * 32 + lane);
-    const uint32_t mt_l = __ldg(m.qmeta + tv * 32 + qt * 8 + (lane & 7));   // lane i holds the plan of q-group qt * 8 + (i & 7)
-    const float c_l = __ldg(m.qcoef + tv * 32 + qt * 8 + (lane & 7));
-    // every output joint of the tile starts at the translation (first warp) and accumulates its terms in the lane's row
-    const int ncols = m.vt_nj[tv] * 3;
-    if (!first) quartet_sync(tl);                            // the last tile's flush has read the partial rows
-    for (int c = 0; c < ncols; c += 3) { my_row[c] = tx; my_row[c + 1] = ty; my_row[c + 2] = tz; }
-    if (first) { mbar_wait(bar, 0); first = false; }
+  if (on) {
+    mbar_wait(bar, 0);
     float a[AELEMS];
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii) {
@@ -118,17 +120,17 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + AG_WORDS + JTL * 32 * pitch + ((JTL * 32 * pitch) & 1));
   const int g = blockIdx.x;
   if (threadIdx.x == 0) fetch_group_transforms(A_s, reinterpret_cast<const float*>(A_blk), g, bar);
-  __syncthreads();                                           // barrier init visible to every waiter
-  float* dA_g = dA_acc + (size_t)g * AG_WORDS;
-  float sx = 0.f, sy = 0.f, sz = 0.f;
-  bool first = true;
-  for (int tv = blockIdx.y * JTL + tl; tv < m.ntv; tv += gridDim.y * JTL) {   // uniform over the tile's four warps
-    float q[24];
+  const int tv = blockIdx.y * JTL + tl;
+  const bool on = tv < m.ntv;                                // uniform over the tile's four warps
+  float q[24];
+  uint32_t mt_l = 0;
+  float c_l = 0.f;
+  int ncols = 0;
+  if (on) {
     load_q24(q, vpB + ((size_t)g * nc4 + (m.ntiles + tv) * 24 + qt * 6) * 32 + lane);
-    const uint32_t mt_l = __ldg(m.qmeta + tv * 32 + qt * 8 + (lane & 7));
-    const float c_l = __ldg(m.qcoef + tv * 32 + qt * 8 + (lane & 7));
-    const int ncols = m.vt_nj[tv] * 3;
-    if (!first) quartet_sync(tl);                            // everyone is done with the last tile's gradients
+    mt_l = __ldg(m.qmeta + tv * 32 + qt * 8 + (lane & 7));
+    c_l = __ldg(m.qcoef + tv * 32 + qt * 8 + (lane & 7));
+    ncols = m.vt_nj[tv] * 3;
     {  // stage the gradients of this tile's joints (3 nj floats of each body row): 8 rows per warp, 4 lanes per row
       const int r = qt * 8 + (lane >> 2);
       const bool live = g * 32 + r < nb;
@@ -143,10 +145,19 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
           if (c0 + u * 4 < ncols) trow[c0 + u * 4] = v[u];
       }
     }
-    quartet_sync(tl);
-    if (first) { mbar_wait(bar, 0); first = false; }
-    if (qt == 0)                                             // dL/dtransl: every output joint of the tile once
+  }
+  __syncthreads();                                           // barrier init visible; every tile staged
+  if (on) {
+    mbar_wait(bar, 0);
+    if (qt == 0) {                                           // dL/dtransl: every output joint of the tile once
+      float sx = 0.f, sy = 0.f, sz = 0.f;
       for (int c = 0; c < ncols; c += 3) { sx += my_row[c]; sy += my_row[c + 1]; sz += my_row[c + 2]; }
+      float* dtr_g = dtr_acc + (size_t)g * 96;
+      red_add(dtr_g + lane, sx);
+      red_add(dtr_g + 32 + lane, sy);
+      red_add(dtr_g + 64 + lane, sz);
+    }
+    float* dA_g = dA_acc + (size_t)g * AG_WORDS;
     float a[AELEMS], d[AELEMS], dq[24];
 #pragma unroll
     for (int e = 0; e < AELEMS; ++e) d[e] = 0.f;
@@ -186,12 +197,6 @@ joints_bwd_kernel(DevModel m, const float4* __restrict__ vpB, int nc4, const flo
     }
     if (__shfl_sync(0xffffffffu, mt_l, 0) & (1u << 14)) flush_slot_g(d, dA_g, jcur, lane);   // not for a quarter of padding
   }
-  if (qt == 0 && !first) {
-    float* dtr_g = dtr_acc + (size_t)g * 96;
-    red_add(dtr_g + lane, sx);
-    red_add(dtr_g + 32 + lane, sy);
-    red_add(dtr_g + 64 + lane, sz);
-  }
   pdl_wait();                 // as in the forward: complete only after lbs_bwd (the gradient GEMM behind needs both)
 }
 
@@ -226,19 +231,8 @@ joint_grad_total_kernel(const float* __restrict__ joints, const float* __restric
   if (gcam != nullptr && threadIdx.x < 3) gcam[b * 3 + threadIdx.x] = sh[threadIdx.x][0] + sh[threadIdx.x][1] + sh[threadIdx.x][2] + sh[threadIdx.x][3];
 }
 
-// CTAs per body group: one per JTL virtual tiles (four warps each) while the grid stays within one wave of
-// `per_sm` resident CTAs per SM, else as many as are resident at once (they loop over their tile pairs)
-static int joints_split(int ntv, int groups, int per_sm) {
-  static const int num_sms = [] {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-  }();
-  static const bool loop = [] { const char* e = getenv("B200_JOINTS_LOOP"); return !(e && e[0] == '0'); }();
-  const int all = std::max(1, (ntv + JTL - 1) / JTL);
-  if (!loop) return all;
-  return std::max(1, std::min(all, (num_sms * per_sm + groups - 1) / groups));
-}
+// CTAs per body group: JTL virtual tiles per CTA, four warps each
+static int joints_split(int ntv) { return std::max(1, (ntv + JTL - 1) / JTL); }
 static size_t joints_smem(int ntiles_s, int pitch) { return (size_t)(AG_WORDS + ntiles_s * 32 * pitch + 1) * 4 + 16; }
 
 // after_lbs: the previous kernel in the stream is the skinning kernel of the same slab -> PDL launch (overlaps its tail)
@@ -250,7 +244,7 @@ int launch_joints_fwd(const DevModel& m, const float* vpB, int S, const float* A
   const size_t smem = joints_smem(JW, pitch);
   B200_SMEM_ATTR_ONCE(joints_fwd_kernel, smem);
   LaunchTimer _timer("joints_fwd", st);
-  B200_CUDA_TRY(launch_k(joints_fwd_kernel, dim3(groups, joints_split(m.ntv, groups, 1024 / JT)), dim3(JT), smem, st, after_lbs, m,
+  B200_CUDA_TRY(launch_k(joints_fwd_kernel, dim3(groups, joints_split(m.ntv)), dim3(JT), smem, st, after_lbs, m,
                          reinterpret_cast<const float4*>(vpB), m.n_pad / 4, reinterpret_cast<const float4*>(A_blk), b0, nb, pitch,
                          transl, joints));
   B200_LAUNCH_CHECK("joints_fwd");
@@ -267,7 +261,7 @@ int launch_joints_bwd(const DevModel& m, const float* vpB, int S, int Sw, const 
   const size_t smem = joints_smem(JTL, pitch);
   B200_SMEM_ATTR_ONCE(joints_bwd_kernel, smem);
   LaunchTimer _timer("joints_bwd", st);
-  B200_CUDA_TRY(launch_k(joints_bwd_kernel, dim3(groups, joints_split(m.ntv, groups, 768 / JT)), dim3(JT), smem, st, after_lbs, m,
+  B200_CUDA_TRY(launch_k(joints_bwd_kernel, dim3(groups, joints_split(m.ntv)), dim3(JT), smem, st, after_lbs, m,
                          reinterpret_cast<const float4*>(vpB), m.n_pad / 4, reinterpret_cast<const float4*>(A_blk), b0, nb, pitch,
                          dJ, dvp_hi, dvp_lo, dA_acc, dtr_acc));
   B200_LAUNCH_CHECK("joints_bwd");
