@@ -283,7 +283,7 @@ int b200smpl_model_debug_array(const b200smpl_model* m, const char* name, const 
   RET("Wf", h.Wf) RET("Wb_hi", h.Wb_hi) RET("Wb_lo", h.Wb_lo) RET("W32", h.W32) RET("vmeta", h.vmeta)
   RET("vwts", h.vwts) RET("term_ptr", h.term_ptr) RET("term_joint", h.term_joint) RET("term_qrow", h.term_qrow)
   RET("term_c", h.term_c) RET("Jt", h.Jt) RET("Jsd", h.Jsd) RET("qmeta", h.qmeta) RET("qcoef", h.qcoef)
-  RET("vt_j0", h.vt_j0) RET("vt_nj", h.vt_nj)
+  RET("vt_j0", h.vt_j0) RET("vt_nj", h.vt_nj) RET("chain_order", h.chain_order) RET("chain_level_ptr", h.chain_level_ptr)
 #undef RET
   return fail(B200SMPL_ERR_INVALID, "unknown debug array: " + n);
 }

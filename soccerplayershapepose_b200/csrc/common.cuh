@@ -122,6 +122,7 @@ struct HostArrays {
   std::vector<float> vwts;     // 4 per vertex
   std::vector<uint32_t> vplan; // 40 words per 8 vertices
   std::vector<int32_t> term_ptr, term_qrow, vt_j0, vt_nj;
+  std::vector<int8_t> chain_order, chain_level_ptr;   // copies of ChainTables::order / level_ptr (debug / tests)
   std::vector<uint32_t> qmeta;
   std::vector<float> qcoef;
   std::vector<uint8_t> term_joint;

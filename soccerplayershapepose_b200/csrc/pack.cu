@@ -354,6 +354,8 @@ int pack_model(const b200smpl_model_desc* d, HostArrays& h, DevModel& dm, std::s
   dm.V = V; dm.ntiles = ntiles; dm.n_real = 3 * V; dm.nq = nq; dm.n_virt0 = n_virt0; dm.n_rows = n_rows;
   dm.n_pad = n_pad; dm.njout = NJ + nvj + nreg; dm.nterms = h.term_ptr.back();
   dm.fl = fl; dm.chain = ch;
+  h.chain_order.assign(ch.order, ch.order + NJ);
+  h.chain_level_ptr.assign(ch.level_ptr, ch.level_ptr + NJ + 1);
   return 0;
 }
 

@@ -57,6 +57,29 @@ def test_model_validation_errors(synthetic_model):
         SMPLEngine(bad, device=None)
 
 
+def test_chain_level_tables(host_engine, synthetic_model):
+    """The pose kernels walk the kinematic tree one level at a time (csrc/pose.cu, P3): `chain_order` must list every
+    joint once, sorted by depth, every parent on an earlier level than its child; `chain_level_ptr` delimits the
+    levels (smplx kintree: 24 joints, 9 levels)."""
+    parents = np.asarray(synthetic_model["parents"]).astype(int)
+    depth = np.zeros(24, int)
+    for j in range(1, 24):
+        depth[j] = depth[parents[j]] + 1
+    order = host_engine.debug_array("chain_order", np.int8).astype(int)
+    ptr = host_engine.debug_array("chain_level_ptr", np.int8).astype(int)
+    assert sorted(order.tolist()) == list(range(24))
+    assert ptr[0] == 0 and ptr[-1] == 24 and np.all(np.diff(ptr) >= 0)
+    nlev = depth.max() + 1
+    assert nlev == 9
+    for d in range(nlev):
+        level = order[ptr[d]:ptr[d + 1]]
+        assert len(level) > 0 and np.all(depth[level] == d)
+        assert np.all(np.diff(level) > 0)                        # stable: joints of a level in index order
+    assert np.all(ptr[nlev:] == 24)
+    level_of = {int(j): int(depth[j]) for j in order}
+    assert all(level_of[int(parents[j])] == level_of[j] - 1 for j in range(1, 24))
+
+
 def _bf16_to_f32(u16):
     return (u16.astype(np.uint32) << 16).view(np.float32)
 

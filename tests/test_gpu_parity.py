@@ -368,6 +368,42 @@ def test_forward_full_size_vs_oracle(engine, oracle64, dev, mode):
         assert ev < POS_TOL[mode] and ej < POS_TOL[mode]
 
 
+@pytest.mark.parametrize("tree", ["chain", "bushy"])
+@pytest.mark.parametrize("axis_angle", [False, True])
+def test_other_kinematic_trees(synthetic_model, dev, tree, axis_angle):
+    """The pose kernels walk the tree level by level (csrc/pose.cu P3, ChainTables::order / level_ptr): a 24-joint
+    chain (24 levels of one joint) and a tree where joints have up to four children (4 levels), forward and backward
+    against the fp64 oracle."""
+    model = dict(synthetic_model)
+    if tree == "chain":
+        parents = np.arange(-1, 23)
+    else:
+        parents = np.array([-1, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5, 5, 5, 5, 9, 9])
+    model["parents"] = parents.astype(np.asarray(synthetic_model["parents"]).dtype)
+    eng = SMPLEngine(model, dev)
+    orc = O.SMPLOracle(model, dtype=torch.float64)
+    B = 37
+    betas, pose_aa, trans, cam = make_inputs(B, 77)
+    pose_aa = pose_aa * 0.5                                   # a 24-deep chain compounds the rotations
+    pose = pose_aa if axis_angle else rotmats_of(pose_aa)
+    g = torch.Generator().manual_seed(78)
+    dV, dJ, dJ2 = torch.randn(B, 6890, 3, generator=g), torch.randn(B, 90, 3, generator=g), torch.randn(B, 90, 2, generator=g)
+    d = lambda x: x.to(dev)  # noqa: E731
+    m = _lib.MODES["fp32"]
+    out = eng.forward(d(betas), d(pose), d(trans), d(cam), axis_angle=axis_angle, mode=m, save=True)
+    ref = orc.forward_flat(betas.double(), pose.double(), trans.double(), pose2rot=axis_angle)
+    scale = max(1.0, ref.vertices.abs().max().item())
+    assert (out[0].cpu().double() - ref.vertices).abs().max().item() < POS_TOL["fp32"] * scale
+    assert (out[1].cpu().double() - ref.joints).abs().max().item() < POS_TOL["fp32"] * scale
+    rb, rp, rt, rc = _oracle_grads(orc, betas, pose, trans, cam, dV, dJ, dJ2, axis_angle)
+    for saved in (out[3], None):
+        gb, gp, gt, gc = eng.backward(d(betas), d(pose), d(trans), d(cam), out[1], d(dV), d(dJ), d(dJ2),
+                                      axis_angle=axis_angle, mode=m, saved=saved)
+        errs = (_rel(gb.cpu().double(), rb), _rel(gp.cpu().double().reshape(rp.shape), rp), _rel(gt.cpu().double(), rt),
+                _rel(gc.cpu().double(), rc))
+        assert max(errs) < GRAD_TOL["fp32"], errs
+
+
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_wide_statistics_model_parity(wide_model, dev, mode):
     """The 'wide' synthetic model (H36M / COCO-plus regressor rows over 6-10 mesh parts -> twice the virtual joint
