@@ -99,8 +99,14 @@ __global__ void fit_adam_kernel(float* __restrict__ p, const float* __restrict__
                                 float beta2, float eps) {
   const long long n = (long long)batch * P;
   const int t = step[1];
-  const float bc1 = 1.f - powf(beta1, (float)t), bc2 = 1.f - powf(beta2, (float)t);
-  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  __shared__ float coef[2];
+  if (threadIdx.x == 0) {                                    // once per CTA: two powf cost more than the update itself
+    const float bc1 = 1.f - powf(beta1, (float)t), bc2 = 1.f - powf(beta2, (float)t);
+    coef[0] = lr / bc1;
+    coef[1] = rsqrtf(bc2);
+  }
+  __syncthreads();
+  const float step_size = coef[0], inv_sqrt_bc2 = coef[1];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / P), c = (int)(i - (long long)b * P);
     const float x = p[i];
@@ -182,6 +188,7 @@ fit_update_kernel(FitGroups G, int bpc, const float* __restrict__ loss, float* _
                   int32_t* __restrict__ best_iter, float* __restrict__ first_loss, int32_t* __restrict__ step, int parity,
                   int batch, float lr, float beta1, float beta2, float eps) {
   __shared__ uint8_t imp[FIT_MAX_BPC];
+  __shared__ float coef[2];
   const int b0 = blockIdx.x * bpc;
   const int nel = bpc * G.ptot;
   FitElem e0;
@@ -200,9 +207,13 @@ fit_update_kernel(FitGroups G, int bpc, const float* __restrict__ loss, float* _
     }
     imp[threadIdx.x] = im ? 1 : 0;
   }
+  if (threadIdx.x == FIT_THREADS - 1) {                      // the bias corrections once per CTA (two powf are ~300
+    const float bc1 = 1.f - powf(beta1, (float)t), bc2 = 1.f - powf(beta2, (float)t);   // instructions: per thread they were
+    coef[0] = lr / bc1;                                      // two thirds of the kernel's instruction count)
+    coef[1] = rsqrtf(bc2);
+  }
   __syncthreads();
-  const float bc1 = 1.f - powf(beta1, (float)t), bc2 = 1.f - powf(beta2, (float)t);
-  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  const float step_size = coef[0], inv_sqrt_bc2 = coef[1];
   if ((int)threadIdx.x < nel) fit_elem_store(e0, G, imp, beta1, beta2, step_size, inv_sqrt_bc2, eps);
   for (int idx = threadIdx.x + FIT_THREADS; idx < nel; idx += FIT_THREADS) {   // rows longer than the CTA
     FitElem e;
